@@ -1,0 +1,568 @@
+// hevcdl.cu -- C-ABI implementation (include/hevcdl.h) over the sm_100a kernels.
+// Host side: frame slots, pinned staging, one compute stream + one D2H stream, CUDA events.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cnn_fp32.cuh"
+#include "cnn_tc.cuh"
+#include "common.cuh"
+#include "rmd.cuh"
+
+using namespace hevcdl;
+
+namespace {
+
+enum SlotState { SLOT_FREE = 0, SLOT_QUEUED = 1, SLOT_DONE = 2 };
+
+struct Slot {
+  int frame = -1;
+  SlotState state = SLOT_FREE;
+  // device
+  uint8_t *dY = nullptr, *dU = nullptr, *dV = nullptr;
+  uint8_t *dLabels = nullptr;
+  float *dLogits = nullptr;
+  int *dCtuOff = nullptr;
+  hevcdl_pu *dPus = nullptr;
+  uint32_t *dSatd = nullptr;
+  uint8_t *dCand = nullptr;
+  // pinned host
+  uint8_t *hPlanes = nullptr;          // staging Y|U|V (pitched like the device planes)
+  uint8_t *hLabels = nullptr;
+  float *hLogits = nullptr;
+  int *hCtuOff = nullptr;
+  hevcdl_pu *hPus = nullptr;
+  uint32_t *hSatd = nullptr;
+  uint8_t *hCand = nullptr;
+  size_t hPuCap = 0;
+  bool pusFetched = false;
+  cudaEvent_t evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
+};
+
+}  // namespace
+
+struct hevcdl_ctx {
+  hevcdl_cfg cfg{};
+  FrameGeom geo{};
+  int pitch = 0, cpitch = 0;           // device plane pitches (bytes)
+  size_t puCap = 0;
+  cudaStream_t stream = nullptr, d2h = nullptr;
+  std::vector<Slot> slots;
+  float *dWeights = nullptr;           // raw HDLW blob
+  float *dPacked = nullptr;            // fp32-path packed weights
+  Fp32Params fp{};
+  TcParams tc{};
+  void *dTcBlob = nullptr;
+  int numSMs = 0;
+  std::string err;
+  hevcdl_stats_t stats{};
+  // scratch for hevcdl_rmd_exact
+  void *dExact = nullptr;
+  size_t exactCap = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      char b_[512];                                                                         \
+      snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = b_;                                                                        \
+      return HEVCDL_E_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+Slot *find_slot(hevcdl_ctx *ctx, int frame) {
+  for (auto &s : ctx->slots)
+    if (s.state != SLOT_FREE && s.frame == frame) return &s;
+  return nullptr;
+}
+
+// [COUT][CIN][K][K] -> [COUT/CG][CIN][K*K][CG]
+void pack_conv(const float *w, int cout, int cin, int kk, int cg, float *out) {
+  for (int co = 0; co < cout; co++)
+    for (int ci = 0; ci < cin; ci++)
+      for (int k = 0; k < kk; k++)
+        out[(((size_t)(co / cg) * cin + ci) * kk + k) * cg + co % cg] = w[((size_t)co * cin + ci) * kk + k];
+}
+void transpose(const float *w, int rows, int cols, float *out) {  // [rows][cols] -> [cols][rows]
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) out[(size_t)c * rows + r] = w[(size_t)r * cols + c];
+}
+
+int load_weights(hevcdl_ctx *ctx) {
+  FILE *f = fopen(ctx->cfg.weights_path, "rb");
+  if (!f) { ctx->err = std::string("cannot open weights: ") + ctx->cfg.weights_path; return HEVCDL_E_WEIGHTS; }
+  char magic[8];
+  std::vector<float> w(HDLW_NFLOATS);
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "HDLW0001", 8) == 0 &&
+            fread(w.data(), sizeof(float), HDLW_NFLOATS, f) == (size_t)HDLW_NFLOATS;
+  char extra;
+  ok = ok && fread(&extra, 1, 1, f) == 0;
+  fclose(f);
+  if (!ok) { ctx->err = "malformed HDLW weight blob"; return HEVCDL_E_WEIGHTS; }
+
+  // fp32 path: packed convs + transposed fcs + the small vectors, one device allocation
+  std::vector<float> pk;
+  auto push = [&](size_t n) { size_t o = pk.size(); pk.resize(o + n); return o; };
+  size_t o_c1 = push(16 * 3 * 25), o_c64 = push(16 * 3 * 25), o_c2 = push(64 * 32 * 9), o_c3 = push(128 * 64 * 9);
+  size_t o_f1 = push(2048 * 256), o_f2 = push(256 * 64), o_f3 = push(64 * 16);
+  pack_conv(&w[O_C1W], 16, 3, 25, 4, &pk[o_c1]);
+  pack_conv(&w[O_C64W], 16, 3, 25, 1, &pk[o_c64]);
+  pack_conv(&w[O_C2W], 64, 32, 9, 4, &pk[o_c2]);
+  pack_conv(&w[O_C3W], 128, 64, 9, 4, &pk[o_c3]);
+  transpose(&w[O_F1W], 256, 2048, &pk[o_f1]);
+  transpose(&w[O_F2W], 64, 256, &pk[o_f2]);
+  transpose(&w[O_F3W], 16, 64, &pk[o_f3]);
+  CK(cudaMalloc(&ctx->dWeights, HDLW_NFLOATS * sizeof(float)));
+  CK(cudaMemcpy(ctx->dWeights, w.data(), HDLW_NFLOATS * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&ctx->dPacked, pk.size() * sizeof(float)));
+  CK(cudaMemcpy(ctx->dPacked, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const float *W = ctx->dWeights, *P = ctx->dPacked;
+  Fp32Params &p = ctx->fp;
+  p.c1w = P + o_c1; p.c64w = P + o_c64; p.c2w = P + o_c2; p.c3w = P + o_c3;
+  p.c1b = W + O_C1B; p.c64b = W + O_C64B; p.c2b = W + O_C2B; p.c3b = W + O_C3B;
+  p.g1 = W + O_BN1G; p.b1 = W + O_BN1B; p.g64 = W + O_BN64G; p.b64 = W + O_BN64B;
+  p.g2 = W + O_BN2G; p.b2 = W + O_BN2B; p.g3 = W + O_BN3G; p.b3 = W + O_BN3B;
+  p.f1wT = P + o_f1; p.f1b = W + O_F1B; p.f2wT = P + o_f2; p.f2b = W + O_F2B; p.f3wT = P + o_f3; p.f3b = W + O_F3B;
+  int rc = tc_prepare_weights(w.data(), ctx->dWeights, &ctx->tc, &ctx->dTcBlob, ctx->err);
+  return rc;
+}
+
+int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
+  const FrameGeom &g = ctx->geo;
+  const size_t ybytes = (size_t)ctx->pitch * g.H, cbytes = (size_t)ctx->cpitch * (g.H / 2);
+  CK(cudaMalloc(&s.dY, ybytes + 2 * cbytes));
+  CK(cudaMemset(s.dY, 0, ybytes + 2 * cbytes));
+  s.dU = s.dY + ybytes; s.dV = s.dU + cbytes;
+  CK(cudaMalloc(&s.dLabels, (size_t)g.nctu * 16));
+  CK(cudaMalloc(&s.dLogits, (size_t)g.nctu * 64 * sizeof(float)));
+  CK(cudaMalloc(&s.dCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
+  CK(cudaMemset(s.dCtuOff, 0, ((size_t)g.nctu + 1) * sizeof(int)));
+  CK(cudaMalloc(&s.dPus, ctx->puCap * sizeof(hevcdl_pu)));
+  CK(cudaMalloc(&s.dSatd, ctx->puCap * 35 * sizeof(uint32_t)));
+  CK(cudaMalloc(&s.dCand, ctx->puCap * 8));
+  CK(cudaMallocHost(&s.hPlanes, ybytes + 2 * cbytes));
+  CK(cudaMallocHost(&s.hLabels, (size_t)g.nctu * 16));
+  CK(cudaMallocHost(&s.hLogits, (size_t)g.nctu * 64 * sizeof(float)));
+  CK(cudaMallocHost(&s.hCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
+  CK(cudaEventCreateWithFlags(&s.evLabels, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s.evRmd, cudaEventDisableTiming));
+  CK(cudaEventCreate(&s.evT0)); CK(cudaEventCreate(&s.evT1)); CK(cudaEventCreate(&s.evT2));
+  return HEVCDL_OK;
+}
+
+int ensure_host_pu_cap(hevcdl_ctx *ctx, Slot &s, size_t n) {
+  if (n <= s.hPuCap) return HEVCDL_OK;
+  size_t cap = s.hPuCap ? s.hPuCap : 4096;
+  while (cap < n) cap *= 2;
+  if (s.hPus) cudaFreeHost(s.hPus);
+  if (s.hSatd) cudaFreeHost(s.hSatd);
+  if (s.hCand) cudaFreeHost(s.hCand);
+  s.hPus = nullptr; s.hSatd = nullptr; s.hCand = nullptr; s.hPuCap = 0;
+  CK(cudaMallocHost(&s.hPus, cap * sizeof(hevcdl_pu)));
+  CK(cudaMallocHost(&s.hSatd, cap * 35 * sizeof(uint32_t)));
+  CK(cudaMallocHost(&s.hCand, cap * 8));
+  s.hPuCap = cap;
+  return HEVCDL_OK;
+}
+
+// Queue the device pipeline of one slot on ctx->stream.  Returns kernels launched.
+int launch_pipeline(hevcdl_ctx *ctx, Slot &s, bool timed) {
+  const FrameGeom g = ctx->geo;
+  FrameGeom gd = g;
+  int launches = 0;
+  if (timed) cudaEventRecord(s.evT0, ctx->stream);
+  if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
+    launches += tc_launch(ctx->tc, s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, s.dLabels,
+                          s.dLogits, ctx->numSMs, ctx->stream);
+  } else {
+    const int grid = g.nctu < 4 * ctx->numSMs ? g.nctu : 4 * ctx->numSMs;
+    k_cnn_fp32<<<grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream>>>(s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch,
+                                                                    ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits);
+    launches++;
+  }
+  if (timed) cudaEventRecord(s.evT1, ctx->stream);
+  if (ctx->cfg.rmd) {
+    k_enum_pus<<<1, 1024, 0, ctx->stream>>>(s.dLabels, gd, s.dCtuOff, s.dPus);
+    const int grid = g.nctu < 8 * ctx->numSMs ? g.nctu : 8 * ctx->numSMs;
+    k_rmd_batched<<<grid, RMD_THREADS, sizeof(RmdSmem), ctx->stream>>>(s.dY, gd, ctx->pitch, s.dCtuOff, s.dPus, s.dSatd,
+                                                                      s.dCand);
+    launches += 2;
+  }
+  if (timed) cudaEventRecord(s.evT2, ctx->stream);
+  return launches;
+}
+
+template <class T>
+int submit_impl(hevcdl_ctx *ctx, int frame, const T *y, int sy, const T *u, const T *v, int sc) {
+  if (!ctx || !y || !u || !v || sy < ctx->geo.W || sc < ctx->geo.W / 2) return HEVCDL_E_INVAL;
+  if (find_slot(ctx, frame)) { ctx->err = "frame id already in flight"; return HEVCDL_E_INVAL; }
+  Slot *s = nullptr;
+  for (auto &c : ctx->slots) if (c.state == SLOT_FREE) { s = &c; break; }
+  if (!s) return HEVCDL_E_BUSY;
+  const FrameGeom &g = ctx->geo;
+  const int W = g.W, H = g.H, P = ctx->pitch, CP = ctx->cpitch;
+  uint8_t *hy = s->hPlanes, *hu = hy + (size_t)P * H, *hv = hu + (size_t)CP * (H / 2);
+  const uint8_t *src_y = nullptr;
+  bool direct = false;
+  if (sizeof(T) == 1) {  // already-pinned 8-bit planes can be copied without staging
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, y) == cudaSuccess && at.type == cudaMemoryTypeHost) direct = true;
+    else cudaGetLastError();
+    src_y = reinterpret_cast<const uint8_t *>(y);
+  }
+  if (direct) {
+    CK(cudaMemcpy2DAsync(s->dY, P, src_y, sy, W, H, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(s->dU, CP, u, sc, W / 2, H / 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(s->dV, CP, v, sc, W / 2, H / 2, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int r = 0; r < H; r++) {
+      const T *row = y + (size_t)r * sy;
+      if (sizeof(T) == 1) memcpy(hy + (size_t)r * P, row, W);
+      else for (int x = 0; x < W; x++) hy[(size_t)r * P + x] = (uint8_t)row[x];
+    }
+    for (int r = 0; r < H / 2; r++) {
+      const T *ru = u + (size_t)r * sc, *rv = v + (size_t)r * sc;
+      if (sizeof(T) == 1) { memcpy(hu + (size_t)r * CP, ru, W / 2); memcpy(hv + (size_t)r * CP, rv, W / 2); }
+      else for (int x = 0; x < W / 2; x++) { hu[(size_t)r * CP + x] = (uint8_t)ru[x]; hv[(size_t)r * CP + x] = (uint8_t)rv[x]; }
+    }
+    CK(cudaMemcpyAsync(s->dY, s->hPlanes, (size_t)P * H + 2 * (size_t)CP * (H / 2), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  s->frame = frame; s->state = SLOT_QUEUED; s->pusFetched = false;
+  ctx->stats.kernel_launches += launch_pipeline(ctx, *s, true);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->cfg.rmd)
+    CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(s->evLabels, ctx->stream));
+  CK(cudaEventRecord(s->evRmd, ctx->stream));
+  return HEVCDL_OK;
+}
+
+int finish_slot(hevcdl_ctx *ctx, Slot *s) {
+  if (s->state == SLOT_QUEUED) {
+    CK(cudaEventSynchronize(s->evLabels));
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, s->evT0, s->evT1) == cudaSuccess) ctx->stats.ms_cnn += a;
+    if (cudaEventElapsedTime(&b, s->evT1, s->evT2) == cudaSuccess) ctx->stats.ms_rmd += b;
+    s->state = SLOT_DONE;
+    ctx->stats.frames++; ctx->stats.ctus += ctx->geo.nctu;
+    if (ctx->cfg.rmd) ctx->stats.pus += s->hCtuOff[ctx->geo.nctu];
+  }
+  return HEVCDL_OK;
+}
+
+int fetch_pus(hevcdl_ctx *ctx, Slot *s) {
+  if (s->pusFetched) return HEVCDL_OK;
+  if (!ctx->cfg.rmd) { ctx->err = "context created with rmd=0"; return HEVCDL_E_INVAL; }
+  const size_t n = (size_t)s->hCtuOff[ctx->geo.nctu];
+  int rc = ensure_host_pu_cap(ctx, *s, n ? n : 1);
+  if (rc) return rc;
+  CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
+  if (n) {
+    CK(cudaMemcpyAsync(s->hPus, s->dPus, n * sizeof(hevcdl_pu), cudaMemcpyDeviceToHost, ctx->d2h));
+    CK(cudaMemcpyAsync(s->hSatd, s->dSatd, n * 35 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->d2h));
+    CK(cudaMemcpyAsync(s->hCand, s->dCand, n * 8, cudaMemcpyDeviceToHost, ctx->d2h));
+  }
+  CK(cudaStreamSynchronize(ctx->d2h));
+  s->pusFetched = true;
+  return HEVCDL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hevcdl_status_str(int st) {
+  switch (st) {
+    case HEVCDL_OK: return "ok";
+    case HEVCDL_E_INVAL: return "invalid argument";
+    case HEVCDL_E_NODEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+    case HEVCDL_E_CUDA: return "CUDA error";
+    case HEVCDL_E_WEIGHTS: return "weight blob missing or malformed";
+    case HEVCDL_E_NOFRAME: return "unknown frame";
+    case HEVCDL_E_BUSY: return "no free frame slot";
+    case HEVCDL_E_NOMEM: return "out of memory";
+  }
+  return "unknown status";
+}
+
+const char *hevcdl_last_error(const hevcdl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
+  if (!cfg || !out || cfg->abi_version != HEVCDL_ABI_VERSION || cfg->width <= 0 || cfg->height <= 0 ||
+      (cfg->width % 8) || (cfg->height % 8) || cfg->width > 8192 || cfg->height > 8192 || !cfg->weights_path ||
+      (cfg->precision != HEVCDL_PREC_FP32 && cfg->precision != HEVCDL_PREC_BF16_TC)) {
+    g_create_err = "invalid hevcdl_cfg";
+    return HEVCDL_E_INVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    g_create_err = "no CUDA device: libhevcdl has no CPU fallback";
+    return HEVCDL_E_NODEVICE;
+  }
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+    g_create_err = "device is not sm_100 (B200): kernels are built for sm_100a only";
+    return HEVCDL_E_NODEVICE;
+  }
+  hevcdl_ctx *ctx = new hevcdl_ctx();
+  ctx->cfg = *cfg;
+  ctx->cfg.slots = cfg->slots < 1 ? 1 : cfg->slots;
+  std::string wp = cfg->weights_path;
+  auto fail = [&](int rc) { g_create_err = ctx->err; hevcdl_destroy(ctx); return rc; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(HEVCDL_E_CUDA); }
+  ctx->numSMs = prop.multiProcessorCount;
+  FrameGeom &g = ctx->geo;
+  g.W = cfg->width; g.H = cfg->height;
+  g.ctu_w = (g.W + 63) / 64; g.ctu_h = (g.H + 63) / 64; g.nctu = g.ctu_w * g.ctu_h;
+  ctx->pitch = ((g.W + 127) / 128) * 128; ctx->cpitch = ctx->pitch / 2;
+  ctx->puCap = (size_t)g.nctu * MAX_PU_CTU;
+  int rc;
+  ctx->cfg.weights_path = wp.c_str();
+  auto cu = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); return true; }
+    return false;
+  };
+  if (cu(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
+  if (cu(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
+  if ((rc = load_weights(ctx))) return fail(rc);
+  ctx->cfg.weights_path = nullptr;
+  if (cu(cudaFuncSetAttribute(k_cnn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_BYTES), "smem attr") ||
+      cu(cudaFuncSetAttribute(k_rmd_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RmdSmem)), "smem attr"))
+    return fail(HEVCDL_E_CUDA);
+  if ((rc = tc_configure(ctx->err))) return fail(rc);
+  ctx->slots.resize(ctx->cfg.slots);
+  for (auto &s : ctx->slots)
+    if ((rc = alloc_slot(ctx, s))) return fail(rc);
+  *out = ctx;
+  return HEVCDL_OK;
+}
+
+void hevcdl_destroy(hevcdl_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+  for (auto &s : ctx->slots) {
+    cudaFree(s.dY); cudaFree(s.dLabels); cudaFree(s.dLogits); cudaFree(s.dCtuOff);
+    cudaFree(s.dPus); cudaFree(s.dSatd); cudaFree(s.dCand);
+    cudaFreeHost(s.hPlanes); cudaFreeHost(s.hLabels); cudaFreeHost(s.hLogits); cudaFreeHost(s.hCtuOff);
+    cudaFreeHost(s.hPus); cudaFreeHost(s.hSatd); cudaFreeHost(s.hCand);
+    if (s.evLabels) cudaEventDestroy(s.evLabels);
+    if (s.evRmd) cudaEventDestroy(s.evRmd);
+    if (s.evT0) cudaEventDestroy(s.evT0);
+    if (s.evT1) cudaEventDestroy(s.evT1);
+    if (s.evT2) cudaEventDestroy(s.evT2);
+  }
+  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dTcBlob); cudaFree(ctx->dExact);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+  cudaGetLastError();
+  delete ctx;
+}
+
+int hevcdl_submit_frame_u8(hevcdl_ctx *ctx, int frame, const uint8_t *y, int sy, const uint8_t *u, const uint8_t *v, int sc) {
+  if (ctx) cudaSetDevice(ctx->cfg.device);
+  return submit_impl<uint8_t>(ctx, frame, y, sy, u, v, sc);
+}
+int hevcdl_submit_frame_pel16(hevcdl_ctx *ctx, int frame, const int16_t *y, int sy, const int16_t *u, const int16_t *v, int sc) {
+  if (ctx) cudaSetDevice(ctx->cfg.device);
+  return submit_impl<int16_t>(ctx, frame, y, sy, u, v, sc);
+}
+
+int hevcdl_wait_frame(hevcdl_ctx *ctx, int frame) {
+  if (!ctx) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  return finish_slot(ctx, s);
+}
+
+int hevcdl_ctu_labels(hevcdl_ctx *ctx, int frame, int addr, uint8_t out[16]) {
+  if (!ctx || !out || addr < 0 || addr >= ctx->geo.nctu) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  memcpy(out, s->hLabels + (size_t)addr * 16, 16);
+  return HEVCDL_OK;
+}
+
+int hevcdl_frame_labels(hevcdl_ctx *ctx, int frame, uint8_t *labels, float *logits) {
+  if (!ctx) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  if (labels) memcpy(labels, s->hLabels, (size_t)ctx->geo.nctu * 16);
+  if (logits) memcpy(logits, s->hLogits, (size_t)ctx->geo.nctu * 64 * sizeof(float));
+  return HEVCDL_OK;
+}
+
+int hevcdl_frame_pu_count(hevcdl_ctx *ctx, int frame, int *npu) {
+  if (!ctx || !npu) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  if (!ctx->cfg.rmd) { ctx->err = "context created with rmd=0"; return HEVCDL_E_INVAL; }
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  *npu = s->hCtuOff[ctx->geo.nctu];
+  return HEVCDL_OK;
+}
+
+int hevcdl_frame_pus(hevcdl_ctx *ctx, int frame, hevcdl_pu *pus, uint32_t *satd, uint8_t *cand) {
+  if (!ctx) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  if ((rc = fetch_pus(ctx, s))) return rc;
+  const size_t n = (size_t)s->hCtuOff[ctx->geo.nctu];
+  if (pus) memcpy(pus, s->hPus, n * sizeof(hevcdl_pu));
+  if (satd) memcpy(satd, s->hSatd, n * 35 * sizeof(uint32_t));
+  if (cand) memcpy(cand, s->hCand, n * 8);
+  return HEVCDL_OK;
+}
+
+int hevcdl_ctu_pu_range(hevcdl_ctx *ctx, int frame, int addr, int *first, int *count) {
+  if (!ctx || !first || !count || addr < 0 || addr >= ctx->geo.nctu) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  if (!ctx->cfg.rmd) { ctx->err = "context created with rmd=0"; return HEVCDL_E_INVAL; }
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  *first = s->hCtuOff[addr];
+  *count = s->hCtuOff[addr + 1] - s->hCtuOff[addr];
+  return HEVCDL_OK;
+}
+
+int hevcdl_release_frame(hevcdl_ctx *ctx, int frame) {
+  if (!ctx) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  if (s->state == SLOT_QUEUED) {
+    int rc = finish_slot(ctx, s);
+    if (rc) return rc;
+  }
+  CK(cudaEventSynchronize(s->evRmd));
+  s->state = SLOT_FREE; s->frame = -1;
+  return HEVCDL_OK;
+}
+
+int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t *org, const int16_t *lines,
+                     const uint32_t *bits, const int8_t *mpm, const uint8_t *mpm_add, double sqrt_lambda,
+                     uint32_t *satd, uint8_t *cand, uint8_t *ncand) {
+  if (!ctx || n < 0 || (n && (!sizes || !org || !lines))) return HEVCDL_E_INVAL;
+  if (n == 0) return HEVCDL_OK;
+  cudaSetDevice(ctx->cfg.device);
+  std::vector<int> org_off(n + 1), line_off(n + 1);
+  org_off[0] = line_off[0] = 0;
+  for (int i = 0; i < n; i++) {
+    const int s = sizes[i];
+    if (s != 4 && s != 8 && s != 16 && s != 32 && s != 64) { ctx->err = "PU size must be 4,8,16,32,64"; return HEVCDL_E_INVAL; }
+    org_off[i + 1] = org_off[i] + s * s;
+    line_off[i + 1] = line_off[i] + 4 * s + 1;
+  }
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_sizes = al(n), b_org = al(org_off[n]), b_ooff = al((size_t)n * 4), b_lines = al((size_t)line_off[n] * 2),
+               b_loff = al((size_t)n * 4), b_bits = al((size_t)n * 35 * 4), b_mpm = al((size_t)n * 3), b_madd = al(n),
+               b_satd = al((size_t)n * 35 * 4), b_cand = al((size_t)n * 10), b_nc = al(n);
+  const size_t total = b_sizes + b_org + b_ooff + b_lines + b_loff + b_bits + b_mpm + b_madd + b_satd + b_cand + b_nc;
+  if (total > ctx->exactCap) {
+    cudaFree(ctx->dExact); ctx->dExact = nullptr; ctx->exactCap = 0;
+    CK(cudaMalloc(&ctx->dExact, total));
+    ctx->exactCap = total;
+  }
+  uint8_t *p = (uint8_t *)ctx->dExact;
+  uint8_t *d_sizes = p; p += b_sizes;
+  uint8_t *d_org = p; p += b_org;
+  int *d_ooff = (int *)p; p += b_ooff;
+  int16_t *d_lines = (int16_t *)p; p += b_lines;
+  int *d_loff = (int *)p; p += b_loff;
+  uint32_t *d_bits = (uint32_t *)p; p += b_bits;
+  int8_t *d_mpm = (int8_t *)p; p += b_mpm;
+  uint8_t *d_madd = p; p += b_madd;
+  uint32_t *d_satd = (uint32_t *)p; p += b_satd;
+  uint8_t *d_cand = p; p += b_cand;
+  uint8_t *d_nc = p;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(d_sizes, sizes, n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_org, org, org_off[n], cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ooff, org_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_lines, lines, (size_t)line_off[n] * 2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_loff, line_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  if (bits) CK(cudaMemcpyAsync(d_bits, bits, (size_t)n * 35 * 4, cudaMemcpyHostToDevice, st));
+  if (mpm) CK(cudaMemcpyAsync(d_mpm, mpm, (size_t)n * 3, cudaMemcpyHostToDevice, st));
+  if (mpm_add) CK(cudaMemcpyAsync(d_madd, mpm_add, n, cudaMemcpyHostToDevice, st));
+  const int grid = n < 16 * ctx->numSMs ? n : 16 * ctx->numSMs;
+  k_rmd_exact<<<grid, 128, 0, st>>>(n, d_sizes, d_org, d_ooff, d_lines, d_loff, bits ? d_bits : nullptr,
+                                    mpm ? d_mpm : nullptr, mpm_add ? d_madd : nullptr, sqrt_lambda, d_satd, d_cand, d_nc);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  if (satd) CK(cudaMemcpyAsync(satd, d_satd, (size_t)n * 35 * 4, cudaMemcpyDeviceToHost, st));
+  if (cand) CK(cudaMemcpyAsync(cand, d_cand, (size_t)n * 10, cudaMemcpyDeviceToHost, st));
+  if (ncand) CK(cudaMemcpyAsync(ncand, d_nc, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return HEVCDL_OK;
+}
+
+int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int iters, float ms[3], int *launches) {
+  if (!ctx || !frames || nframes <= 0 || iters <= 0 || !ms) return HEVCDL_E_INVAL;
+  cudaSetDevice(ctx->cfg.device);
+  std::vector<Slot *> sl(nframes);
+  for (int i = 0; i < nframes; i++) {
+    sl[i] = find_slot(ctx, frames[i]);
+    if (!sl[i]) return HEVCDL_E_NOFRAME;
+    int rc = finish_slot(ctx, sl[i]);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  int nl = 0;
+  // pass 1: whole pipeline, one pair of events around all iterations
+  CK(cudaEventRecord(e0, ctx->stream));
+  for (int it = 0; it < iters; it++) nl += launch_pipeline(ctx, *sl[it % nframes], false);
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&ms[0], e0, e1));
+  // pass 2: same work with per-stage events (stage split; not used for the headline)
+  double cnn = 0, rmd = 0;
+  for (int it = 0; it < iters; it++) {
+    Slot &s = *sl[it % nframes];
+    nl += launch_pipeline(ctx, s, true);
+    CK(cudaEventSynchronize(s.evT2));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, s.evT0, s.evT1));
+    CK(cudaEventElapsedTime(&b, s.evT1, s.evT2));
+    cnn += a; rmd += b;
+  }
+  ms[1] = (float)cnn; ms[2] = (float)rmd;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (launches) *launches = nl / 2;
+  ctx->stats.kernel_launches += nl;
+  return HEVCDL_OK;
+}
+
+int hevcdl_get_stats(hevcdl_ctx *ctx, hevcdl_stats_t *out) {
+  if (!ctx || !out) return HEVCDL_E_INVAL;
+  *out = ctx->stats;
+  return HEVCDL_OK;
+}
+
+void *hevcdl_stream(hevcdl_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+}  // extern "C"

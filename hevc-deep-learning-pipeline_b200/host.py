@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference sidecar over the C-ABI (include/hevcdl.h).
+
+The reference's depth-prediction interface is two scripts coupled to the encoder by files:
+gen_frames.py (frame dump) and use_model.py (per-CTU labels written to ./pred/<frame>/ctu<i>.txt,
+use_model.py:73-127).  `DepthPredictor` exposes the same operations -- predict the 16 labels of
+every CTU of a frame, optionally write the reference's text files -- backed by libhevcdl.so.
+There is no CPU path: constructing a DepthPredictor without the CUDA library or a B200 raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libhevcdl.so")
+DEFAULT_WEIGHTS = os.path.join(os.path.dirname(_HERE), "weights", "hevc_encoder_model.hdlw")
+
+PREC_FP32, PREC_BF16_TC = 0, 1
+
+EXPORTS = [
+    "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
+    "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
+    "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
+    "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_get_stats", "hevcdl_stream",
+]
+
+
+class Cfg(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("slots", C.c_int32), ("precision", C.c_int32), ("rmd", C.c_int32), ("boundary_fix", C.c_int32),
+                ("weights_path", C.c_char_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("ctus", C.c_uint64), ("pus", C.c_uint64), ("ms_cnn", C.c_double),
+                ("ms_rmd", C.c_double), ("kernel_launches", C.c_uint64)]
+
+
+PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("part", "u1"), ("ctu", "<u2")])
+
+
+class HevcdlError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libhevcdl.so (built in-tree by __graft_entry__.build()); fail loudly if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HevcdlError("libhevcdl.so not built (%s): run __graft_entry__.build(); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, ip = C.c_void_p, C.c_int
+    L.hevcdl_create.argtypes = [C.POINTER(Cfg), C.POINTER(vp)]
+    L.hevcdl_destroy.argtypes = [vp]
+    L.hevcdl_destroy.restype = None
+    L.hevcdl_last_error.argtypes = [vp]
+    L.hevcdl_last_error.restype = C.c_char_p
+    L.hevcdl_status_str.argtypes = [ip]
+    L.hevcdl_status_str.restype = C.c_char_p
+    L.hevcdl_submit_frame_u8.argtypes = [vp, ip, vp, ip, vp, vp, ip]
+    L.hevcdl_submit_frame_pel16.argtypes = [vp, ip, vp, ip, vp, vp, ip]
+    L.hevcdl_wait_frame.argtypes = [vp, ip]
+    L.hevcdl_ctu_labels.argtypes = [vp, ip, ip, vp]
+    L.hevcdl_frame_labels.argtypes = [vp, ip, vp, vp]
+    L.hevcdl_frame_pu_count.argtypes = [vp, ip, C.POINTER(ip)]
+    L.hevcdl_frame_pus.argtypes = [vp, ip, vp, vp, vp]
+    L.hevcdl_ctu_pu_range.argtypes = [vp, ip, ip, C.POINTER(ip), C.POINTER(ip)]
+    L.hevcdl_release_frame.argtypes = [vp, ip]
+    L.hevcdl_rmd_exact.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp]
+    L.hevcdl_bench_resident.argtypes = [vp, vp, ip, ip, C.POINTER(C.c_float), C.POINTER(ip)]
+    L.hevcdl_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.hevcdl_stream.argtypes = [vp]
+    L.hevcdl_stream.restype = vp
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class DepthPredictor:
+    """One context per GPU (device = LOCAL_RANK).  Frames are independent (all-intra,
+    encoder_intra_main.cfg:20-22), so ranks shard frames f -> rank f % world with no exchange."""
+
+    def __init__(self, width, height, device=0, slots=2, precision=PREC_FP32, rmd=True, boundary_fix=False,
+                 weights=DEFAULT_WEIGHTS):
+        self.lib = load_library()
+        self.width, self.height = int(width), int(height)
+        self.ctu_w, self.ctu_h = (self.width + 63) // 64, (self.height + 63) // 64
+        self.nctu = self.ctu_w * self.ctu_h
+        self.rmd = bool(rmd)
+        cfg = Cfg(1, device, self.width, self.height, slots, precision, int(rmd), int(boundary_fix),
+                  os.fsencode(weights))
+        h = C.c_void_p()
+        rc = self.lib.hevcdl_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise HevcdlError("hevcdl_create: %s (%s)" % (self.lib.hevcdl_status_str(rc).decode(),
+                                                          self.lib.hevcdl_last_error(None).decode()))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hevcdl_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise HevcdlError("%s: %s (%s)" % (what, self.lib.hevcdl_status_str(rc).decode(),
+                                               self.lib.hevcdl_last_error(self.h).decode()))
+
+    # -- frame pipeline ---------------------------------------------------------------------
+    def submit(self, frame, Y, U, V):
+        """Queue one 8-bit 4:2:0 picture (uint8 planes, or int16 'Pel' planes as HM holds them)."""
+        assert Y.shape == (self.height, self.width) and U.shape == (self.height // 2, self.width // 2)
+        if Y.dtype == np.int16:
+            fn, esz = self.lib.hevcdl_submit_frame_pel16, 2
+        else:
+            assert Y.dtype == np.uint8
+            fn, esz = self.lib.hevcdl_submit_frame_u8, 1
+        assert Y.strides[1] == esz and U.strides[1] == esz and V.strides == U.strides
+        self._ck(fn(self.h, frame, _ptr(Y), Y.strides[0] // esz, _ptr(U), _ptr(V), U.strides[0] // esz), "submit_frame")
+
+    def wait(self, frame):
+        self._ck(self.lib.hevcdl_wait_frame(self.h, frame), "wait_frame")
+
+    def labels(self, frame, want_logits=False):
+        lab = np.empty((self.nctu, 16), np.uint8)
+        lg = np.empty((self.nctu, 4, 16), np.float32) if want_logits else None
+        self._ck(self.lib.hevcdl_frame_labels(self.h, frame, _ptr(lab), _ptr(lg)), "frame_labels")
+        return (lab, lg) if want_logits else lab
+
+    def ctu_labels(self, frame, addr):
+        out = np.empty(16, np.uint8)
+        self._ck(self.lib.hevcdl_ctu_labels(self.h, frame, addr, _ptr(out)), "ctu_labels")
+        return out
+
+    def pus(self, frame):
+        n = C.c_int()
+        self._ck(self.lib.hevcdl_frame_pu_count(self.h, frame, C.byref(n)), "frame_pu_count")
+        pus = np.empty(n.value, PU_DTYPE)
+        satd = np.empty((n.value, 35), np.uint32)
+        cand = np.empty((n.value, 8), np.uint8)
+        self._ck(self.lib.hevcdl_frame_pus(self.h, frame, _ptr(pus), _ptr(satd), _ptr(cand)), "frame_pus")
+        return pus, satd, cand
+
+    def ctu_pu_range(self, frame, addr):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.lib.hevcdl_ctu_pu_range(self.h, frame, addr, C.byref(a), C.byref(b)), "ctu_pu_range")
+        return a.value, b.value
+
+    def release(self, frame):
+        self._ck(self.lib.hevcdl_release_frame(self.h, frame), "release_frame")
+
+    def predict_frame(self, Y, U, V, frame=0, want_logits=False):
+        """use_model.py's per-frame loop (:74-127) in one call: labels [nctu,16] in CTU raster order."""
+        self.submit(frame, Y, U, V)
+        out = self.labels(frame, want_logits)
+        self.release(frame)
+        return out
+
+    def write_pred_files(self, labels, pred_dir, frame):
+        """Emit the reference's handshake files (use_model.py:121-125: '<d> ' x16, no newline) so an
+        UNMODIFIED TAppEncoder can consume labels computed here."""
+        d = os.path.join(pred_dir, str(frame))
+        os.makedirs(d, exist_ok=True)
+        for i, l in enumerate(labels):
+            with open(os.path.join(d, "ctu.txt"), "w") as f:
+                f.write("".join("%d " % v for v in l))
+            os.rename(os.path.join(d, "ctu.txt"), os.path.join(d, "ctu%d.txt" % i))
+
+    # -- exact RMD ---------------------------------------------------------------------------
+    def rmd_exact(self, sizes, org_blocks, lines, bits=None, mpm=None, mpm_add=None, sqrt_lambda=0.0):
+        """sizes [n] u8; org_blocks: list of (s,s) u8; lines: list of (4s+1,) i16; bits [n,35] u32;
+        mpm [n,3] i8; mpm_add [n] u8.  Returns satd [n,35], cand [n,10], ncand [n]."""
+        n = len(sizes)
+        sizes = np.ascontiguousarray(sizes, np.uint8)
+        org = np.ascontiguousarray(np.concatenate([np.asarray(b, np.uint8).ravel() for b in org_blocks]))
+        ln = np.ascontiguousarray(np.concatenate([np.asarray(l, np.int16).ravel() for l in lines]))
+        bits = None if bits is None else np.ascontiguousarray(bits, np.uint32)
+        mpm = None if mpm is None else np.ascontiguousarray(mpm, np.int8)
+        mpm_add = None if mpm_add is None else np.ascontiguousarray(mpm_add, np.uint8)
+        satd = np.empty((n, 35), np.uint32)
+        cand = np.empty((n, 10), np.uint8)
+        ncand = np.empty(n, np.uint8)
+        self._ck(self.lib.hevcdl_rmd_exact(self.h, n, _ptr(sizes), _ptr(org), _ptr(ln), _ptr(bits), _ptr(mpm),
+                                           _ptr(mpm_add), float(sqrt_lambda), _ptr(satd), _ptr(cand), _ptr(ncand)),
+                 "rmd_exact")
+        return satd, cand, ncand
+
+    # -- measurement -------------------------------------------------------------------------
+    def bench_resident(self, frames, iters):
+        fr = np.ascontiguousarray(frames, np.int32)
+        ms = (C.c_float * 3)()
+        nl = C.c_int()
+        self._ck(self.lib.hevcdl_bench_resident(self.h, _ptr(fr), len(fr), iters, ms, C.byref(nl)), "bench_resident")
+        return list(ms), nl.value
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.hevcdl_get_stats(self.h, C.byref(s)), "get_stats")
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def frame_to_rank(frame, world_size):
+    """All-intra frames shard one-frame-per-GPU: frame f -> rank f mod G."""
+    return frame % world_size
+
+
+def rank_frames(n_frames, rank, world_size):
+    return [f for f in range(n_frames) if frame_to_rank(f, world_size) == rank]

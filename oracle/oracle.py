@@ -1,0 +1,171 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes loader for oracle/liboracle.so (cnn_oracle.c + rmd_oracle.c).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build():
+    """Compile the C restatement (gcc, seconds)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c")]
+    if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so] + srcs + ["-lm"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.oracle_hdlw_nfloats.restype = C.c_int
+        L.oracle_stage_ctu_rgb.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.oracle_convnet2_forward.argtypes = [f32p, u8p, u8p, f32p]
+        L.oracle_ctu_labels.argtypes = [f32p, u8p, C.c_void_p]
+        L.oracle_frame_labels.argtypes = [f32p, u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p,
+                                          C.c_void_p, C.c_void_p]
+        L.oracle_build_ref_line.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i16p]
+        L.oracle_filter_ref_line.argtypes = [i16p, C.c_int, i16p]
+        L.oracle_mode_uses_filter.argtypes = [C.c_int, C.c_int]
+        L.oracle_mode_uses_filter.restype = C.c_int
+        L.oracle_predict.argtypes = [i16p, C.c_int, C.c_int, i16p]
+        L.oracle_satd.argtypes = [u8p, C.c_int, i16p, C.c_int]
+        L.oracle_satd.restype = C.c_uint32
+        L.oracle_pu_satd35.argtypes = [C.c_void_p, C.c_int, i16p, C.c_int, u32p]
+        L.oracle_cand_list.argtypes = [u32p, u32p, C.c_double, C.c_int, i32p, C.c_int, u8p, C.c_void_p]
+        L.oracle_cand_list.restype = C.c_int
+        L.oracle_mpm.argtypes = [C.c_int, C.c_int, i32p]
+        L.oracle_mpm.restype = C.c_int
+        L.oracle_enum_ctu_pus.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+        L.oracle_enum_ctu_pus.restype = C.c_int
+        L.oracle_frame_rmd.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int, i32p, u32p]
+        L.oracle_frame_rmd.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def load_weights(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"HDLW0001", "bad weight blob"
+    w = np.frombuffer(raw, dtype="<f4", offset=8).astype(np.float32).copy()
+    assert w.size == lib().oracle_hdlw_nfloats()
+    return w
+
+
+def stage_ctu_rgb(Y, U, V, ctu_x, ctu_y):
+    H, W = Y.shape
+    out = np.zeros((3, 64, 64), np.uint8)
+    lib().oracle_stage_ctu_rgb(np.ascontiguousarray(Y), np.ascontiguousarray(U), np.ascontiguousarray(V),
+                               W, H, ctu_x, ctu_y, out)
+    return out
+
+
+def convnet2_forward(w, x32, x64):
+    out = np.zeros(16, np.float32)
+    lib().oracle_convnet2_forward(w, np.ascontiguousarray(x32), np.ascontiguousarray(x64), out)
+    return out
+
+
+def ctu_labels(logits4):
+    lab = np.zeros(16, np.uint8)
+    mar = np.zeros(16, np.float32)
+    lib().oracle_ctu_labels(np.ascontiguousarray(logits4, np.float32), lab, mar.ctypes.data)
+    return lab, mar
+
+
+def frame_labels(w, Y, U, V, ctu_begin=0, ctu_end=None, want_logits=False):
+    H, W = Y.shape
+    nctu = ((W + 63) // 64) * ((H + 63) // 64)
+    if ctu_end is None:
+        ctu_end = nctu
+    labels = np.zeros((nctu, 16), np.uint8)
+    logits = np.zeros((nctu, 4, 16), np.float32)
+    margins = np.zeros((nctu, 16), np.float32)
+    lib().oracle_frame_labels(w, np.ascontiguousarray(Y), np.ascontiguousarray(U), np.ascontiguousarray(V),
+                              W, H, ctu_begin, ctu_end, labels, logits.ctypes.data, margins.ctypes.data)
+    if want_logits:
+        return labels, logits, margins
+    return labels
+
+
+def build_ref_line(pic, x0, y0, n):
+    H, W = pic.shape
+    line = np.zeros(4 * n + 1, np.int16)
+    lib().oracle_build_ref_line(np.ascontiguousarray(pic), W, W, H, x0, y0, n, line)
+    return line
+
+
+def filter_ref_line(line, n):
+    out = np.zeros_like(line)
+    lib().oracle_filter_ref_line(np.ascontiguousarray(line), n, out)
+    return out
+
+
+def predict(line, n, mode):
+    out = np.zeros((n, n), np.int16)
+    lib().oracle_predict(np.ascontiguousarray(line), n, mode, out)
+    return out
+
+
+def pu_satd35(org_pic, x0, y0, n, line):
+    """org_pic: full uint8 picture; PU at (x0,y0)."""
+    H, W = org_pic.shape
+    org_pic = np.ascontiguousarray(org_pic)
+    out = np.zeros(35, np.uint32)
+    lib().oracle_pu_satd35(C.c_void_p(int(org_pic.ctypes.data) + int(y0) * int(W) + int(x0)), W, np.ascontiguousarray(line), n, out)
+    return out
+
+
+def block_satd35(org_block, line):
+    n = org_block.shape[0]
+    blk = np.ascontiguousarray(org_block, np.uint8)
+    out = np.zeros(35, np.uint32)
+    lib().oracle_pu_satd35(C.c_void_p(int(blk.ctypes.data)), n, np.ascontiguousarray(line), n, out)
+    return out
+
+
+def cand_list(satd, bits, sqrt_lambda, n, mpm, n_mpm_add):
+    modes = np.zeros(10, np.uint8)
+    k = lib().oracle_cand_list(np.ascontiguousarray(satd, np.uint32), np.ascontiguousarray(bits, np.uint32),
+                               float(sqrt_lambda), n, np.ascontiguousarray(mpm, np.int32), n_mpm_add, modes, None)
+    return modes[:k].copy()
+
+
+def mpm(left, above):
+    m = np.zeros(3, np.int32)
+    k = lib().oracle_mpm(left, above, m)
+    return m, k
+
+
+def enum_ctu_pus(label16, ctu_x, ctu_y, W, H):
+    pu = np.zeros((340, 4), np.int32)
+    k = lib().oracle_enum_ctu_pus(np.ascontiguousarray(label16, np.uint8), ctu_x, ctu_y, W, H, pu)
+    return pu[:k].copy()
+
+
+def frame_rmd(pic, labels, ctu_begin=0, ctu_end=None):
+    H, W = pic.shape
+    nctu = ((W + 63) // 64) * ((H + 63) // 64)
+    if ctu_end is None:
+        ctu_end = nctu
+    cap = (ctu_end - ctu_begin) * 320
+    pu = np.zeros((cap, 4), np.int32)
+    satd = np.zeros((cap, 35), np.uint32)
+    k = lib().oracle_frame_rmd(np.ascontiguousarray(pic), W, H, np.ascontiguousarray(labels, np.uint8),
+                               ctu_begin, ctu_end, pu, satd)
+    return pu[:k].copy(), satd[:k].copy()

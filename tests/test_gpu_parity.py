@@ -1,0 +1,222 @@
+"""Parity of the CUDA path (called through the C-ABI) with the oracle and with the reference's own
+golden vectors.  Run on the GPU box: pytest -m gpu."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+# label parity is demanded wherever the oracle's argmax margin exceeds eps (logit units)
+EPS = {0: 1e-3, 1: 0.25}
+
+
+def _precisions(host):
+    return [host.PREC_FP32, host.PREC_BF16_TC]
+
+
+def _mk(host, w, h, prec, **kw):
+    try:
+        return host.DepthPredictor(w, h, precision=prec, **kw)
+    except host.HevcdlError as e:
+        if prec == host.PREC_BF16_TC and "tensor-core" in str(e):
+            pytest.skip("bf16 tensor-core path not built")
+        raise
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_labels_vs_unmodified_use_model_golden(built, host, prec):
+    g = np.load(os.path.join(GOLDEN, "cnn_labels_416x240.npz"))
+    dp = _mk(host, 416, 240, prec, rmd=False)
+    lab = dp.predict_frame(g["Y"], g["U"], g["V"])
+    if prec == 0:
+        assert (lab == g["labels"]).all()
+    else:
+        assert (lab != g["labels"]).mean() < 0.02
+    dp.close()
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_logits_and_labels_vs_oracle_1080p(built, host, oracle, weights, pkg, prec):
+    Y, U, V = pkg.synth.synth_frame(1920, 1080, 0)
+    dp = _mk(host, 1920, 1080, prec, rmd=False)
+    lab, lg = dp.predict_frame(Y, U, V, want_logits=True)
+    dp.close()
+    # oracle on a bounded sample of CTUs (3 rows incl. the partial bottom row) -- seconds on CPU
+    rows = (0, 8, 16)
+    for r in rows:
+        a, b = r * 30, r * 30 + 30
+        olab, olg, mar = oracle.frame_labels(weights, Y, U, V, a, b, want_logits=True)
+        d = np.abs(lg[a:b] - olg[a:b]).max()
+        assert d < (2e-3 if prec == 0 else 1.0), d
+        bad = (lab[a:b] != olab[a:b]) & (mar[a:b] > EPS[prec])
+        assert not bad.any(), (r, int(bad.sum()))
+
+
+@pytest.mark.parametrize("kind", ["noise", "flat"])
+def test_edge_content(built, host, oracle, weights, pkg, kind):
+    Y, U, V = pkg.synth.synth_frame(128, 64, 1, kind)
+    dp = _mk(host, 128, 64, 0, rmd=True)
+    dp.submit(5, Y, U, V)
+    lab, lg = dp.labels(5, want_logits=True)
+    pus, satd, cand = dp.pus(5)
+    dp.release(5)
+    dp.close()
+    olab, olg, mar = oracle.frame_labels(weights, Y, U, V, want_logits=True)
+    assert not ((lab != olab) & (mar > EPS[0])).any()
+    opu, osatd = oracle.frame_rmd(Y, lab)
+    assert len(opu) == len(pus) and (osatd == satd).all()
+
+
+def test_batched_rmd_bit_exact_vs_oracle(built, host, oracle, pkg):
+    """K6 on the original picture == oracle on the same picture and labels: PU list, 35 SATDs,
+    SATD-ranked candidates (ties -> lower mode)."""
+    Y, U, V = pkg.synth.synth_frame(416, 240, 2)
+    dp = _mk(host, 416, 240, 0, rmd=True)
+    dp.submit(0, Y, U, V)
+    lab = dp.labels(0)
+    pus, satd, cand = dp.pus(0)
+    opu, osatd = oracle.frame_rmd(Y, lab)
+    assert len(pus) == len(opu) > 0
+    assert (pus["x"] == opu[:, 0]).all() and (pus["y"] == opu[:, 1]).all() and (pus["size"] == opu[:, 2]).all()
+    assert (pus["part"] == opu[:, 3]).all()
+    assert (satd == osatd).all()
+    for i in range(0, len(pus), 7):
+        keep = 3 if pus["size"][i] >= 16 else 8
+        ref = oracle.cand_list(osatd[i], np.zeros(35, np.uint32), 0.0, int(pus["size"][i]), np.zeros(3, np.int32), 0)
+        assert (cand[i, :keep] == ref[:keep]).all()
+    # per-CTU ranges are consistent with the PU list
+    for a in (0, 13, 27):
+        f, c = dp.ctu_pu_range(0, a)
+        assert (pus["ctu"][f:f + c] == a).all()
+        assert (lab[a] == dp.ctu_labels(0, a)).all()
+    dp.release(0)
+    dp.close()
+
+
+def test_exact_rmd_vs_reference_trace(built, host, oracle):
+    """K6's exact entry point fed the reference's reconstruction and mode bits reproduces the
+    reference encoder's own printed SADs and uiRdModeList (first N entries) bit-exactly."""
+    g = np.load(os.path.join(GOLDEN, "rmd_trace_192x128_qp32.npz"))
+    Y, rec = g["Y"], g["rec"]
+    H, W = Y.shape
+    sizes, orgs, lines, idx = [], [], [], []
+    k = 0
+    for a, lab in enumerate(g["labels"]):
+        for (x, y, n, part) in oracle.enum_ctu_pus(lab, a % (W // 64), a // (W // 64), W, H):
+            if part <= 1:
+                sizes.append(n); orgs.append(Y[y:y + n, x:x + n]); lines.append(oracle.build_ref_line(rec, x, y, n)); idx.append(k)
+            k += 1
+    idx = np.array(idx)
+    dp = _mk(host, 192, 128, 0, rmd=False)
+    sl = math.sqrt(0.57 * 2 ** ((int(g["qp"]) - 12) / 3.0))
+    satd, cand, ncand = dp.rmd_exact(sizes, orgs, lines, bits=g["bits"][idx], sqrt_lambda=sl)
+    dp.close()
+    assert (satd == g["sad"][idx]).all()
+    for j, i in enumerate(idx):
+        keep = 3 if sizes[j] >= 16 else 8
+        assert (cand[j, :keep] == g["cand"][i, :keep]).all(), (j, i)
+        assert ncand[j] == keep
+
+
+def test_exact_rmd_mpm_append_and_random_blocks(built, host, oracle):
+    rng = np.random.default_rng(3)
+    sizes, orgs, lines, bits, mpms, adds = [], [], [], [], [], []
+    for n in (4, 8, 16, 32, 64) * 6:
+        sizes.append(n)
+        orgs.append(rng.integers(0, 256, (n, n), dtype=np.uint8))
+        base = rng.integers(0, 256)
+        lines.append(np.clip(base + rng.integers(-40, 40, 4 * n + 1), 0, 255).astype(np.int16) if rng.random() < 0.7
+                     else np.full(4 * n + 1, base, np.int16))
+        l, a = int(rng.integers(-1, 35)), int(rng.integers(-1, 35))
+        m, k = oracle.mpm(l, a)
+        b = np.full(35, 6, np.uint32); b[m[0]] = 2; b[m[1]] = 3; b[m[2]] = 3
+        bits.append(b); mpms.append(m.astype(np.int8)); adds.append(k)
+    dp = _mk(host, 64, 64, 0, rmd=False)
+    satd, cand, ncand = dp.rmd_exact(sizes, orgs, lines, bits=np.array(bits), mpm=np.array(mpms),
+                                     mpm_add=np.array(adds, np.uint8), sqrt_lambda=7.61)
+    dp.close()
+    for i, n in enumerate(sizes):
+        ref = oracle.block_satd35(orgs[i], lines[i])
+        assert (satd[i] == ref).all(), (i, n)
+        rl = oracle.cand_list(ref, bits[i], 7.61, n, mpms[i].astype(np.int32), adds[i])
+        assert ncand[i] == len(rl) and (cand[i, :len(rl)] == rl).all(), (i, n)
+
+
+def test_pel16_input_equals_u8(built, host, pkg):
+    Y, U, V = pkg.synth.synth_frame(416, 240, 4)
+    dp = _mk(host, 416, 240, 0, rmd=False, slots=2)
+    a = dp.predict_frame(Y, U, V, frame=1)
+    # HM holds Pel (int16) planes with a stride wider than the picture (margins)
+    Yp = np.zeros((240, 416 + 160), np.int16); Yp[:, 80:80 + 416] = Y
+    Up = np.zeros((120, 208 + 80), np.int16); Up[:, 40:40 + 208] = U
+    Vp = np.zeros((120, 208 + 80), np.int16); Vp[:, 40:40 + 208] = V
+    b = dp.predict_frame(Yp[:, 80:80 + 416], Up[:, 40:40 + 208], Vp[:, 40:40 + 208], frame=2)
+    dp.close()
+    assert (a == b).all()
+
+
+def test_boundary_fix_makes_partial_ctus_tile(built, host, pkg):
+    Y, U, V = pkg.synth.synth_frame(416, 240, 0)
+    ref = host.DepthPredictor(416, 240, precision=0, rmd=True, boundary_fix=False)
+    fix = host.DepthPredictor(416, 240, precision=0, rmd=True, boundary_fix=True)
+    l0 = ref.predict_frame(Y, U, V)
+    fix.submit(0, Y, U, V)
+    l1 = fix.labels(0)
+    pus, _, _ = fix.pus(0)
+    fix.release(0)
+    interior = np.array([(a % 7) < 6 and (a // 7) < 3 for a in range(28)])
+    assert (l0[interior] == l1[interior]).all()               # 416 = 6.5 CTUs, 240 = 3.75 CTUs
+    assert (l1[~interior] >= 1).all() and (l1 >= l0).all()
+    # with the fix the evaluated 2Nx2N PUs tile the whole picture exactly once
+    cover = np.zeros((240, 416), np.int32)
+    for p in pus[pus["part"] == 0]:
+        cover[p["y"]:p["y"] + p["size"], p["x"]:p["x"] + p["size"]] += 1
+    assert (cover == 1).all()
+    ref.close(); fix.close()
+
+
+def test_slots_busy_and_release(built, host, pkg):
+    Y, U, V = pkg.synth.synth_frame(128, 64, 0)
+    dp = _mk(host, 128, 64, 0, rmd=False, slots=2)
+    dp.submit(0, Y, U, V); dp.submit(1, Y, U, V)
+    with pytest.raises(host.HevcdlError):
+        dp.submit(2, Y, U, V)                                  # HEVCDL_E_BUSY
+    with pytest.raises(host.HevcdlError):
+        dp.labels(7)                                           # HEVCDL_E_NOFRAME
+    a = dp.labels(0); dp.release(0)
+    dp.submit(2, Y, U, V)
+    assert (dp.labels(1) == a).all() and (dp.labels(2) == a).all()
+    st = dp.stats()
+    assert st["frames"] == 3 and st["ctus"] == 6 and st["kernel_launches"] == 3
+    dp.close()
+
+
+def test_full_size_properties_4k(built, host, pkg):
+    """BASELINE full size (3840x2160): size-independent properties -- determinism, translation by
+    whole CTUs, and SATD(mode) invariants -- instead of a CPU oracle pass."""
+    Y, U, V = pkg.synth.synth_frame(3840, 2160, 0)
+    dp = _mk(host, 3840, 2160, 0, rmd=True, slots=2)
+    dp.submit(0, Y, U, V); dp.submit(1, Y, U, V)
+    l0, l1 = dp.labels(0), dp.labels(1)
+    assert (l0 == l1).all()                                    # deterministic
+    p0, s0, _ = dp.pus(0)
+    p1, s1, _ = dp.pus(1)
+    assert (s0 == s1).all() and len(p0) == len(p1)
+    # every CTU's evaluated 2Nx2N PUs cover interior CTUs exactly once (quadtree consistency)
+    inter = p0[(p0["part"] == 0)]
+    area = np.bincount(inter["ctu"], weights=inter["size"].astype(np.int64) ** 2, minlength=dp.nctu)
+    full = np.array([(a // 60) < 33 for a in range(dp.nctu)])  # 2160 = 33.75 CTU rows
+    assert (area[full] == 4096).all()
+    dp.release(0); dp.release(1)
+    # translation: the same content shifted by one CTU gives the same labels for interior CTUs
+    dp2 = _mk(host, 3840 - 64, 2160 - 64, 0, rmd=False)
+    l2 = dp2.predict_frame(np.ascontiguousarray(Y[64:, 64:]), np.ascontiguousarray(U[32:, 32:]),
+                           np.ascontiguousarray(V[32:, 32:]))
+    a = l0.reshape(34, 60, 16)[1:33, 1:59]
+    b = l2.reshape(33, 59, 16)[0:32, 0:58]
+    assert (a == b).all()
+    dp.close(); dp2.close()
