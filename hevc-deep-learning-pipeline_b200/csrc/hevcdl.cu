@@ -318,6 +318,10 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
     g_create_err = "device is not sm_100 (B200): kernels are built for sm_100a only";
     return HEVCDL_E_NODEVICE;
   }
+  if (cfg->precision == HEVCDL_PREC_BF16_TC && !TC_BUILT) {
+    g_create_err = "tensor-core (bf16 tcgen05) CNN path not built in this library";
+    return HEVCDL_E_INVAL;
+  }
   hevcdl_ctx *ctx = new hevcdl_ctx();
   ctx->cfg = *cfg;
   ctx->cfg.slots = cfg->slots < 1 ? 1 : cfg->slots;
