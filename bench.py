@@ -240,7 +240,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": ach_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
                      "frac": ach_tflops / pk["tensor"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
-                     "kernel": "k_cnn_tc" if prec else "k_cnn_fp32", "kernel_ms": ms_cnn,
+                     "kernel": "CNN stage = k_tc_l1 + k_tc_conv2 + k_tc_conv3 + k_tc_fc (tcgen05)" if prec else "k_cnn_fp32", "kernel_ms": ms_cnn,
                      "hbm_achieved_gbs": BYTES_PER_CTU * nctu / (ms_cnn / 1000.0) / 1e9, "hbm_peak_gbs": pk["hbm"],
                      "stage_ms": {"cnn": ms_cnn, "rmd": ms[2] / args.steps}},
     }
@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("HEVCDL_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("HEVCDL_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--pool", type=int, default=48)

@@ -1,15 +1,801 @@
-// cnn_tc.cuh -- tcgen05 (5th-gen tensor core) implementation of the depth-prediction CNN.
-// PLACEHOLDER until the tensor-core kernels land: HEVCDL_PREC_BF16_TC is rejected at create time.
+// cnn_tc.cuh -- tcgen05 (5th-gen tensor core, TMEM accumulators) implementation of the
+// depth-prediction CNN (use_model.py:16-58, BatchNorm in TRAINING mode per sample) for a whole
+// frame: four persistent kernels chained through L2-resident bf16 intermediates.
+//
+//   K1 k_tc_l1   : CTU staging (Y + co-sited Cb/Cr -> RGB, zero outside the picture) + conv64 and the
+//                  four per-quadrant conv1 as implicit GEMMs over 4x2-pixel "super-pixels"
+//                  (M = 128 super-pixels, N = 8 positions x 16 channels, K = 8-pixel window rows of
+//                  the (R,G) / (B,0) planes), batch-stat BN + ReLU + max-pool in the epilogue -> cat
+//   K2 k_tc_conv2: conv2 (M = 8x16 pixels, N = 64 channels, K = 9 taps x 32 channels)      -> a2
+//   K3 k_tc_conv3: conv3 (M = 128 channels, N = 256 = 4 samples x 8x8 pixels, K = 9 x 64)  -> features
+//   K4 k_tc_fc   : fc1/fc2 on tensor cores for 128 samples per CTA, fc3 + argmax + label rules
+//
+// All activations operands are read by the tensor core straight out of padded planes through
+// sliding-window shared-memory descriptors (K-major, no swizzle: 16-byte units = one pixel x 8
+// channels, LBO selects the second 8 channels / next pixels, SBO = plane row pitch) -- no im2col
+// buffer is ever materialised.  Layouts, descriptor parameters and the packed weight blob are
+// replayed on the CPU by tools/tc_emulate.py (tests/test_tc_layout_cpu.py).
 #pragma once
 #include <string>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace hevcdl {
-struct TcParams { int ready = 0; };
-inline int tc_prepare_weights(const float *, const float *, TcParams *, void **, std::string &) { return HEVCDL_OK; }
-inline int tc_configure(std::string &) { return HEVCDL_OK; }
-constexpr bool TC_BUILT = false;
-inline int tc_launch(const TcParams &, const uint8_t *, const uint8_t *, const uint8_t *, FrameGeom, int, int, int,
-                     uint8_t *, float *, int, cudaStream_t) { return 0; }
+
+constexpr bool TC_BUILT = true;
+
+// ---- packed weight blob (tools/tc_pack.py) -------------------------------------------------
+constexpr int SZ_L1W = 24 * 4096, SZ_W2 = 18 * 2048, SZ_W3 = 36 * 4096, SZ_FC1 = 32 * 32768, SZ_FC2 = 128 * 256 * 2;
+constexpr int OFF_L1W = 0, OFF_W2 = OFF_L1W + SZ_L1W, OFF_W3 = OFF_W2 + SZ_W2, OFF_FC1 = OFF_W3 + SZ_W3,
+              OFF_FC2 = OFF_FC1 + SZ_FC1, OFF_F32 = OFF_FC2 + SZ_FC2;
+constexpr int N_F32 = 32 + 32 + 128 + 256 + 256 + 64 + 1024 + 16;
+constexpr int SZ_HDLT = OFF_F32 + 4 * N_F32;
+// float offsets inside the fp32 section
+constexpr int F_G64 = 0, F_B64 = 16, F_G1 = 32, F_B1 = 48, F_G2 = 64, F_B2 = 128, F_G3 = 192, F_B3 = 320, F_F1B = 448,
+              F_F2B = 704, F_F3W = 768, F_F3B = 1792;
+
+// ---- global intermediate layouts ---------------------------------------------------------------
+constexpr int CAT_PLANE = 18 * 18 * 16, CAT_BYTES = 10 * CAT_PLANE;   // 10 planes [18][18][8 ch] bf16
+constexpr int A2_PLANE = 40 * 10 * 16, A2_BYTES = 8 * A2_PLANE;       // 8 planes [4*(y+1)+s][10][8 ch] bf16
+
+struct TcParams {
+  const uint8_t *blob = nullptr;   // device copy of the HDLT payload
+  uint8_t *cat = nullptr, *a2 = nullptr, *feats = nullptr;
+  float *logits_scratch = nullptr;
+  int npad = 0;                    // samples padded to a multiple of 128
+};
+
+constexpr int TC_THREADS = 288;    // warps 0-7: staging + epilogue, warp 8: loads + MMA issue
+#define EPI_BAR_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+
+// Sum of v[e] over the 32 lanes, for all e in [0,32): lane l returns the total of element l.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int j = 0; j < n / 2; j++) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float *y) {
+  return make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7]));
+}
+
+// ================================================================================================
+// K1: staging + conv64 + conv1
+// ================================================================================================
+constexpr int P64_PITCH = 68, P64_BYTES = 68 * 68 * 4;   // (R,G) or (B,0) bf16 pairs, 2-pixel zero halo
+constexpr int P1_PITCH = 36, P1_BYTES = 36 * 36 * 4;
+constexpr int K1_W = 0, K1_P64 = K1_W + SZ_L1W, K1_P1 = K1_P64 + 2 * P64_BYTES, K1_RED = K1_P1 + 8 * P1_BYTES,
+              K1_BAR = K1_RED + 2 * 8 * 16 * 4, K1_SMEM = K1_BAR + 64;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint8_t *__restrict__ V, FrameGeom geo, int pitch,
+        int cpitch, const uint8_t *__restrict__ blob, uint8_t *__restrict__ cat) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K1_BAR);   // [2]
+  uint64_t *bar_empty = bar_full + 2;                               // [2]
+  uint64_t *bar_w = bar_full + 4;
+  float *red = reinterpret_cast<float *>(sm + K1_RED);              // [2][8 warps][16]
+  const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_empty[0], 8); mbar_init(&bar_empty[1], 8);
+    mbar_init(bar_w, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  for (int i = tid; i < (2 * P64_BYTES + 8 * P1_BYTES) / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm + K1_P64)[i] = make_uint4(0, 0, 0, 0);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  if (warp == 8 && elect_one()) {
+    mbar_expect_tx(bar_w, SZ_L1W);
+    for (int i = 0; i < 24; i++) bulk_g2s(sm + K1_W + i * 4096, blob + OFF_L1W + i * 4096, 4096, bar_w);
+  }
+  const uint32_t idesc = idesc_bf16(128, 128);
+  uint32_t npair = 0;   // running count of tile pairs (same sequence in every role)
+
+  for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x) {
+    const int ctu_x = ctu % geo.ctu_w, ctu_y = ctu / geo.ctu_w;
+    // ---- staging: (R,G) and (B,0) planes of the CTU and of its four zero-padded quadrants ----
+    if (warp < 8) {
+      for (int it = tid; it < 1024; it += 256) {
+        const int y = it >> 4, x4 = (it & 15) * 4;
+        const int gy = ctu_y * 64 + y, gx = ctu_x * 64 + x4;
+        uint32_t yv = 0, uv = 0, vv = 0;
+        const bool in = gy < geo.H && gx < geo.W;   // W is a multiple of 8: 4 pixels are in or out together
+        if (in) {
+          yv = *reinterpret_cast<const uint32_t *>(Y + (size_t)gy * pitch + gx);
+          uv = *reinterpret_cast<const uint16_t *>(U + (size_t)(gy >> 1) * cpitch + (gx >> 1));
+          vv = *reinterpret_cast<const uint16_t *>(V + (size_t)(gy >> 1) * cpitch + (gx >> 1));
+        }
+        uint32_t rg[4], b0[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          int r = 0, g = 0, b = 0;
+          if (in) yuv2rgb((yv >> (8 * k)) & 255, (uv >> (8 * (k >> 1))) & 255, (vv >> (8 * (k >> 1))) & 255, r, g, b);
+          rg[k] = pack_bf16((float)r, (float)g);
+          b0[k] = pack_bf16((float)b, 0.f);
+        }
+        uint8_t *d64 = sm + K1_P64 + ((y + 2) * P64_PITCH + x4 + 2) * 4;
+        *reinterpret_cast<uint2 *>(d64) = make_uint2(rg[0], rg[1]);
+        *reinterpret_cast<uint2 *>(d64 + 8) = make_uint2(rg[2], rg[3]);
+        *reinterpret_cast<uint2 *>(d64 + P64_BYTES) = make_uint2(b0[0], b0[1]);
+        *reinterpret_cast<uint2 *>(d64 + P64_BYTES + 8) = make_uint2(b0[2], b0[3]);
+        const int q = (y >> 5) * 2 + (x4 >> 5);
+        uint8_t *d1 = sm + K1_P1 + q * 2 * P1_BYTES + (((y & 31) + 2) * P1_PITCH + (x4 & 31) + 2) * 4;
+        *reinterpret_cast<uint2 *>(d1) = make_uint2(rg[0], rg[1]);
+        *reinterpret_cast<uint2 *>(d1 + 8) = make_uint2(rg[2], rg[3]);
+        *reinterpret_cast<uint2 *>(d1 + P1_BYTES) = make_uint2(b0[0], b0[1]);
+        *reinterpret_cast<uint2 *>(d1 + P1_BYTES + 8) = make_uint2(b0[2], b0[3]);
+      }
+      fence_async_smem();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+      // ---- MMA issue: 4 tile pairs (conv64 quarters 0-1, 2-3; conv1 quadrants 0-1, 2-3) ----------
+      if (elect_one()) {
+        mbar_wait(bar_w, 0);
+        const uint32_t sb = smem_u32(sm);
+#pragma unroll 1
+        for (int pi = 0; pi < 4; pi++) {
+          const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
+          mbar_wait(&bar_empty[p], (use & 1) ^ 1);
+          fence_after_sync();
+          const bool c1 = pi >= 2;
+          uint32_t a0, a1, plane_stride, row_stride;
+          if (!c1) {   // quarters t = 2*pi, 2*pi+1 -> qy = pi, qx = 0 / 1
+            a0 = sb + K1_P64 + ((pi * 32) * P64_PITCH) * 4;
+            a1 = a0 + 32 * 4;
+            plane_stride = P64_BYTES; row_stride = P64_PITCH * 4;
+          } else {
+            a0 = sb + K1_P1 + ((pi - 2) * 2) * 2 * P1_BYTES;
+            a1 = a0 + 2 * P1_BYTES;
+            plane_stride = P1_BYTES; row_stride = P1_PITCH * 4;
+          }
+          const uint64_t da0 = smem_desc(a0, 16, 2 * row_stride), da1 = smem_desc(a1, 16, 2 * row_stride);
+          const uint64_t db = smem_desc(sb + K1_W + (c1 ? 12 * 4096 : 0), 128, 256);
+          const uint32_t d0 = tbase + (2 * p) * 128, d1 = d0 + 128;
+#pragma unroll
+          for (int kb = 0; kb < 12; kb++) {
+            const uint64_t aofs = (uint64_t)(((kb & 1) * plane_stride + (kb >> 1) * row_stride) >> 4);
+            const uint64_t bofs = (uint64_t)((kb * 4096) >> 4);
+            mma_bf16_ss(d0, da0 + aofs, db + bofs, idesc, kb ? 1u : 0u);
+            mma_bf16_ss(d1, da1 + aofs, db + bofs, idesc, kb ? 1u : 0u);
+          }
+          mma_commit(&bar_full[p]);
+        }
+      }
+      __syncwarp();
+    } else {
+      // ---- epilogue: warp = (lane quarter, channel half) ---------------------------------------
+      const int lq = warp & 3, h = warp >> 2;
+      const int m = lq * 32 + lane, g = m >> 3, ii = m & 7;
+      float s[8], q[8], pool64[4][8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
+      uint32_t rb = 0;
+#pragma unroll 1
+      for (int pi = 0; pi < 4; pi++) {
+        const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
+        mbar_wait(&bar_full[p], use & 1);
+        fence_after_sync();
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int t = pi * 2 + e;
+          float v[8][8];
+#pragma unroll
+          for (int pos = 0; pos < 8; pos++) tmem_ld8(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + pos * 16 + 8 * h), v[pos]);
+          tmem_ld_wait();
+          if (e == 1) {   // both accumulators of the pair are in registers: hand the TMEM slots back
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[p]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int pos = 0; pos < 8; pos++) { s[c] += v[pos][c]; q[c] = fmaf(v[pos][c], v[pos][c], q[c]); }
+          if (t < 4) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              float mx = v[0][c];
+#pragma unroll
+              for (int pos = 1; pos < 8; pos++) mx = fmaxf(mx, v[pos][c]);
+              mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));     // other row pair of the 4x4 window
+              pool64[t & 3][c] = mx;
+            }
+          }
+          const bool reduce_now = t >= 3;
+          if (reduce_now) {
+            // per-channel totals over the sample: lanes (butterfly), then the 4 warps of this half
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+                q[c] += __shfl_xor_sync(0xffffffffu, q[c], o);
+              }
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 8; c++) { red[(rb * 8 + warp) * 16 + c] = s[c]; red[(rb * 8 + warp) * 16 + 8 + c] = q[c]; }
+            }
+            EPI_BAR_SYNC();
+            const float cnt = t == 3 ? 4096.f : 1024.f;
+            const int gofs = t == 3 ? F_G64 : F_G1, bofs = t == 3 ? F_B64 : F_B1;
+            float sc[8], sh[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              double ts = 0.0, tq = 0.0;
+#pragma unroll
+              for (int k = 0; k < 4; k++) { ts += (double)red[(rb * 8 + h * 4 + k) * 16 + c]; tq += (double)red[(rb * 8 + h * 4 + k) * 16 + 8 + c]; }
+              const double mean = ts / cnt;
+              double var = tq / cnt - mean * mean;
+              var = var < 0.0 ? 0.0 : var;
+              const double inv = (double)__ldg(fp + gofs + 8 * h + c) * rsqrt(var + 1e-5 * 255.0 * 255.0);
+              sc[c] = (float)inv;
+              sh[c] = (float)((double)__ldg(fp + bofs + 8 * h + c) - mean * inv);
+            }
+            rb ^= 1;
+            uint8_t *cbase = cat + (size_t)ctu * CAT_BYTES;
+            if (t == 3) {
+              if ((g & 1) == 0) {
+#pragma unroll
+                for (int tt = 0; tt < 4; tt++) {
+                  float yv[8];
+#pragma unroll
+                  for (int c = 0; c < 8; c++) yv[c] = fmaxf(fmaf(pool64[tt][c], sc[c], sh[c]), 0.f);
+                  const int py = (tt >> 1) * 8 + (g >> 1), px = (tt & 1) * 8 + ii;
+                  *reinterpret_cast<uint4 *>(cbase + (8 + h) * CAT_PLANE + ((py + 1) * 18 + px + 1) * 16) = pack8_bf16(yv);
+                }
+              }
+            } else {
+              const int smp = t - 4;
+              float y0[8], y1[8];
+#pragma unroll
+              for (int c = 0; c < 8; c++) {
+                const float w0 = fmaxf(fmaxf(v[0][c], v[1][c]), fmaxf(v[4][c], v[5][c]));
+                const float w1 = fmaxf(fmaxf(v[2][c], v[3][c]), fmaxf(v[6][c], v[7][c]));
+                y0[c] = fmaxf(fmaf(w0, sc[c], sh[c]), 0.f);
+                y1[c] = fmaxf(fmaf(w1, sc[c], sh[c]), 0.f);
+              }
+              uint8_t *d = cbase + (smp * 2 + h) * CAT_PLANE + ((g + 1) * 18 + 2 * ii + 1) * 16;
+              *reinterpret_cast<uint4 *>(d) = pack8_bf16(y0);
+              *reinterpret_cast<uint4 *>(d + 16) = pack8_bf16(y1);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
+          }
+        }
+      }
+    }
+    npair += 4;
+    __syncthreads();   // every MMA of this CTU has completed (the epilogue saw all four commits): planes are reusable
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tbase, 512);
+}
+
+// ================================================================================================
+// K2: conv2
+// ================================================================================================
+constexpr int K2_W = 0, K2_CAT = K2_W + SZ_W2, K2_RED = K2_CAT + 2 * CAT_BYTES, K2_BAR = K2_RED + 2 * 8 * 64 * 4,
+              K2_SMEM = K2_BAR + 128;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ cat, uint8_t *__restrict__ a2) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K2_BAR);   // [4] per sample
+  uint64_t *bar_empty = bar_full + 4;                               // [4]
+  uint64_t *bar_cfull = bar_full + 8;                               // [2] cat buffer landed
+  uint64_t *bar_cfree = bar_full + 10;                              // [2] cat buffer no longer read
+  uint64_t *bar_w = bar_full + 12;
+  float *red = reinterpret_cast<float *>(sm + K2_RED);              // [2][8 warps][64]
+  const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 8); }
+    for (int i = 0; i < 2; i++) { mbar_init(&bar_cfull[i], 1); mbar_init(&bar_cfree[i], 1); }
+    mbar_init(bar_w, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t idesc = idesc_bf16(128, 64);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_w, SZ_W2);
+      for (int i = 0; i < 9; i++) bulk_g2s(sm + K2_W + i * 4096, blob + OFF_W2 + i * 4096, 4096, bar_w);
+      if ((int)blockIdx.x < geo.nctu) {
+        mbar_expect_tx(&bar_cfull[0], CAT_BYTES);
+        bulk_g2s(sm + K2_CAT, cat + (size_t)blockIdx.x * CAT_BYTES, CAT_BYTES, &bar_cfull[0]);
+      }
+      mbar_wait(bar_w, 0);
+      const uint32_t sb = smem_u32(sm);
+      uint32_t it = 0;
+      for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
+        const uint32_t b = it & 1;
+        const int next = ctu + gridDim.x;
+        if (next < geo.nctu) {   // prefetch the next CTU's planes into the other buffer
+          if (it >= 1) mbar_wait(&bar_cfree[b ^ 1], ((it - 1) >> 1) & 1);
+          mbar_expect_tx(&bar_cfull[b ^ 1], CAT_BYTES);
+          bulk_g2s(sm + K2_CAT + (b ^ 1) * CAT_BYTES, cat + (size_t)next * CAT_BYTES, CAT_BYTES, &bar_cfull[b ^ 1]);
+        }
+        mbar_wait(&bar_cfull[b], (it >> 1) & 1);
+        const uint32_t cbuf = sb + K2_CAT + b * CAT_BYTES;
+        const uint64_t db = smem_desc(sb + K2_W, 128, 256);
+        const uint64_t d64 = smem_desc(cbuf + 8 * CAT_PLANE, CAT_PLANE, 288);   // shared conv64 planes
+#pragma unroll 1
+        for (int smp = 0; smp < 4; smp++) {
+          mbar_wait(&bar_empty[smp], (it & 1) ^ 1);
+          fence_after_sync();
+          const uint64_t d1 = smem_desc(cbuf + smp * 2 * CAT_PLANE, CAT_PLANE, 288);
+          const uint32_t t0 = tbase + (2 * smp) * 64, t1 = t0 + 64;
+#pragma unroll
+          for (int tap = 0; tap < 9; tap++) {
+            const uint64_t aofs = (uint64_t)((tap / 3) * 18 + (tap % 3));   // 16-byte units
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const uint64_t da = (j ? d64 : d1) + aofs;
+              const uint64_t bofs = (uint64_t)(((tap * 2 + j) * 2048) >> 4);
+              const uint32_t acc = (tap | j) ? 1u : 0u;
+              mma_bf16_ss(t0, da, db + bofs, idesc, acc);
+              mma_bf16_ss(t1, da + 8, db + bofs, idesc, acc);     // right half: +8 pixels
+            }
+          }
+          mma_commit(&bar_full[smp]);
+        }
+        mma_commit(&bar_cfree[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lq = warp & 3, h = warp >> 2;
+    const int m = lq * 32 + lane, yy = m >> 3, xi = m & 7;
+    uint32_t it = 0, rb = 0;
+    for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
+#pragma unroll 1
+      for (int smp = 0; smp < 4; smp++) {
+        mbar_wait(&bar_full[smp], it & 1);
+        fence_after_sync();
+        float v0[32], v1[32];
+        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * smp) * 64 + 32 * h), v0);
+        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * smp + 1) * 64 + 32 * h), v1);
+        tmem_ld_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[smp]);
+        float s[32], q[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) { s[c] = v0[c] + v1[c]; q[c] = fmaf(v0[c], v0[c], v1[c] * v1[c]); }
+        const float ts = warp_transpose_sum32(s, lane), tq = warp_transpose_sum32(q, lane);
+        red[(rb * 8 + warp) * 64 + lane] = ts;
+        red[(rb * 8 + warp) * 64 + 32 + lane] = tq;
+        // 2x2 max-pool: exchange halves with the x neighbour (lane^1) then the y neighbour (lane^8);
+        // this thread ends with 8 channels of one window for each of the two tiles
+        const bool b0 = lane & 1, b3 = lane & 8;
+        float p0[16], p1[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          const float keep0 = b0 ? v0[16 + c] : v0[c], send0 = b0 ? v0[c] : v0[16 + c];
+          const float keep1 = b0 ? v1[16 + c] : v1[c], send1 = b0 ? v1[c] : v1[16 + c];
+          p0[c] = fmaxf(keep0, __shfl_xor_sync(0xffffffffu, send0, 1));
+          p1[c] = fmaxf(keep1, __shfl_xor_sync(0xffffffffu, send1, 1));
+        }
+        float w0[8], w1[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const float keep0 = b3 ? p0[8 + c] : p0[c], send0 = b3 ? p0[c] : p0[8 + c];
+          const float keep1 = b3 ? p1[8 + c] : p1[c], send1 = b3 ? p1[c] : p1[8 + c];
+          w0[c] = fmaxf(keep0, __shfl_xor_sync(0xffffffffu, send0, 8));
+          w1[c] = fmaxf(keep1, __shfl_xor_sync(0xffffffffu, send1, 8));
+        }
+        EPI_BAR_SYNC();
+        const int chunk = 4 * h + 2 * (b0 ? 1 : 0) + (b3 ? 1 : 0);   // 8 channels [8*chunk, 8*chunk+8)
+        float y0[8], y1[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int cl = (chunk & 3) * 8 + c;   // channel index inside this half's 32
+          double a = 0.0, bq = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) { a += (double)red[(rb * 8 + h * 4 + k) * 64 + cl]; bq += (double)red[(rb * 8 + h * 4 + k) * 64 + 32 + cl]; }
+          const double mean = a / 256.0;
+          double var = bq / 256.0 - mean * mean;
+          var = var < 0.0 ? 0.0 : var;
+          const double inv = (double)__ldg(fp + F_G2 + 8 * chunk + c) * rsqrt(var + 1e-5);
+          const float sc = (float)inv, sh = (float)((double)__ldg(fp + F_B2 + 8 * chunk + c) - mean * inv);
+          y0[c] = fmaxf(fmaf(w0[c], sc, sh), 0.f);
+          y1[c] = fmaxf(fmaf(w1[c], sc, sh), 0.f);
+        }
+        rb ^= 1;
+        // window (py, px): py = y/2, px = xi/2 (+4 for the right-half tile); plane row 4*(py+1)+smp, col px+1
+        uint8_t *d = a2 + (size_t)ctu * A2_BYTES + chunk * A2_PLANE + ((4 * ((yy >> 1) + 1) + smp) * 10 + (xi >> 1) + 1) * 16;
+        *reinterpret_cast<uint4 *>(d) = pack8_bf16(y0);
+        *reinterpret_cast<uint4 *>(d + 4 * 16) = pack8_bf16(y1);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tbase, 512);
+}
+
+// ================================================================================================
+// K3: conv3
+// ================================================================================================
+constexpr int K3_W = 0, K3_A2 = K3_W + SZ_W3, K3_RED = K3_A2 + A2_BYTES, K3_BAR = K3_RED + 2 * 2 * 8 * 128 * 4,
+              K3_SMEM = K3_BAR + 128;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ a2, uint8_t *__restrict__ feats, int npad) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K3_BAR);   // [2] accumulator ready
+  uint64_t *bar_empty = bar_full + 2;                               // [2]
+  uint64_t *bar_afull = bar_full + 4;                               // [4] plane pair landed
+  uint64_t *bar_afree = bar_full + 8;                               // [4] plane pair no longer read
+  uint64_t *bar_w = bar_full + 12;
+  float *red = reinterpret_cast<float *>(sm + K3_RED);              // [2][2 halves][8][128]
+  const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 8); }
+    for (int i = 0; i < 4; i++) { mbar_init(&bar_afull[i], 1); mbar_init(&bar_afree[i], 1); }
+    mbar_init(bar_w, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t idesc = idesc_bf16(128, 256);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_w, SZ_W3);
+      for (int i = 0; i < 36; i++) bulk_g2s(sm + K3_W + i * 4096, blob + OFF_W3 + i * 4096, 4096, bar_w);
+      if ((int)blockIdx.x < geo.nctu)
+        for (int j = 0; j < 4; j++) {
+          mbar_expect_tx(&bar_afull[j], 2 * A2_PLANE);
+          bulk_g2s(sm + K3_A2 + j * 2 * A2_PLANE, a2 + (size_t)blockIdx.x * A2_BYTES + j * 2 * A2_PLANE, 2 * A2_PLANE, &bar_afull[j]);
+        }
+      mbar_wait(bar_w, 0);
+      const uint32_t sb = smem_u32(sm);
+      const uint64_t dw = smem_desc(sb + K3_W, 128, 256);
+      uint32_t it = 0;
+      for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
+        const uint32_t t = it & 1;
+        mbar_wait(&bar_empty[t], ((it >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t dacc = tbase + t * 256;
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+          mbar_wait(&bar_afull[j], it & 1);
+          const uint64_t dact = smem_desc(sb + K3_A2 + j * 2 * A2_PLANE, A2_PLANE, 160);
+#pragma unroll
+          for (int tap = 0; tap < 9; tap++) {
+            const uint64_t aofs = (uint64_t)(4 * (tap / 3) * 10 + (tap % 3));   // 16-byte units
+            mma_bf16_ss(dacc, dw + (uint64_t)(((j * 9 + tap) * 4096) >> 4), dact + aofs, idesc, (j | tap) ? 1u : 0u);
+          }
+          mma_commit(&bar_afree[j]);
+        }
+        mma_commit(&bar_full[t]);
+        const int next = ctu + gridDim.x;
+        if (next < geo.nctu)
+          for (int j = 0; j < 4; j++) {   // refill each plane pair as soon as its MMAs have drained
+            mbar_wait(&bar_afree[j], it & 1);
+            mbar_expect_tx(&bar_afull[j], 2 * A2_PLANE);
+            bulk_g2s(sm + K3_A2 + j * 2 * A2_PLANE, a2 + (size_t)next * A2_BYTES + j * 2 * A2_PLANE, 2 * A2_PLANE, &bar_afull[j]);
+          }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lq = warp & 3, hy = warp >> 2;
+    const int c = lq * 32 + lane;   // output channel
+    uint32_t it = 0, rb = 0;
+    const float gam = __ldg(fp + F_G3 + c), bet = __ldg(fp + F_B3 + c);
+    for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
+      const uint32_t t = it & 1;
+      mbar_wait(&bar_full[t], (it >> 1) & 1);
+      fence_after_sync();
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+      float pooled[2][4][4];   // [py local][sample][px]
+#pragma unroll
+      for (int pr = 0; pr < 2; pr++) {   // pairs of rows y = 4*hy + 2*pr, +1
+        float r0[32], r1[32];   // columns 8*s + x of one row
+        tmem_ld32(tmem_addr(tbase, lq * 32, t * 256 + 128 * hy + 64 * pr), r0);
+        tmem_ld32(tmem_addr(tbase, lq * 32, t * 256 + 128 * hy + 64 * pr + 32), r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sx = 0; sx < 32; sx++) {
+          s[sx >> 3] += r0[sx] + r1[sx];
+          q[sx >> 3] = fmaf(r0[sx], r0[sx], fmaf(r1[sx], r1[sx], q[sx >> 3]));
+        }
+#pragma unroll
+        for (int smp = 0; smp < 4; smp++)
+#pragma unroll
+          for (int px = 0; px < 4; px++)
+            pooled[pr][smp][px] = fmaxf(fmaxf(r0[8 * smp + 2 * px], r0[8 * smp + 2 * px + 1]), fmaxf(r1[8 * smp + 2 * px], r1[8 * smp + 2 * px + 1]));
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[t]);
+      float *rr = red + ((rb * 2 + hy) * 8) * 128;
+#pragma unroll
+      for (int smp = 0; smp < 4; smp++) { rr[smp * 128 + c] = s[smp]; rr[(4 + smp) * 128 + c] = q[smp]; }
+      EPI_BAR_SYNC();
+      const float *ro = red + ((rb * 2 + (hy ^ 1)) * 8) * 128;
+      rb ^= 1;
+#pragma unroll
+      for (int smp = 0; smp < 4; smp++) {
+        const double ts = (double)s[smp] + (double)ro[smp * 128 + c], tq = (double)q[smp] + (double)ro[(4 + smp) * 128 + c];
+        const double mean = ts / 64.0;
+        double var = tq / 64.0 - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double inv = (double)gam * rsqrt(var + 1e-5);
+        const float sc = (float)inv, sh = (float)((double)bet - mean * inv);
+        float yv[8];
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++)
+#pragma unroll
+          for (int px = 0; px < 4; px++) yv[pr * 4 + px] = fmaxf(fmaf(pooled[pr][smp][px], sc, sh), 0.f);
+        // feature k = c*16 + (2*hy+pr)*4 + px -> 8 consecutive k = one 16-byte core-matrix row
+        const int n = 4 * ctu + smp, kcore = 2 * c + hy;
+        const size_t ofs = ((size_t)(kcore >> 3) * (npad >> 3) + (n >> 3)) * 1024 + (kcore & 7) * 128 + (n & 7) * 16;
+        *reinterpret_cast<uint4 *>(feats + ofs) = pack8_bf16(yv);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tbase, 512);
+}
+
+// ================================================================================================
+// K4: fc1 + fc2 (tensor cores), fc3 + argmax + label rules; one CTA = 128 samples = 32 CTUs
+// ================================================================================================
+constexpr int K4_STAGE = 32768 + 16384, K4_NSTAGE = 4;
+constexpr int K4_BAR = K4_NSTAGE * K4_STAGE, K4_SMEM = K4_BAR + 128;
+// after the fc1 K loop the stage memory is reused:
+constexpr int K4_FC2W = 0, K4_H1 = 65536, K4_H2 = 131072 /* fp32 [128][65] */, K4_F3W = K4_H2 + 128 * 65 * 4 /* [16][64] fp32 */,
+              K4_LG = K4_F3W + 4096 /* fp32 [128][16] */;
+static_assert(K4_LG + 128 * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in the stage memory");
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix,
+        uint8_t *__restrict__ labels, float *__restrict__ logits_out) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K4_BAR);   // [4]
+  uint64_t *bar_free = bar_full + 4;                                // [4]
+  uint64_t *bar_done = bar_full + 8;                                // fc1 accumulators complete
+  uint64_t *bar_w2 = bar_full + 9;                                  // fc2 weights landed
+  uint64_t *bar_done2 = bar_full + 10;
+  const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nt = blockIdx.x;   // sample tile
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_free[i], 1); }
+    mbar_init(bar_done, 1); mbar_init(bar_w2, 1); mbar_init(bar_done2, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t idesc = idesc_bf16(128, 128);
+  const uint32_t sb = smem_u32(sm);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      auto load = [&](int kc) {
+        const int st = kc & 3;
+        mbar_expect_tx(&bar_full[st], K4_STAGE);
+        bulk_g2s(sm + st * K4_STAGE, blob + OFF_FC1 + (size_t)kc * 32768, 32768, &bar_full[st]);
+        bulk_g2s(sm + st * K4_STAGE + 32768, feats + ((size_t)kc * (npad >> 3) + nt * 16) * 1024, 16384, &bar_full[st]);
+      };
+      for (int kc = 0; kc < K4_NSTAGE; kc++) load(kc);
+#pragma unroll 1
+      for (int kc = 0; kc < 32; kc++) {
+        const int st = kc & 3;
+        mbar_wait(&bar_full[st], (kc >> 2) & 1);
+        fence_after_sync();
+        const uint64_t da = smem_desc(sb + st * K4_STAGE, 128, 1024), db = smem_desc(sb + st * K4_STAGE + 32768, 128, 1024);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const uint32_t acc = (kc | t) ? 1u : 0u;
+          mma_bf16_ss(tbase, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, acc);
+          mma_bf16_ss(tbase + 128, da + (uint64_t)(1024 + t * 16), db + (uint64_t)(t * 16), idesc, acc);
+        }
+        mma_commit(&bar_free[st]);
+        if (kc >= 1 && kc - 1 + K4_NSTAGE < 32) {   // refill the stage consumed one iteration ago
+          mbar_wait(&bar_free[(kc - 1) & 3], ((kc - 1) >> 2) & 1);
+          load(kc - 1 + K4_NSTAGE);
+        }
+      }
+      mma_commit(bar_done);
+      mbar_wait(bar_done, 0);   // all stage memory is free now: bring in the fc2 weights
+      mbar_expect_tx(bar_w2, SZ_FC2);
+      for (int i = 0; i < 16; i++) bulk_g2s(sm + K4_FC2W + i * 4096, blob + OFF_FC2 + i * 4096, 4096, bar_w2);
+    }
+    __syncwarp();
+  } else {
+    // fc1 epilogue: thread = output o, 128 sample columns -> relu -> bf16 -> fc2 B operand [n][k=o]
+    const int lq = warp & 3, mh = warp >> 2;
+    const int o = mh * 128 + lq * 32 + lane;
+    const float bias = __ldg(fp + F_F1B + o);
+    mbar_wait(bar_done, 0);
+    fence_after_sync();
+    for (int f = tid; f < 16 * 64; f += 256) reinterpret_cast<float *>(sm + K4_F3W)[f] = __ldg(fp + F_F3W + f);
+#pragma unroll 1
+    for (int cb = 0; cb < 128; cb += 32) {
+      float v[32];
+      tmem_ld32(tmem_addr(tbase, lq * 32, mh * 128 + cb), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int n = cb + j;
+        const __nv_bfloat16 hv = __float2bfloat16(fmaxf(v[j] + bias, 0.f));
+        *reinterpret_cast<__nv_bfloat16 *>(sm + K4_H1 + (n >> 3) * 4096 + (o >> 3) * 128 + (n & 7) * 16 + (o & 7) * 2) = hv;
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+  }
+  __syncthreads();
+  fence_after_sync();
+  if (warp == 8) {
+    if (elect_one()) {
+      mbar_wait(bar_w2, 0);
+      const uint64_t da = smem_desc(sb + K4_FC2W, 128, 4096), db = smem_desc(sb + K4_H1, 128, 4096);
+#pragma unroll
+      for (int t = 0; t < 16; t++) mma_bf16_ss(tbase + 256, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t ? 1u : 0u);
+      mma_commit(bar_done2);
+    }
+    __syncwarp();
+  } else {
+    const int lq = warp & 3, nh = warp >> 2;   // lanes = fc2 outputs (0..63 real), nh = sample half
+    mbar_wait(bar_done2, 0);
+    fence_after_sync();
+    if (lq < 2) {
+      const int o = lq * 32 + lane;
+      const float bias = __ldg(fp + F_F2B + o);
+      float *h2 = reinterpret_cast<float *>(sm + K4_H2);
+#pragma unroll 1
+      for (int cb = 0; cb < 64; cb += 32) {
+        float v[32];
+        tmem_ld32(tmem_addr(tbase, lq * 32, 256 + nh * 64 + cb), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) h2[(nh * 64 + cb + j) * 65 + o] = fmaxf(v[j] + bias, 0.f);
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  // fc3 (use_model.py:40,57): one thread per sample
+  float *lg = reinterpret_cast<float *>(sm + K4_LG);
+  if (tid < 128) {
+    const float *h2 = reinterpret_cast<const float *>(sm + K4_H2) + tid * 65;
+    const float *w3 = reinterpret_cast<const float *>(sm + K4_F3W);
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; o++) acc[o] = __ldg(fp + F_F3B + o);
+    for (int i = 0; i < 64; i++) {
+      const float x = h2[i];
+#pragma unroll
+      for (int o = 0; o < 16; o++) acc[o] = fmaf(w3[o * 64 + i], x, acc[o]);
+    }
+    const int n = nt * 128 + tid;
+#pragma unroll
+    for (int o = 0; o < 16; o++) lg[tid * 16 + o] = acc[o];
+    if (n < 4 * geo.nctu && logits_out)
+#pragma unroll
+      for (int o = 0; o < 16; o += 4) *reinterpret_cast<float4 *>(logits_out + (size_t)n * 16 + o) = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int ctu = nt * 32 + tid;
+    if (ctu < geo.nctu) {
+      uint8_t lab[16];
+      logits_to_labels(lg + tid * 64, lab, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H, boundary_fix);
+      uint4 pk;
+      uint32_t *pw = reinterpret_cast<uint32_t *>(&pk);
+      for (int i = 0; i < 4; i++) pw[i] = lab[4 * i] | (lab[4 * i + 1] << 8) | (lab[4 * i + 2] << 16) | (lab[4 * i + 3] << 24);
+      *reinterpret_cast<uint4 *>(labels + (size_t)ctu * 16) = pk;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tbase, 512);
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+inline int tc_prepare(const char *hdlt_path, int nctu, TcParams *p, std::string &err) {
+  FILE *f = fopen(hdlt_path, "rb");
+  if (!f) { err = std::string("cannot open tensor-core weight blob: ") + hdlt_path; return HEVCDL_E_WEIGHTS; }
+  std::vector<uint8_t> buf(SZ_HDLT);
+  char magic[8], extra;
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "HDLT0001", 8) == 0 && fread(buf.data(), 1, SZ_HDLT, f) == (size_t)SZ_HDLT &&
+            fread(&extra, 1, 1, f) == 0;
+  fclose(f);
+  if (!ok) { err = "malformed HDLT weight blob"; return HEVCDL_E_WEIGHTS; }
+  uint8_t *d = nullptr;
+  p->npad = ((4 * nctu + 127) / 128) * 128;
+  const size_t feats_bytes = (size_t)p->npad * 4096;
+  if (cudaMalloc(&d, SZ_HDLT) != cudaSuccess || cudaMemcpy(d, buf.data(), SZ_HDLT, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&p->cat, (size_t)nctu * CAT_BYTES) != cudaSuccess || cudaMemset(p->cat, 0, (size_t)nctu * CAT_BYTES) != cudaSuccess ||
+      cudaMalloc(&p->a2, (size_t)nctu * A2_BYTES) != cudaSuccess || cudaMemset(p->a2, 0, (size_t)nctu * A2_BYTES) != cudaSuccess ||
+      cudaMalloc(&p->feats, feats_bytes) != cudaSuccess || cudaMemset(p->feats, 0, feats_bytes) != cudaSuccess) {
+    err = std::string("tensor-core path allocation: ") + cudaGetErrorString(cudaGetLastError());
+    return HEVCDL_E_CUDA;
+  }
+  p->blob = d;
+  return HEVCDL_OK;
+}
+
+inline void tc_release(TcParams *p) {
+  cudaFree(const_cast<uint8_t *>(p->blob)); cudaFree(p->cat); cudaFree(p->a2); cudaFree(p->feats);
+  *p = TcParams{};
+}
+
+inline int tc_configure(std::string &err) {
+  if (cudaFuncSetAttribute(k_tc_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tc_conv2, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tc_conv3, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tc_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM) != cudaSuccess) {
+    err = std::string("tensor-core kernels: shared-memory attribute: ") + cudaGetErrorString(cudaGetLastError());
+    return HEVCDL_E_CUDA;
+  }
+  return HEVCDL_OK;
+}
+
+// Queue the four CNN kernels of one frame.  Returns the number of kernels launched.
+inline int tc_launch(const TcParams &p, const uint8_t *Y, const uint8_t *U, const uint8_t *V, FrameGeom g, int pitch, int cpitch,
+                     int boundary_fix, uint8_t *labels, float *logits, int num_sms, cudaStream_t st) {
+  const int grid = g.nctu < num_sms ? g.nctu : num_sms;
+  k_tc_l1<<<grid, TC_THREADS, K1_SMEM, st>>>(Y, U, V, g, pitch, cpitch, p.blob, p.cat);
+  k_tc_conv2<<<grid, TC_THREADS, K2_SMEM, st>>>(g, p.blob, p.cat, p.a2);
+  k_tc_conv3<<<grid, TC_THREADS, K3_SMEM, st>>>(g, p.blob, p.a2, p.feats, p.npad);
+  k_tc_fc<<<p.npad / 128, TC_THREADS, K4_SMEM, st>>>(g, p.blob, p.feats, p.npad, boundary_fix, labels, logits);
+  return 4;
+}
+
 }  // namespace hevcdl

@@ -57,7 +57,6 @@ struct hevcdl_ctx {
   float *dPacked = nullptr;            // fp32-path packed weights
   Fp32Params fp{};
   TcParams tc{};
-  void *dTcBlob = nullptr;
   int numSMs = 0;
   std::string err;
   hevcdl_stats_t stats{};
@@ -134,8 +133,14 @@ int load_weights(hevcdl_ctx *ctx) {
   p.g1 = W + O_BN1G; p.b1 = W + O_BN1B; p.g64 = W + O_BN64G; p.b64 = W + O_BN64B;
   p.g2 = W + O_BN2G; p.b2 = W + O_BN2B; p.g3 = W + O_BN3G; p.b3 = W + O_BN3B;
   p.f1wT = P + o_f1; p.f1b = W + O_F1B; p.f2wT = P + o_f2; p.f2b = W + O_F2B; p.f3wT = P + o_f3; p.f3b = W + O_F3B;
-  int rc = tc_prepare_weights(w.data(), ctx->dWeights, &ctx->tc, &ctx->dTcBlob, ctx->err);
-  return rc;
+  if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
+    // pre-packed tensor-core operands live next to the fp32 blob: <name>.hdlw -> <name>.hdlt (tools/tc_pack.py)
+    std::string tp = ctx->cfg.weights_path;
+    const size_t dot = tp.rfind('.');
+    tp = (dot == std::string::npos ? tp : tp.substr(0, dot)) + ".hdlt";
+    return tc_prepare(tp.c_str(), ctx->geo.nctu, &ctx->tc, ctx->err);
+  }
+  return HEVCDL_OK;
 }
 
 int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
@@ -371,7 +376,8 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     if (s.evT1) cudaEventDestroy(s.evT1);
     if (s.evT2) cudaEventDestroy(s.evT2);
   }
-  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dTcBlob); cudaFree(ctx->dExact);
+  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact);
+  tc_release(&ctx->tc);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
   cudaGetLastError();
@@ -558,6 +564,20 @@ int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int i
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (launches) *launches = nl / 2;
   ctx->stats.kernel_launches += nl;
+  return HEVCDL_OK;
+}
+
+int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size_t *size) {
+  if (!ctx || which < 0 || which > 2) return HEVCDL_E_INVAL;
+  if (ctx->cfg.precision != HEVCDL_PREC_BF16_TC) { ctx->err = "intermediates exist only on the tensor-core path"; return HEVCDL_E_INVAL; }
+  cudaSetDevice(ctx->cfg.device);
+  const size_t sz[3] = {(size_t)ctx->geo.nctu * CAT_BYTES, (size_t)ctx->geo.nctu * A2_BYTES, (size_t)ctx->tc.npad * 4096};
+  const uint8_t *src[3] = {ctx->tc.cat, ctx->tc.a2, ctx->tc.feats};
+  if (size) *size = sz[which];
+  if (!dst) return HEVCDL_OK;
+  if (nbytes < sz[which]) return HEVCDL_E_INVAL;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(dst, src[which], sz[which], cudaMemcpyDeviceToHost));
   return HEVCDL_OK;
 }
 

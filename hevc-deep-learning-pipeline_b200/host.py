@@ -21,7 +21,8 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_get_stats", "hevcdl_stream",
+    "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_debug_copy", "hevcdl_get_stats",
+    "hevcdl_stream",
 ]
 
 
@@ -73,6 +74,7 @@ def load_library():
     L.hevcdl_release_frame.argtypes = [vp, ip]
     L.hevcdl_rmd_exact.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp]
     L.hevcdl_bench_resident.argtypes = [vp, vp, ip, ip, C.POINTER(C.c_float), C.POINTER(ip)]
+    L.hevcdl_debug_copy.argtypes = [vp, ip, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hevcdl_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hevcdl_stream.argtypes = [vp]
     L.hevcdl_stream.restype = vp
@@ -202,6 +204,14 @@ class DepthPredictor:
         nl = C.c_int()
         self._ck(self.lib.hevcdl_bench_resident(self.h, _ptr(fr), len(fr), iters, ms, C.byref(nl)), "bench_resident")
         return list(ms), nl.value
+
+    def debug_copy(self, which):
+        """Tensor-core path intermediates of the last frame (0 cat, 1 a2, 2 features) as raw bf16 bits."""
+        n = C.c_size_t()
+        self._ck(self.lib.hevcdl_debug_copy(self.h, which, None, 0, C.byref(n)), "debug_copy")
+        out = np.empty(n.value // 2, np.uint16)
+        self._ck(self.lib.hevcdl_debug_copy(self.h, which, _ptr(out), n.value, C.byref(n)), "debug_copy")
+        return out
 
     def stats(self):
         s = Stats()

@@ -11,6 +11,7 @@
  */
 #ifndef HEVCDL_H
 #define HEVCDL_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -123,6 +124,11 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
  * launched per pass. */
 int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int iters, float ms[3],
                           int *launches);
+
+/* Test hook (tensor-core path only): copy one L2-resident intermediate of the most recent frame to
+ * the host -- which = 0: conv1/conv64 output planes ("cat"), 1: conv2 output planes, 2: conv3
+ * features in the fc1 operand layout.  *size receives the byte size; dst may be NULL to query it. */
+int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size_t *size);
 
 int hevcdl_get_stats(hevcdl_ctx *ctx, hevcdl_stats_t *out);
 /* CUDA stream handle (cudaStream_t) of the context, for callers that time with their own events */

@@ -44,3 +44,13 @@ def built():
     if not os.path.exists(so):
         ge.build()
     return so
+
+
+def unsafe_label_mismatches(lab, olab, margins, eps):
+    """Label mismatches that count as parity failures.  The reference's fix-up rules
+    (use_model.py:102-119) couple the 16 labels of a CTU -- one argmax flip can rewrite the other
+    digits of its quadrant (R1/R2) and of later quadrants (R3/R4) -- so a CTU is only required to
+    match when EVERY argmax margin of that CTU exceeds eps."""
+    import numpy as np
+    safe_ctu = margins.reshape(len(lab), -1).min(axis=1) > eps
+    return int(((lab != olab).any(axis=1) & safe_ctu).sum()), int(safe_ctu.sum())

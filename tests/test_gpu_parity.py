@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, unsafe_label_mismatches
 
 pytestmark = pytest.mark.gpu
 
@@ -35,7 +35,7 @@ def test_labels_vs_unmodified_use_model_golden(built, host, prec):
     if prec == 0:
         assert (lab == g["labels"]).all()
     else:
-        assert (lab != g["labels"]).mean() < 0.02
+        assert (lab != g["labels"]).any(axis=1).mean() < 0.1      # CTUs whose labels moved (bf16 operands)
     dp.close()
 
 
@@ -52,8 +52,8 @@ def test_logits_and_labels_vs_oracle_1080p(built, host, oracle, weights, pkg, pr
         olab, olg, mar = oracle.frame_labels(weights, Y, U, V, a, b, want_logits=True)
         d = np.abs(lg[a:b] - olg[a:b]).max()
         assert d < (2e-3 if prec == 0 else 1.0), d
-        bad = (lab[a:b] != olab[a:b]) & (mar[a:b] > EPS[prec])
-        assert not bad.any(), (r, int(bad.sum()))
+        nbad, nsafe = unsafe_label_mismatches(lab[a:b], olab[a:b], mar[a:b], EPS[prec])
+        assert nbad == 0 and nsafe > 0, (r, nbad, nsafe)
 
 
 @pytest.mark.parametrize("kind", ["noise", "flat"])
@@ -66,7 +66,7 @@ def test_edge_content(built, host, oracle, weights, pkg, kind):
     dp.release(5)
     dp.close()
     olab, olg, mar = oracle.frame_labels(weights, Y, U, V, want_logits=True)
-    assert not ((lab != olab) & (mar > EPS[0])).any()
+    assert unsafe_label_mismatches(lab, olab, mar, EPS[0])[0] == 0
     opu, osatd = oracle.frame_rmd(Y, lab)
     assert len(opu) == len(pus) and (osatd == satd).all()
 
