@@ -198,10 +198,10 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot &s, bool timed) {
   }
   if (timed) cudaEventRecord(s.evT1, ctx->stream);
   if (ctx->cfg.rmd) {
-    k_enum_pus<<<1, 1024, 0, ctx->stream>>>(s.dLabels, gd, s.dCtuOff, s.dPus);
+    k_enum_pus<<<1, 1024, 0, ctx->stream>>>(s.dLabels, gd, s.dCtuOff);
     const int grid = g.nctu < 8 * ctx->numSMs ? g.nctu : 8 * ctx->numSMs;
-    k_rmd_batched<<<grid, RMD_THREADS, sizeof(RmdSmem), ctx->stream>>>(s.dY, gd, ctx->pitch, s.dCtuOff, s.dPus, s.dSatd,
-                                                                      s.dCand);
+    k_rmd_batched<<<grid, RMD_THREADS, sizeof(RmdSmem), ctx->stream>>>(s.dY, gd, ctx->pitch, s.dLabels, s.dCtuOff, s.dPus,
+                                                                      s.dSatd, s.dCand);
     launches += 2;
   }
   if (timed) cudaEventRecord(s.evT2, ctx->stream);

@@ -10,6 +10,8 @@
 // Reference-sample line layout (n = PU size, 4n+1 samples):
 //   line[0..2n-1] left column bottom-up (below-left first), line[2n] corner, line[2n+1..4n] above row.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace hevcdl {
@@ -19,6 +21,7 @@ constexpr int MAX_PU_CTU = 320;                 // 64 8x8 CUs x (1 + 4 NxN PUs)
 constexpr int TILE_P = 144;                     // staged luma pitch: x0-16 .. x0+127
 constexpr int TILE_H = 65;                      // y0-1 .. y0+63
 constexpr int LINE_POOL = 2 * (64 * 33 + 256 * 17);  // worst case: unfiltered + filtered lines of a CTU
+constexpr int MAX_SLABS = 64 * 18 * 2;          // 64 8x8 CUs x (2Nx2N + NxN) x 36 units / 2
 
 __device__ __forceinline__ int zidx4(int ux, int uy) {   // z-order of a 4x4 unit in a CTU (TComRom.cpp:284)
   int z = 0;
@@ -83,10 +86,10 @@ __device__ inline int enum_ctu_pus(const uint8_t *label, int ctu, int ctu_x, int
   return cnt;
 }
 
-// counts -> exclusive offsets -> descriptors, one launch, one block (nctu <= 8160 at 8K)
+// per-CTU PU counts -> exclusive offsets (one block; nctu <= 8160 at 8K).  The descriptors themselves are
+// written by k_rmd_batched, which enumerates its CTU again with one thread per 8x8 position.
 __global__ void __launch_bounds__(1024, 1)
-k_enum_pus(const uint8_t *__restrict__ labels, FrameGeom geo, int *__restrict__ ctu_off /* nctu+1 */,
-           hevcdl_pu *__restrict__ pus) {
+k_enum_pus(const uint8_t *__restrict__ labels, FrameGeom geo, int *__restrict__ ctu_off /* nctu+1 */) {
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -94,13 +97,11 @@ k_enum_pus(const uint8_t *__restrict__ labels, FrameGeom geo, int *__restrict__ 
   for (int base = 0; base < geo.nctu; base += blockDim.x) {
     const int ctu = base + threadIdx.x;
     int cnt = 0;
-    uint8_t lab[16];
     if (ctu < geo.nctu) {
-      const uint4 pk = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
-      *reinterpret_cast<uint4 *>(lab) = pk;
+      uint8_t lab[16];
+      *reinterpret_cast<uint4 *>(lab) = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
       cnt = enum_ctu_pus(lab, ctu, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H, nullptr);
     }
-    // block exclusive scan
     int v = cnt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -121,11 +122,7 @@ k_enum_pus(const uint8_t *__restrict__ labels, FrameGeom geo, int *__restrict__ 
     }
     __syncthreads();
     const int carry = carry_s;
-    const int excl = carry + (warp ? warp_tot[warp - 1] : 0) + v - cnt;
-    if (ctu < geo.nctu) {
-      ctu_off[ctu] = excl;
-      enum_ctu_pus(lab, ctu, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H, pus + excl);
-    }
+    if (ctu < geo.nctu) ctu_off[ctu] = carry + (warp ? warp_tot[warp - 1] : 0) + v - cnt;
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[31];
     __syncthreads();
@@ -293,9 +290,17 @@ __device__ inline int cand_list(const uint32_t *satd, const uint32_t *bits, doub
 __device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
 
 // ---- K6 (batched, references taken from the staged picture itself) ---------------------------
+// Work decomposition: a "unit" is one 8x8 block of one PU for one mode (for the four 4x4 PUs of an
+// 8x8 CU: the CU's 8x8 area for one mode, each quadrant predicted from its own PU's references);
+// a warp processes "slabs" of two units.  Each lane predicts two neighbouring pixels per unit
+// with one packed 16-bit interpolation, forms the residual as an exact fp16 pair, and the 2-D
+// Hadamard transform of both units is two chained mma.sync (A = diag(H8,H8) or diag(H4 x4), entries
+// +-1): stage 1 gives H*D (|v| <= 2040, exact in fp16), the accumulator fragment re-read as the
+// next B operand is its transpose, stage 2 gives (H*D*H^T)^T (|v| <= 16320, exact in fp32).
+// Sum of magnitudes and the per-block rounding are those of TComRdCost.cpp:1549-1750.
 struct RmdSmem {
   uint8_t tile[TILE_H * TILE_P];                // luma rows y0-1..y0+63, cols x0-16..x0+127
-  int16_t lines[LINE_POOL];
+  int16_t lines[LINE_POOL + 8];
   uint32_t satd[MAX_PU_CTU * 35];
   hevcdl_pu pu[MAX_PU_CTU];
   int line_off[MAX_PU_CTU + 1];
@@ -303,20 +308,99 @@ struct RmdSmem {
   int16_t dc[MAX_PU_CTU];
   uint8_t avail[RMD_THREADS / 32][68];
   int8_t src[RMD_THREADS / 32][68];
+  uint16_t slab_pu[MAX_SLABS];                  // PU owning each slab (slabs never straddle PUs: unit counts are padded to even)
+  int npu_w0;
 };
 
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                              uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Two neighbouring predicted pixels of one PU for one mode, packed (first | second << 16).
+// (X, Yc): position of the first pixel inside the PU; the second is (X+1, Yc) for vertical-type
+// modes (planar, DC, 18..34) and (X, Yc+1) for horizontal modes (2..17).  c = centre (corner) of
+// the reference line chosen for this mode, u = centre of the unfiltered line (DC edge filter).
+__device__ __forceinline__ uint32_t predict_pair(const int16_t *__restrict__ c, const int16_t *__restrict__ u, int n, int lg,
+                                                 int mode, int X, int Yc, int dc) {
+  if (mode >= 2) {                                // angular (TComPrediction.cpp:229-388)
+    const bool ver = mode >= 18;
+    const int am = ver ? mode - 26 : 10 - mode;
+    const int aabs = abs(am);
+    const int angle = am < 0 ? -(int)c_ang[aabs] : (int)c_ang[aabs];
+    const int inv = c_inv[aabs];
+    const int sg = ver ? 1 : -1;
+    const int jj = ver ? Yc : X, ii = ver ? X : Yc;     // jj: distance from the main reference, ii: along it
+    const int pos = (jj + 1) * angle, di = pos >> 5, df = pos & 31;
+    const int k = ii + di + 1;
+    int k0 = sg * k, k1 = k0 + sg, k2 = k1 + sg;
+    if (angle < 0) {                              // warp-uniform: negative angles project the side reference for k < 0
+      if (k < 0) k0 = -sg * ((128 - k * inv) >> 8);
+      if (k + 1 < 0) k1 = -sg * ((128 - (k + 1) * inv) >> 8);
+      if (k + 2 < 0) k2 = -sg * ((128 - (k + 2) * inv) >> 8);
+    }
+    const uint32_t s0 = (uint16_t)c[k0], s1 = (uint16_t)c[k1], s2 = (uint16_t)c[k2];
+    const uint32_t A = s0 | (s1 << 16), B = s1 | (s2 << 16);
+    uint32_t P = (((32 - df) * A + df * B + 0x00100010u) >> 5) & 0x07FF07FFu;
+    if (angle == 0 && n <= 16 && ii == 0) {        // pure V/H edge filter on the first column along the reference
+      const int p0 = clip255((int)(P & 0xFFFF) + ((c[-sg * (jj + 1)] - c[0]) >> 1));
+      P = (P & 0xFFFF0000u) | (uint32_t)p0;
+    }
+    return P;
+  }
+  int p0, p1;
+  const int X1 = X + 1;                            // vertical-type pairing: second pixel to the right
+  if (mode == 0) {                                 // planar (TComPrediction.cpp:731-781)
+    const int blv = c[-1 - n], trv = c[1 + n], l = c[-1 - Yc];
+    const int t0 = c[1 + X], t1 = c[1 + X1];
+    p0 = ((l << lg) + n + (X + 1) * (trv - l) + (t0 << lg) + (Yc + 1) * (blv - t0)) >> (lg + 1);
+    p1 = ((l << lg) + n + (X1 + 1) * (trv - l) + (t1 << lg) + (Yc + 1) * (blv - t1)) >> (lg + 1);
+  } else {                                         // DC + edge filter for n <= 16 (:183-201,794-817)
+    p0 = p1 = dc;
+    if (n <= 16) {
+      if (Yc == 0) {
+        p0 = X == 0 ? (u[1] + u[-1] + 2 * dc + 2) >> 2 : (u[1 + X] + 3 * dc + 2) >> 2;
+        p1 = (u[1 + X1] + 3 * dc + 2) >> 2;
+      } else if (X == 0) {
+        p0 = (u[-1 - Yc] + 3 * dc + 2) >> 2;
+      }
+    }
+  }
+  return (uint32_t)p0 | ((uint32_t)p1 << 16);
+}
+
 __global__ void __launch_bounds__(RMD_THREADS, 2)
-k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const int *__restrict__ ctu_off,
-              const hevcdl_pu *__restrict__ pus, uint32_t *__restrict__ satd_out, uint8_t *__restrict__ cand_out) {
+k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uint8_t *__restrict__ labels,
+              const int *__restrict__ ctu_off, hevcdl_pu *__restrict__ pus_out, uint32_t *__restrict__ satd_out,
+              uint8_t *__restrict__ cand_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
   RmdSmem &S = *reinterpret_cast<RmdSmem *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = geo.W, H = geo.H;
+  const int g = lane >> 2, t = lane & 3;
+  // A fragments (m16n8k16 row-major A): only the diagonal 8x8 blocks are non-zero
+  uint32_t a8, a4;
+  {
+    const uint32_t one = 0x3C00u, neg = 0xBC00u;
+    const int c0 = 2 * t, c1 = 2 * t + 1;
+    a8 = ((__popc(g & c0) & 1) ? neg : one) | (((__popc(g & c1) & 1) ? neg : one) << 16);
+    const bool on = (g >> 2) == (t >> 1);
+    a4 = on ? (((__popc((g & 3) & (c0 & 3)) & 1) ? neg : one) | (((__popc((g & 3) & (c1 & 3)) & 1) ? neg : one) << 16)) : 0u;
+  }
 
   for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x) {
     const int first = ctu_off[ctu], npu = ctu_off[ctu + 1] - first;
     if (npu == 0) continue;                     // uniform per block
-    const int x0 = (ctu % geo.ctu_w) * 64, y0 = (ctu / geo.ctu_w) * 64;
+    const int ctu_x = ctu % geo.ctu_w, ctu_y = ctu / geo.ctu_w;
+    const int x0 = ctu_x * 64, y0 = ctu_y * 64;
     // stage luma: 16-byte vectors, zero outside the picture (never read: availability masks it)
     for (int i = tid; i < TILE_H * (TILE_P / 16); i += RMD_THREADS) {
       const int r = i / (TILE_P / 16), cv = i % (TILE_P / 16);
@@ -325,21 +409,69 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const int
       if (gy >= 0 && gy < H && gx >= 0 && gx < pitch) v = *reinterpret_cast<const uint4 *>(Y + (size_t)gy * pitch + gx);
       *reinterpret_cast<uint4 *>(&S.tile[r * TILE_P + cv * 16]) = v;
     }
-    for (int i = tid; i < npu; i += RMD_THREADS) S.pu[i] = pus[first + i];
     for (int i = tid; i < npu * 35; i += RMD_THREADS) S.satd[i] = 0;
-    __syncthreads();
-    if (tid == 0) {                             // offsets of each PU's lines and SATD units
-      int lo = 0, uo = 0;
-      for (int i = 0; i < npu; i++) {
-        const int n = S.pu[i].size;
-        S.line_off[i] = lo; S.unit_off[i] = uo;
-        lo += (4 * n + 1 + 1) & ~1;             // unfiltered
-        if (n == 8 || n == 16 || n == 32) lo += (4 * n + 1 + 1) & ~1;
-        uo += 35 * (n >= 8 ? (n >> 3) * (n >> 3) : 1);
+    // ---- PU enumeration: one thread per 8x8 position (z-order index), TEncCu.cpp:496-520 ----------
+    if (tid < 64) {
+      const int i3 = tid;
+      const uint4 pk = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
+      const uint32_t lw[4] = {pk.x, pk.y, pk.z, pk.w};
+      int emit = 0, esize = 0, ex = 0, ey = 0;
+      for (int d = 0; d < 4; d++) {
+        const int span = 64 >> (2 * d), o = i3 & ~(span - 1);
+        int bx = 0, by = 0;
+#pragma unroll
+        for (int b = 0; b < 3; b++) { bx |= ((o >> (2 * b)) & 1) << b; by |= ((o >> (2 * b + 1)) & 1) << b; }
+        const int x = x0 + bx * 8, y = y0 + by * 8, size = 64 >> d;
+        if (x >= W || y >= H) break;                                   // CU outside the picture: skipped
+        const int li = 4 * ((y & 63) >> 4) + ((x & 63) >> 4);
+        const int pl = (lw[li >> 2] >> (8 * (li & 3))) & 255;
+        const bool boundary = (x + size > W) || (y + size > H);
+        if (pl == d && !boundary) {
+          if (o == i3) { emit = d == 3 ? 5 : 1; esize = size; ex = x; ey = y; }
+          break;
+        }
+        if (!(pl > d && d < 3)) break;                                 // pruned
       }
-      S.line_off[npu] = lo; S.unit_off[npu] = uo;
+      const uint32_t m1 = __ballot_sync(0xffffffffu, emit >= 1), m5 = __ballot_sync(0xffffffffu, emit == 5);
+      const uint32_t lt = (1u << lane) - 1;
+      int pos = __popc(m1 & lt) + 4 * __popc(m5 & lt);
+      if (tid == 31) S.npu_w0 = pos + emit;
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      if (warp == 1) pos += S.npu_w0;
+      if (emit) {
+        S.pu[pos] = hevcdl_pu{(uint16_t)ex, (uint16_t)ey, (uint8_t)esize, 0, (uint16_t)ctu};
+        if (emit == 5)
+          for (int k = 0; k < 4; k++)
+            S.pu[pos + 1 + k] = hevcdl_pu{(uint16_t)(ex + (k & 1) * 4), (uint16_t)(ey + (k >> 1) * 4), 4, (uint8_t)(k + 1), (uint16_t)ctu};
+      }
     }
     __syncthreads();
+    if (warp == 0) {                            // offsets of each PU's lines and SATD units (warp scan)
+      int lo_run = 0, uo_run = 0;
+      for (int base = 0; base < npu; base += 32) {
+        const int i = base + lane;
+        int lo = 0, uo = 0;
+        if (i < npu) {
+          const int n = S.pu[i].size;
+          lo = (4 * n + 1 + 1) & ~1;
+          if (n == 8 || n == 16 || n == 32) lo *= 2;
+          uo = n >= 16 ? 35 * (n >> 3) * (n >> 3) : ((n == 8 || S.pu[i].part == 1) ? 36 : 0);   // even: slabs stay inside a PU
+        }
+        int li = lo, ui = uo;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(0xffffffffu, li, o), b = __shfl_up_sync(0xffffffffu, ui, o);
+          if (lane >= o) { li += a; ui += b; }
+        }
+        if (i < npu) { S.line_off[i] = lo_run + li - lo; S.unit_off[i] = uo_run + ui - uo; }
+        lo_run += __shfl_sync(0xffffffffu, li, 31);
+        uo_run += __shfl_sync(0xffffffffu, ui, 31);
+      }
+      if (lane == 0) { S.line_off[npu] = lo_run; S.unit_off[npu] = uo_run; }
+    }
+    __syncthreads();
+    for (int p = warp; p < npu; p += RMD_THREADS / 32)
+      for (int sl = (S.unit_off[p] >> 1) + lane; sl < (S.unit_off[p + 1] >> 1); sl += 32) S.slab_pu[sl] = (uint16_t)p;
     auto pix = [&](int gx, int gy) -> int { return S.tile[(gy - (y0 - 1)) * TILE_P + gx - (x0 - 16)]; };
 
     // reference lines: one warp per PU (HM TComPattern.cpp:326-543)
@@ -393,30 +525,82 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const int
     }
     __syncthreads();
 
-    // SATD units, flattened over (PU, mode, block)
-    const int nunits = S.unit_off[npu];
-    for (int uidx = tid; uidx < nunits; uidx += RMD_THREADS) {
-      int lo = 0, hi = npu - 1;                 // last p with unit_off[p] <= uidx
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (S.unit_off[mid] <= uidx) lo = mid; else hi = mid - 1;
+    // ---- SATD slabs: two units per warp iteration ------------------------------------------------
+    const int nslabs = S.unit_off[npu] >> 1;
+    for (int slab = warp; slab < nslabs; slab += RMD_THREADS / 32) {
+      const int p = S.slab_pu[slab], n = S.pu[p].size;
+      const int r0 = 2 * slab - S.unit_off[p];
+      const bool small = n < 8;
+      const int lgb = n >= 8 ? 2 * (ilog2(n) - 3) : 0;   // log2(blocks per mode)
+      const int nb = n >= 8 ? n >> 3 : 1;
+      const int pox = S.pu[p].x - (x0 - 16), poy = S.pu[p].y - (y0 - 1);
+      uint32_t bfrag[2];
+      int umode[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int r = r0 + e;
+        const int mode = r >> lgb, blk = r & ((1 << lgb) - 1);
+        umode[e] = mode;
+        bfrag[e] = 0u;
+        if (mode >= 35) continue;               // padding unit (warp-uniform)
+        const bool hor = mode >= 2 && mode < 18;
+        // position of this lane's first pixel inside the unit's 8x8 area
+        const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
+        int q = p, X = ux, Yc = uy, nn = n, ox = pox, oy = poy;
+        if (!small) {
+          X += (blk & (nb - 1)) * 8; Yc += (blk >> (lgb >> 1)) * 8;
+        } else {                                 // four 4x4 PUs of one CU: p is part 1, the others follow
+          q = p + (uy >> 2) * 2 + (ux >> 2);
+          X = ux & 3; Yc = uy & 3; nn = 4;
+          ox += ux & 4; oy += uy & 4;
+        }
+        const int16_t *line = S.lines + S.line_off[q];
+        const int16_t *ref = mode_uses_filter(mode, nn) ? line + ((4 * nn + 2) & ~1) : line;
+        const uint32_t P = predict_pair(ref + 2 * nn, line + 2 * nn, nn, ilog2(nn), mode, X, Yc, S.dc[q]);
+        const uint8_t *op = &S.tile[(oy + Yc) * TILE_P + ox + X];
+        // exact fp16 integers: bits 0x6400|v are the half 1024 + v for v < 1024
+        uint32_t Om = ((uint32_t)op[0] | ((uint32_t)op[hor ? TILE_P : 1] << 16)) | 0x64006400u, Pm = P | 0x64006400u;
+        const __half2 d = __hsub2(*reinterpret_cast<__half2 *>(&Om), *reinterpret_cast<__half2 *>(&Pm));
+        bfrag[e] = *reinterpret_cast<const uint32_t *>(&d);
       }
-      const int p = lo, n = S.pu[p].size, r = uidx - S.unit_off[p];
-      const int nb = n >= 8 ? n >> 3 : 1, nblk = nb * nb;
-      const int mode = r / nblk, blk = r % nblk;
-      const int16_t *line = S.lines + S.line_off[p];
-      const int16_t *ref = mode_uses_filter(mode, n) ? line + ((4 * n + 2) & ~1) : line;
-      const int lx = S.pu[p].x - (x0 - 16), ly = S.pu[p].y - (y0 - 1);
-      uint32_t v;
-      if (n >= 8) {
-        const int bx = (blk % nb) * 8, by = (blk / nb) * 8;
-        v = satd_unit<8>(&S.tile[(ly + by) * TILE_P + lx + bx], TILE_P, ref, line, n, ilog2(n), mode, bx, by, S.dc[p]);
+      const uint32_t a = small ? a4 : a8;
+      float c1[4], c2[4];
+      mma_f16_16816(c1, a, 0u, 0u, a, bfrag[0], bfrag[1]);
+      mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+      float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
+      if (!small) {
+        // totals over the 32 lanes: exchange step then butterfly; lane 0 -> unit A, lane 16 -> unit B
+        const bool upper = lane & 16;
+        float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((lane & 15) == 0) {
+          const int mode = upper ? umode[1] : umode[0];
+          if (mode < 35) atomicAdd(&S.satd[p * 35 + mode], ((uint32_t)v + 2) >> 2);
+        }
       } else {
-        v = satd_unit<4>(&S.tile[ly * TILE_P + lx], TILE_P, ref, line, 4, 2, mode, 0, 0, S.dc[p]);
+        // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
+#pragma unroll
+        for (int o = 1; o <= 8; o <<= 1) {
+          if (o == 2) continue;
+          sA += __shfl_xor_sync(0xffffffffu, sA, o);
+          sB += __shfl_xor_sync(0xffffffffu, sB, o);
+        }
+        if ((lane & 13) == 0) {                   // lanes 0, 2, 16, 18
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int mode = umode[e];
+            if (mode >= 35) continue;
+            // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
+            const bool hor = mode >= 2 && mode < 18;
+            const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
+            atomicAdd(&S.satd[(p + sub) * 35 + mode], ((uint32_t)(e ? sB : sA) + 1) >> 1);
+          }
+        }
       }
-      atomicAdd(&S.satd[p * 35 + mode], v);
     }
     __syncthreads();
+    for (int i = tid; i < npu; i += RMD_THREADS) pus_out[first + i] = S.pu[i];
     for (int i = tid; i < npu * 35; i += RMD_THREADS) satd_out[(size_t)first * 35 + i] = S.satd[i];
     for (int p = tid; p < npu; p += RMD_THREADS) {
       uint8_t modes[10];
