@@ -377,6 +377,62 @@ __device__ __forceinline__ uint32_t predict_pair(const int16_t *__restrict__ c, 
   return (uint32_t)p0 | ((uint32_t)p1 << 16);
 }
 
+__device__ __constant__ int8_t c_mode_angle[35] = {0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
+                                                   -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
+__device__ __constant__ int16_t c_mode_inv[35] = {0, 0, 256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315,
+                                                  256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+
+// Everything about (PU, mode) that does not depend on the pixel: computed once per work item.
+struct ModeK {
+  const int16_t *c;      // centre of the reference line used by this mode (filtered or not)
+  const int16_t *u;      // centre of the unfiltered line
+  int mode, n, lg, dc, angle, inv, sg;
+  bool hor, edge;
+};
+__device__ __forceinline__ ModeK make_modek(const int16_t *line, int n, int mode, int dc) {
+  ModeK k;
+  const int16_t *ref = mode_uses_filter(mode, n) ? line + ((4 * n + 2) & ~1) : line;
+  k.c = ref + 2 * n; k.u = line + 2 * n;
+  k.mode = mode; k.n = n; k.lg = ilog2(n); k.dc = dc;
+  k.angle = c_mode_angle[mode]; k.inv = c_mode_inv[mode];
+  k.hor = mode >= 2 && mode < 18;
+  k.sg = k.hor ? -1 : 1;
+  k.edge = mode >= 2 && k.angle == 0 && n <= 16;
+  return k;
+}
+// Two neighbouring predicted pixels, packed as exact fp16 integers (1024 + value each): first pixel (X, Yc),
+// second (X+1, Yc) for vertical-type modes / (X, Yc+1) for horizontal modes.
+__device__ __forceinline__ uint32_t predict_pair_k(const ModeK &k, int X, int Yc) {
+  if (k.mode >= 2) {
+    const int jj = k.hor ? X : Yc, ii = k.hor ? Yc : X;
+    const int pos = (jj + 1) * k.angle, di = pos >> 5, df = pos & 31;
+    const int kk = ii + di + 1;
+    int k0 = k.sg * kk, k1 = k0 + k.sg, k2 = k1 + k.sg;
+    if (k.angle < 0) {                            // warp-uniform: negative angles project the side reference for kk < 0
+      if (kk < 0) k0 = -k.sg * ((128 - kk * k.inv) >> 8);
+      if (kk + 1 < 0) k1 = -k.sg * ((128 - (kk + 1) * k.inv) >> 8);
+      if (kk + 2 < 0) k2 = -k.sg * ((128 - (kk + 2) * k.inv) >> 8);
+    }
+    const uint32_t s0 = (uint16_t)k.c[k0], s1 = (uint16_t)k.c[k1], s2 = (uint16_t)k.c[k2];
+    const uint32_t A = s0 | (s1 << 16), B = s1 | (s2 << 16);
+    uint32_t P = (((32 - df) * A + df * B + 0x00100010u) >> 5) & 0x07FF07FFu;
+    if (k.edge && ii == 0) {
+      const int p0 = clip255((int)(P & 0xFFFF) + ((k.c[-k.sg * (jj + 1)] - k.c[0]) >> 1));
+      P = (P & 0xFFFF0000u) | (uint32_t)p0;
+    }
+    return P | 0x64006400u;
+  }
+  return predict_pair(k.c, k.u, k.n, k.lg, k.mode, X, Yc, k.dc) | 0x64006400u;
+}
+// Residual pair (original - prediction) as an exact half2; org points at the first pixel in the staged tile.
+__device__ __forceinline__ uint32_t resid_pair(const uint8_t *org, bool hor, uint32_t Pm) {
+  uint32_t Om;
+  if (!hor) Om = __byte_perm((uint32_t)*reinterpret_cast<const uint16_t *>(org), 0x64u, 0x4140);   // 0x64 b1 0x64 b0
+  else Om = ((uint32_t)org[0] | ((uint32_t)org[TILE_P] << 16)) | 0x64006400u;
+  const __half2 d = __hsub2(*reinterpret_cast<__half2 *>(&Om), *reinterpret_cast<__half2 *>(&Pm));
+  return *reinterpret_cast<const uint32_t *>(&d);
+}
+
 __global__ void __launch_bounds__(RMD_THREADS, 2)
 k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uint8_t *__restrict__ labels,
               const int *__restrict__ ctu_off, hevcdl_pu *__restrict__ pus_out, uint32_t *__restrict__ satd_out,
@@ -409,7 +465,6 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uin
       if (gy >= 0 && gy < H && gx >= 0 && gx < pitch) v = *reinterpret_cast<const uint4 *>(Y + (size_t)gy * pitch + gx);
       *reinterpret_cast<uint4 *>(&S.tile[r * TILE_P + cv * 16]) = v;
     }
-    for (int i = tid; i < npu * 35; i += RMD_THREADS) S.satd[i] = 0;
     // ---- PU enumeration: one thread per 8x8 position (z-order index), TEncCu.cpp:496-520 ----------
     if (tid < 64) {
       const int i3 = tid;
@@ -455,7 +510,7 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uin
           const int n = S.pu[i].size;
           lo = (4 * n + 1 + 1) & ~1;
           if (n == 8 || n == 16 || n == 32) lo *= 2;
-          uo = n >= 16 ? 35 * (n >> 3) * (n >> 3) : ((n == 8 || S.pu[i].part == 1) ? 36 : 0);   // even: slabs stay inside a PU
+          uo = n >= 16 ? 35 : ((n == 8 || S.pu[i].part == 1) ? 18 : 0);   // work items: (PU, mode) or (PU, mode pair)
         }
         int li = lo, ui = uo;
 #pragma unroll
@@ -471,7 +526,7 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uin
     }
     __syncthreads();
     for (int p = warp; p < npu; p += RMD_THREADS / 32)
-      for (int sl = (S.unit_off[p] >> 1) + lane; sl < (S.unit_off[p + 1] >> 1); sl += 32) S.slab_pu[sl] = (uint16_t)p;
+      for (int sl = S.unit_off[p] + lane; sl < S.unit_off[p + 1]; sl += 32) S.slab_pu[sl] = (uint16_t)p;
     auto pix = [&](int gx, int gy) -> int { return S.tile[(gy - (y0 - 1)) * TILE_P + gx - (x0 - 16)]; };
 
     // reference lines: one warp per PU (HM TComPattern.cpp:326-543)
@@ -525,76 +580,103 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uin
     }
     __syncthreads();
 
-    // ---- SATD slabs: two units per warp iteration ------------------------------------------------
-    const int nslabs = S.unit_off[npu] >> 1;
-    for (int slab = warp; slab < nslabs; slab += RMD_THREADS / 32) {
-      const int p = S.slab_pu[slab], n = S.pu[p].size;
-      const int r0 = 2 * slab - S.unit_off[p];
-      const bool small = n < 8;
-      const int lgb = n >= 8 ? 2 * (ilog2(n) - 3) : 0;   // log2(blocks per mode)
-      const int nb = n >= 8 ? n >> 3 : 1;
-      const int pox = S.pu[p].x - (x0 - 16), poy = S.pu[p].y - (y0 - 1);
-      uint32_t bfrag[2];
-      int umode[2];
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int r = r0 + e;
-        const int mode = r >> lgb, blk = r & ((1 << lgb) - 1);
-        umode[e] = mode;
-        bfrag[e] = 0u;
-        if (mode >= 35) continue;               // padding unit (warp-uniform)
-        const bool hor = mode >= 2 && mode < 18;
-        // position of this lane's first pixel inside the unit's 8x8 area
-        const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
-        int q = p, X = ux, Yc = uy, nn = n, ox = pox, oy = poy;
-        if (!small) {
-          X += (blk & (nb - 1)) * 8; Yc += (blk >> (lgb >> 1)) * 8;
-        } else {                                 // four 4x4 PUs of one CU: p is part 1, the others follow
-          q = p + (uy >> 2) * 2 + (ux >> 2);
-          X = ux & 3; Yc = uy & 3; nn = 4;
-          ox += ux & 4; oy += uy & 4;
-        }
-        const int16_t *line = S.lines + S.line_off[q];
-        const int16_t *ref = mode_uses_filter(mode, nn) ? line + ((4 * nn + 2) & ~1) : line;
-        const uint32_t P = predict_pair(ref + 2 * nn, line + 2 * nn, nn, ilog2(nn), mode, X, Yc, S.dc[q]);
-        const uint8_t *op = &S.tile[(oy + Yc) * TILE_P + ox + X];
-        // exact fp16 integers: bits 0x6400|v are the half 1024 + v for v < 1024
-        uint32_t Om = ((uint32_t)op[0] | ((uint32_t)op[hor ? TILE_P : 1] << 16)) | 0x64006400u, Pm = P | 0x64006400u;
-        const __half2 d = __hsub2(*reinterpret_cast<__half2 *>(&Om), *reinterpret_cast<__half2 *>(&Pm));
-        bfrag[e] = *reinterpret_cast<const uint32_t *>(&d);
-      }
-      const uint32_t a = small ? a4 : a8;
-      float c1[4], c2[4];
-      mma_f16_16816(c1, a, 0u, 0u, a, bfrag[0], bfrag[1]);
-      mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-      float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
-      if (!small) {
-        // totals over the 32 lanes: exchange step then butterfly; lane 0 -> unit A, lane 16 -> unit B
-        const bool upper = lane & 16;
-        float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((lane & 15) == 0) {
-          const int mode = upper ? umode[1] : umode[0];
-          if (mode < 35) atomicAdd(&S.satd[p * 35 + mode], ((uint32_t)v + 2) >> 2);
-        }
-      } else {
-        // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
-#pragma unroll
-        for (int o = 1; o <= 8; o <<= 1) {
-          if (o == 2) continue;
-          sA += __shfl_xor_sync(0xffffffffu, sA, o);
-          sB += __shfl_xor_sync(0xffffffffu, sB, o);
-        }
-        if ((lane & 13) == 0) {                   // lanes 0, 2, 16, 18
+    // ---- SATD: work items (PU, mode) for PUs >= 16, (PU, mode pair) for 8x8 PUs and 4x4 groups ---------
+    const int nitems = S.unit_off[npu];
+    for (int item = warp; item < nitems; item += RMD_THREADS / 32) {
+      const int p = S.slab_pu[item], n = S.pu[p].size;
+      const int r = item - S.unit_off[p];
+      const uint8_t *porg = &S.tile[(S.pu[p].y - (y0 - 1)) * TILE_P + S.pu[p].x - (x0 - 16)];
+      if (n >= 16) {
+        // one mode, all 8x8 blocks of the PU, two per slab
+        const ModeK k = make_modek(S.lines + S.line_off[p], n, r, S.dc[p]);
+        const int ux = k.hor ? g : 2 * t, uy = k.hor ? 2 * t : g;
+        const int lgnb = k.lg - 3, nb = 1 << lgnb, nslabs = 1 << (2 * lgnb - 1);
+        auto slab = [&](int sl, float &sA, float &sB) {
+          uint32_t bf[2];
 #pragma unroll
           for (int e = 0; e < 2; e++) {
-            const int mode = umode[e];
-            if (mode >= 35) continue;
-            // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
-            const bool hor = mode >= 2 && mode < 18;
-            const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
-            atomicAdd(&S.satd[(p + sub) * 35 + mode], ((uint32_t)(e ? sB : sA) + 1) >> 1);
+            const int blk = 2 * sl + e;
+            const int X = ux + (blk & (nb - 1)) * 8, Yc = uy + (blk >> lgnb) * 8;
+            bf[e] = resid_pair(porg + Yc * TILE_P + X, k.hor, predict_pair_k(k, X, Yc));
+          }
+          float c1[4], c2[4];
+          mma_f16_16816(c1, a8, 0u, 0u, a8, bf[0], bf[1]);
+          mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+          sA = fabsf(c2[0]) + fabsf(c2[1]); sB = fabsf(c2[2]) + fabsf(c2[3]);
+        };
+        uint32_t acc = 0;
+        if (n == 16) {
+#pragma unroll
+          for (int sl = 0; sl < 2; sl++) {
+            float sA, sB;
+            slab(sl, sA, sB);
+            const bool upper = lane & 16;
+            float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc += ((uint32_t)v + 2) >> 2;        // lanes 0-15 hold block A's total, 16-31 block B's
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        } else {
+          for (int ch = 0; ch < nslabs; ch += 16) {
+            float part[32];
+#pragma unroll
+            for (int sl = 0; sl < 16; sl++) {
+              part[2 * sl] = 0.f; part[2 * sl + 1] = 0.f;
+              if (ch + sl < nslabs) slab(ch + sl, part[2 * sl], part[2 * sl + 1]);   // warp-uniform
+            }
+            const float tot = warp_transpose_sum32(part, lane);                     // lane l: total of block l of this chunk
+            acc += ((uint32_t)tot + 2) >> 2;                                        // per-block rounding (0 for unused slots)
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0) S.satd[p * 35 + r] = acc;
+      } else {
+        // two modes of one 8x8 PU, or of the four 4x4 PUs of one CU (p is part 1, parts 2-4 follow)
+        const bool small = n < 8;
+        uint32_t bf[2] = {0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int mode = 2 * r + e;
+          if (mode >= 35) continue;               // warp-uniform
+          const bool hor = mode >= 2 && mode < 18;
+          const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
+          const int q = small ? p + (uy >> 2) * 2 + (ux >> 2) : p;
+          const ModeK k = make_modek(S.lines + S.line_off[q], small ? 4 : 8, mode, S.dc[q]);
+          const int X = small ? ux & 3 : ux, Yc = small ? uy & 3 : uy;
+          bf[e] = resid_pair(porg + uy * TILE_P + ux, hor, predict_pair_k(k, X, Yc));
+        }
+        const uint32_t a = small ? a4 : a8;
+        float c1[4], c2[4];
+        mma_f16_16816(c1, a, 0u, 0u, a, bf[0], bf[1]);
+        mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+        float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
+        if (!small) {
+          const bool upper = lane & 16;
+          float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          const int mode = 2 * r + (upper ? 1 : 0);
+          if ((lane & 15) == 0 && mode < 35) S.satd[p * 35 + mode] = ((uint32_t)v + 2) >> 2;
+        } else {
+          // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
+#pragma unroll
+          for (int o = 1; o <= 8; o <<= 1) {
+            if (o == 2) continue;
+            sA += __shfl_xor_sync(0xffffffffu, sA, o);
+            sB += __shfl_xor_sync(0xffffffffu, sB, o);
+          }
+          if ((lane & 13) == 0) {                 // lanes 0, 2, 16, 18
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int mode = 2 * r + e;
+              if (mode >= 35) continue;
+              // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
+              const bool hor = mode >= 2 && mode < 18;
+              const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
+              S.satd[(p + sub) * 35 + mode] = ((uint32_t)(e ? sB : sA) + 1) >> 1;
+            }
           }
         }
       }
