@@ -1,0 +1,126 @@
+// hm_plugin/TEncCu_hevcdl.cpp -- the reference-side binding of libhevcdl.so.
+//
+// A from-scratch definition of
+//     Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
+// (declared at HM_dl/source/Lib/TLibEncoder/TEncCu.h:120, reference body at TEncCu.cpp:234-287)
+// that obtains the 16 CU-depth labels of the CTU from the B200 library instead of busy-polling
+// ./pred/<frame>/ctu<addr>.txt (TEncCu.cpp:243-252), then runs the reference's own pruned quadtree
+// search (xCompressCU, TEncCu.cpp:470) exactly as the reference does.  Nothing else in HM changes:
+// same caller (TEncSlice::compressSlice, TEncSlice.cpp:879), same pre/post-conditions, same
+// bitstream for the same labels.
+//
+// How it is linked without editing the reference: hm_plugin/Makefile compiles the reference's
+// TEncCu.cpp with -DcompressCtu=compressCtu_filehandshake (its file-polling body keeps existing under
+// another name) and links this translation unit's compressCtu in its place.  A maintainer applying
+// the change by hand would simply replace the body at TEncCu.cpp:234-287 with the one below
+// (INTEGRATION.md).
+//
+// Configuration comes from the environment, because the signature leaves no room for it:
+//   HEVCDL_WEIGHTS    path of the HDLW weight blob (default: weights/hevc_encoder_model.hdlw next to the repo root
+//                     baked in at build time as HEVCDL_DEFAULT_WEIGHTS)
+//   HEVCDL_DEVICE     CUDA ordinal (default 0)
+//   HEVCDL_PRECISION  fp32 (default: tightest parity with the torch sidecar) | bf16 (tcgen05 tensor cores)
+//   HEVCDL_BOUNDARY_FIX 1 = raise labels of picture-edge CTUs so partial CTUs tile (default 0 = reference)
+//   HEVCDL_RMD        1 = also run the batched 35-mode SATD pass (results are fetched by hevcdl_frame_pus; the
+//                     stock estIntraPredLumaQT does not consume them) (default 0)
+// There is no fallback: any library failure aborts the encoder with the library's error text.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "TLibEncoder/TEncCu.h"
+#include "TLibEncoder/TEncTop.h"
+
+#include "hevcdl.h"
+
+namespace {
+
+struct HevcdlSession {
+  hevcdl_ctx *ctx = nullptr;
+  int width = 0, height = 0;
+  int frame = -1;               // frame currently resident on the device (-1: none)
+
+  static void die(const char *what, int rc, hevcdl_ctx *c) {
+    fprintf(stderr, "hevcdl: %s failed: %s (%s)\n", what, hevcdl_status_str(rc), hevcdl_last_error(c));
+    exit(EXIT_FAILURE);
+  }
+
+  void open(int w, int h) {
+    hevcdl_cfg cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.abi_version = HEVCDL_ABI_VERSION;
+    const char *e;
+    cfg.device = (e = getenv("HEVCDL_DEVICE")) ? atoi(e) : 0;
+    cfg.width = w; cfg.height = h;
+    cfg.slots = 2;
+    cfg.precision = ((e = getenv("HEVCDL_PRECISION")) && !strcmp(e, "bf16")) ? HEVCDL_PREC_BF16_TC : HEVCDL_PREC_FP32;
+    cfg.rmd = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
+    cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
+    cfg.weights_path = (e = getenv("HEVCDL_WEIGHTS")) ? e : HEVCDL_DEFAULT_WEIGHTS;
+    const int rc = hevcdl_create(&cfg, &ctx);
+    if (rc) die("hevcdl_create", rc, nullptr);
+    width = w; height = h;
+  }
+
+  // Hand the picture's ORIGINAL planes (the same ones xCompressCU reads at TEncCu.cpp:484) to the device.
+  // This replaces gen_frames.py:21 (ffmpeg dump) and the sidecar's whole per-frame loop (use_model.py:74-127).
+  void begin_frame(int id, TComPicYuv *org) {
+    const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
+    if (!ctx) open(w, h);
+    if (w != width || h != height) { fprintf(stderr, "hevcdl: picture size changed mid-sequence\n"); exit(EXIT_FAILURE); }
+    if (frame >= 0) { const int rc = hevcdl_release_frame(ctx, frame); if (rc) die("hevcdl_release_frame", rc, ctx); }
+    const int rc = hevcdl_submit_frame_pel16(ctx, id, org->getAddr(COMPONENT_Y), org->getStride(COMPONENT_Y),
+                                             org->getAddr(COMPONENT_Cb), org->getAddr(COMPONENT_Cr), org->getStride(COMPONENT_Cb));
+    if (rc) die("hevcdl_submit_frame_pel16", rc, ctx);
+    frame = id;
+  }
+
+  ~HevcdlSession() {
+    if (ctx) {
+      if (getenv("HEVCDL_VERBOSE")) {
+        hevcdl_stats_t st;
+        if (!hevcdl_get_stats(ctx, &st))
+          fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches\n",
+                  (unsigned long long)st.frames, (unsigned long long)st.ctus, st.ms_cnn, st.ms_rmd,
+                  (unsigned long long)st.kernel_launches);
+      }
+      hevcdl_destroy(ctx);
+    }
+  }
+};
+
+HevcdlSession g_session;   // one encoder thread, one TEncCu instance (TEncTop.h:93): a process-wide session is enough
+
+}  // namespace
+
+Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
+{
+  const UInt ctuRsAddr = pCtu->getCtuRsAddr();
+  m_ppcBestCU[0]->initCtu( pCtu->getPic(), ctuRsAddr );
+  m_ppcTempCU[0]->initCtu( pCtu->getPic(), ctuRsAddr );
+
+  // First CTU of a picture the device has not seen yet: upload it; every kernel of the frame is queued
+  // behind the copy and the labels of all CTUs come back in one transfer.
+  if ( g_session.frame != m_iFrame )
+  {
+    g_session.begin_frame( m_iFrame, pCtu->getPic()->getPicYuvOrg() );
+  }
+
+  uint8_t depth8[16];
+  const int rc = hevcdl_ctu_labels( g_session.ctx, m_iFrame, (int)ctuRsAddr, depth8 );   // blocks on the frame's event
+  if ( rc ) HevcdlSession::die( "hevcdl_ctu_labels", rc, g_session.ctx );
+  UInt label[16];                                   // same lifetime as the reference's stack array (TEncCu.cpp:247)
+  for ( Int i = 0; i < 16; i++ ) label[i] = depth8[i];
+  m_ppcBestCU[0]->set_pred( label );
+
+  DEBUG_STRING_NEW(sDebug)
+  xCompressCU( m_ppcBestCU[0], m_ppcTempCU[0], 0 DEBUG_STRING_PASS_INTO(sDebug) );
+  DEBUG_STRING_OUTPUT(std::cout, sDebug)
+
+#if ADAPTIVE_QP_SELECTION
+  if ( m_pcEncCfg->getUseAdaptQpSelect() && pCtu->getSlice()->getSliceType() != I_SLICE )
+  {
+    xCtuCollectARLStats( pCtu );
+  }
+#endif
+}

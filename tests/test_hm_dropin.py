@@ -1,0 +1,72 @@
+"""The drop-in encoder (reference HM_dl sources + this repo's TEncCu::compressCtu over libhevcdl.so,
+hm_plugin/) against the UNMODIFIED reference encoder fed the same labels through its ./pred file
+handshake: the two must write byte-identical bitstreams (SURVEY.md 7 'minimum slice' (b)), and the
+reference decoder must accept the result (MD5 SEI)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import hm_util
+
+needs_bins = pytest.mark.skipif(not hm_util.have("ref", "dec", "hevcdl"),
+                                reason="reference/drop-in encoder binaries not built (need /root/reference at build time)")
+
+
+@needs_bins
+def test_dropin_fails_loudly_without_a_gpu(tmp_path, pkg):
+    """No CPU fallback on the named path: without a B200 the drop-in aborts with the library's message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    hm_util.write_yuv(str(tmp_path / "in.yuv"), [pkg.synth.synth_frame(64, 64, 0)])
+    r = hm_util.encode("hevcdl", str(tmp_path), "in.yuv", 64, 64, 1, 32)
+    assert r["rc"] != 0 and "no CPU fallback" in r["stderr"]
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,nframes,qp", [(192, 128, 3, 32), (416, 240, 1, 37), (256, 192, 2, 22)])
+def test_dropin_bitstream_equals_reference_fed_same_labels(tmp_path, built, host, pkg, w, h, nframes, qp):
+    frames = [pkg.synth.synth_frame(w, h, 10 + i) for i in range(nframes)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    dp = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=False)
+    for f, (Y, U, V) in enumerate(frames):
+        hm_util.write_pred(str(a / "pred"), f, dp.predict_frame(Y, U, V, frame=f))
+    dp.close()
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, nframes, qp)
+    rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, nframes, qp, env={"HEVCDL_PRECISION": "fp32"})
+    assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-400:])
+    assert ra["bytes"] > 0 and ra["sha1"] == rb["sha1"], (ra["bytes"], rb["bytes"])
+    assert (ra["kbps"], ra["psnr_y"]) == (rb["kbps"], rb["psnr_y"])
+    if w % 64 == 0 and h % 64 == 0:            # partial CTUs are non-conformant in the reference itself
+        ok, out = hm_util.decode_ok(str(b))
+        assert ok, out[-400:]
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_dropin_boundary_fix_decodes_cleanly(tmp_path, built, pkg):
+    """With HEVCDL_BOUNDARY_FIX=1 the labels of picture-edge CTUs are raised so partial CTUs tile:
+    the stream of a non-64-aligned picture passes the decoder's MD5 check, which the reference's does not."""
+    w, h = 416, 240
+    hm_util.write_yuv(str(tmp_path / "in.yuv"), [pkg.synth.synth_frame(w, h, 3)])
+    r = hm_util.encode("hevcdl", str(tmp_path), "in.yuv", w, h, 1, 32, env={"HEVCDL_BOUNDARY_FIX": "1"})
+    assert r["rc"] == 0, r["stderr"][-400:]
+    ok, out = hm_util.decode_ok(str(tmp_path))
+    assert ok, out[-400:]
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_dropin_tensor_core_precision_runs(tmp_path, built, pkg):
+    w, h = 192, 128
+    hm_util.write_yuv(str(tmp_path / "in.yuv"), [pkg.synth.synth_frame(w, h, 5)])
+    r = hm_util.encode("hevcdl", str(tmp_path), "in.yuv", w, h, 1, 32, env={"HEVCDL_PRECISION": "bf16", "HEVCDL_VERBOSE": "1"})
+    assert r["rc"] == 0 and "kernel launches" in r["stderr"], r["stderr"][-400:]
+    ok, out = hm_util.decode_ok(str(tmp_path))
+    assert ok, out[-400:]
