@@ -156,7 +156,7 @@ __device__ __forceinline__ void stage_ctu_rgb(const uint8_t *__restrict__ Y, con
 __global__ void __launch_bounds__(FP32_THREADS, 1)
 k_cnn_fp32(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint8_t *__restrict__ V,
            FrameGeom geo, int pitch, int cpitch, Fp32Params P, int boundary_fix, uint8_t *__restrict__ labels,
-           float *__restrict__ logits_out) {
+           float *__restrict__ logits_out, uint32_t *__restrict__ ctu_cnt) {
   extern __shared__ float smem[];
   float *regAC = smem;                 // img, then conv2 out
   float *regB = smem + SM_AC;          // conv1/conv64 out, then conv3 out
@@ -254,6 +254,7 @@ k_cnn_fp32(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const u
       uint32_t *pw = reinterpret_cast<uint32_t *>(&pk);
       for (int i = 0; i < 4; i++) pw[i] = lab[4 * i] | (lab[4 * i + 1] << 8) | (lab[4 * i + 2] << 16) | (lab[4 * i + 3] << 24);
       *reinterpret_cast<uint4 *>(labels + (size_t)ctu * 16) = pk;
+      if (ctu_cnt) ctu_cnt[ctu] = ctu_plan_counts(lab, ctu_x, ctu_y, geo.W, geo.H);
     }
     __syncthreads();
   }

@@ -72,6 +72,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
                : "memory");
 }
 
+// Train-mode BatchNorm of one channel of one sample (use_model.py:16-46): totals of x and
+// x^2 over the sample -> y = x*sc + sh with the BIASED variance.  fp32: the sample sizes are powers of two, so
+// the mean is exact up to the rounding of the total; the cancellation error of E[x^2]-mean^2 is ~6e-8*(1+mean^2/var)
+// relative, orders below the bf16 operand rounding of this path (the fp32 parity path is cnn_fp32.cuh).
+__device__ __forceinline__ void bn_scale_shift(float sum, float sumsq, float rcnt, float eps, float gamma, float beta,
+                                               float &sc, float &sh) {
+  const float mean = sum * rcnt;
+  const float var = fmaxf(fmaf(-mean, mean, sumsq * rcnt), 0.f);
+  sc = gamma * rsqrtf(var + eps);
+  sh = fmaf(-mean, sc, beta);
+}
+
 __device__ __forceinline__ uint4 pack8_bf16(const float *y) {
   return make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7]));
 }
@@ -243,20 +255,15 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
               for (int c = 0; c < 8; c++) { red[(rb * 8 + warp) * 16 + c] = s[c]; red[(rb * 8 + warp) * 16 + 8 + c] = q[c]; }
             }
             EPI_BAR_SYNC();
-            const float cnt = t == 3 ? 4096.f : 1024.f;
+            const float rcnt = t == 3 ? 1.f / 4096.f : 1.f / 1024.f;   // sample sizes are powers of two: exact
             const int gofs = t == 3 ? F_G64 : F_G1, bofs = t == 3 ? F_B64 : F_B1;
             float sc[8], sh[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-              double ts = 0.0, tq = 0.0;
+              float ts = 0.f, tq = 0.f;
 #pragma unroll
-              for (int k = 0; k < 4; k++) { ts += (double)red[(rb * 8 + h * 4 + k) * 16 + c]; tq += (double)red[(rb * 8 + h * 4 + k) * 16 + 8 + c]; }
-              const double mean = ts / cnt;
-              double var = tq / cnt - mean * mean;
-              var = var < 0.0 ? 0.0 : var;
-              const double inv = (double)__ldg(fp + gofs + 8 * h + c) * rsqrt(var + 1e-5 * 255.0 * 255.0);
-              sc[c] = (float)inv;
-              sh[c] = (float)((double)__ldg(fp + bofs + 8 * h + c) - mean * inv);
+              for (int k = 0; k < 4; k++) { ts += red[(rb * 8 + h * 4 + k) * 16 + c]; tq += red[(rb * 8 + h * 4 + k) * 16 + 8 + c]; }
+              bn_scale_shift(ts, tq, rcnt, 1e-5f * 255.f * 255.f, __ldg(fp + gofs + 8 * h + c), __ldg(fp + bofs + 8 * h + c), sc[c], sh[c]);
             }
             rb ^= 1;
             uint8_t *cbase = cat + (size_t)ctu * CAT_BYTES;
@@ -426,14 +433,11 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 #pragma unroll
         for (int c = 0; c < 8; c++) {
           const int cl = (chunk & 3) * 8 + c;   // channel index inside this half's 32
-          double a = 0.0, bq = 0.0;
+          float a = 0.f, bq = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; k++) { a += (double)red[(rb * 8 + h * 4 + k) * 64 + cl]; bq += (double)red[(rb * 8 + h * 4 + k) * 64 + 32 + cl]; }
-          const double mean = a / 256.0;
-          double var = bq / 256.0 - mean * mean;
-          var = var < 0.0 ? 0.0 : var;
-          const double inv = (double)__ldg(fp + F_G2 + 8 * chunk + c) * rsqrt(var + 1e-5);
-          const float sc = (float)inv, sh = (float)((double)__ldg(fp + F_B2 + 8 * chunk + c) - mean * inv);
+          for (int k = 0; k < 4; k++) { a += red[(rb * 8 + h * 4 + k) * 64 + cl]; bq += red[(rb * 8 + h * 4 + k) * 64 + 32 + cl]; }
+          float sc, sh;
+          bn_scale_shift(a, bq, 1.f / 256.f, 1e-5f, __ldg(fp + F_G2 + 8 * chunk + c), __ldg(fp + F_B2 + 8 * chunk + c), sc, sh);
           y0[c] = fmaxf(fmaf(w0[c], sc, sh), 0.f);
           y1[c] = fmaxf(fmaf(w1[c], sc, sh), 0.f);
         }
@@ -562,12 +566,8 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
       rb ^= 1;
 #pragma unroll
       for (int smp = 0; smp < 4; smp++) {
-        const double ts = (double)s[smp] + (double)ro[smp * 128 + c], tq = (double)q[smp] + (double)ro[(4 + smp) * 128 + c];
-        const double mean = ts / 64.0;
-        double var = tq / 64.0 - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        const double inv = (double)gam * rsqrt(var + 1e-5);
-        const float sc = (float)inv, sh = (float)((double)bet - mean * inv);
+        float sc, sh;
+        bn_scale_shift(s[smp] + ro[smp * 128 + c], q[smp] + ro[(4 + smp) * 128 + c], 1.f / 64.f, 1e-5f, gam, bet, sc, sh);
         float yv[8];
 #pragma unroll
         for (int pr = 0; pr < 2; pr++)
@@ -597,7 +597,7 @@ static_assert(K4_LG + 128 * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in t
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix,
-        uint8_t *__restrict__ labels, float *__restrict__ logits_out) {
+        uint8_t *__restrict__ labels, float *__restrict__ logits_out, uint32_t *__restrict__ ctu_cnt) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
@@ -740,6 +740,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
       uint32_t *pw = reinterpret_cast<uint32_t *>(&pk);
       for (int i = 0; i < 4; i++) pw[i] = lab[4 * i] | (lab[4 * i + 1] << 8) | (lab[4 * i + 2] << 16) | (lab[4 * i + 3] << 24);
       *reinterpret_cast<uint4 *>(labels + (size_t)ctu * 16) = pk;
+      if (ctu_cnt) ctu_cnt[ctu] = ctu_plan_counts(lab, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H);
     }
   }
   fence_before_sync();
@@ -789,12 +790,12 @@ inline int tc_configure(std::string &err) {
 
 // Queue the four CNN kernels of one frame.  Returns the number of kernels launched.
 inline int tc_launch(const TcParams &p, const uint8_t *Y, const uint8_t *U, const uint8_t *V, FrameGeom g, int pitch, int cpitch,
-                     int boundary_fix, uint8_t *labels, float *logits, int num_sms, cudaStream_t st) {
+                     int boundary_fix, uint8_t *labels, float *logits, uint32_t *ctu_cnt, int num_sms, cudaStream_t st) {
   const int grid = g.nctu < num_sms ? g.nctu : num_sms;
   k_tc_l1<<<grid, TC_THREADS, K1_SMEM, st>>>(Y, U, V, g, pitch, cpitch, p.blob, p.cat);
   k_tc_conv2<<<grid, TC_THREADS, K2_SMEM, st>>>(g, p.blob, p.cat, p.a2);
   k_tc_conv3<<<grid, TC_THREADS, K3_SMEM, st>>>(g, p.blob, p.a2, p.feats, p.npad);
-  k_tc_fc<<<p.npad / 128, TC_THREADS, K4_SMEM, st>>>(g, p.blob, p.feats, p.npad, boundary_fix, labels, logits);
+  k_tc_fc<<<p.npad / 128, TC_THREADS, K4_SMEM, st>>>(g, p.blob, p.feats, p.npad, boundary_fix, labels, logits, ctu_cnt);
   return 4;
 }
 

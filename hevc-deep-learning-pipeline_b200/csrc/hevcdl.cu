@@ -28,6 +28,9 @@ struct Slot {
   uint8_t *dLabels = nullptr;
   float *dLogits = nullptr;
   int *dCtuOff = nullptr;
+  uint32_t *dCtuCnt = nullptr;         // per-CTU npu | nitems << 16, written by the label kernel
+  int *dCtrl = nullptr;                // [0] work counter, [1] item count (k_rmd_plan / k_rmd_items)
+  RmdItem *dItems = nullptr;
   hevcdl_pu *dPus = nullptr;
   uint32_t *dSatd = nullptr;
   uint8_t *dCand = nullptr;
@@ -58,6 +61,7 @@ struct hevcdl_ctx {
   Fp32Params fp{};
   TcParams tc{};
   int numSMs = 0;
+  int rmdBlocks = 0;                   // persistent grid of k_rmd_items: resident blocks per SM x SMs
   std::string err;
   hevcdl_stats_t stats{};
   // scratch for hevcdl_rmd_exact
@@ -153,6 +157,10 @@ int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
   CK(cudaMalloc(&s.dLogits, (size_t)g.nctu * 64 * sizeof(float)));
   CK(cudaMalloc(&s.dCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
   CK(cudaMemset(s.dCtuOff, 0, ((size_t)g.nctu + 1) * sizeof(int)));
+  CK(cudaMalloc(&s.dCtuCnt, (size_t)g.nctu * sizeof(uint32_t)));
+  CK(cudaMalloc(&s.dCtrl, 2 * sizeof(int)));
+  CK(cudaMemset(s.dCtrl, 0, 2 * sizeof(int)));
+  CK(cudaMalloc(&s.dItems, (size_t)g.nctu * MAX_ITEMS_CTU * sizeof(RmdItem)));
   CK(cudaMalloc(&s.dPus, ctx->puCap * sizeof(hevcdl_pu)));
   CK(cudaMalloc(&s.dSatd, ctx->puCap * 35 * sizeof(uint32_t)));
   CK(cudaMalloc(&s.dCand, ctx->puCap * 8));
@@ -189,20 +197,20 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot &s, bool timed) {
   if (timed) cudaEventRecord(s.evT0, ctx->stream);
   if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
     launches += tc_launch(ctx->tc, s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, s.dLabels,
-                          s.dLogits, ctx->numSMs, ctx->stream);
+                          s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr, ctx->numSMs, ctx->stream);
   } else {
     const int grid = g.nctu < 4 * ctx->numSMs ? g.nctu : 4 * ctx->numSMs;
     k_cnn_fp32<<<grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream>>>(s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch,
-                                                                    ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits);
+                                                                    ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits,
+                                                                    ctx->cfg.rmd ? s.dCtuCnt : nullptr);
     launches++;
   }
   if (timed) cudaEventRecord(s.evT1, ctx->stream);
   if (ctx->cfg.rmd) {
-    k_enum_pus<<<1, 1024, 0, ctx->stream>>>(s.dLabels, gd, s.dCtuOff);
-    const int grid = g.nctu < 8 * ctx->numSMs ? g.nctu : 8 * ctx->numSMs;
-    k_rmd_batched<<<grid, RMD_THREADS, sizeof(RmdSmem), ctx->stream>>>(s.dY, gd, ctx->pitch, s.dLabels, s.dCtuOff, s.dPus,
-                                                                      s.dSatd, s.dCand);
-    launches += 2;
+    k_rmd_plan<<<(g.nctu + 7) / 8, 256, 0, ctx->stream>>>(s.dLabels, s.dCtuCnt, gd, s.dCtuOff, s.dPus, s.dItems, s.dSatd, s.dCtrl);
+    k_rmd_items<<<ctx->rmdBlocks, RMD_WARPS * 32, 0, ctx->stream>>>(s.dY, gd, ctx->pitch, s.dPus, s.dItems, s.dCtrl, s.dSatd);
+    k_rmd_rank<<<2 * ctx->numSMs, 256, 0, ctx->stream>>>(s.dCtuOff, g.nctu, s.dPus, s.dSatd, s.dCand);
+    launches += 3;
   }
   if (timed) cudaEventRecord(s.evT2, ctx->stream);
   return launches;
@@ -350,8 +358,16 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   if ((rc = load_weights(ctx))) return fail(rc);
   ctx->cfg.weights_path = nullptr;
   if (cu(cudaFuncSetAttribute(k_cnn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_BYTES), "smem attr") ||
-      cu(cudaFuncSetAttribute(k_rmd_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RmdSmem)), "smem attr"))
+      cu(cudaFuncSetAttribute(k_rmd_items, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout"))
     return fail(HEVCDL_E_CUDA);
+  {
+    int per_sm = 0;
+    if (cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rmd_items, RMD_WARPS * 32, 0), "occupancy") || per_sm < 1) {
+      if (ctx->err.empty()) ctx->err = "k_rmd_items does not fit on an SM";
+      return fail(HEVCDL_E_CUDA);
+    }
+    ctx->rmdBlocks = per_sm * ctx->numSMs;
+  }
   if ((rc = tc_configure(ctx->err))) return fail(rc);
   ctx->slots.resize(ctx->cfg.slots);
   for (auto &s : ctx->slots)
@@ -367,7 +383,7 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
   if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
   for (auto &s : ctx->slots) {
     cudaFree(s.dY); cudaFree(s.dLabels); cudaFree(s.dLogits); cudaFree(s.dCtuOff);
-    cudaFree(s.dPus); cudaFree(s.dSatd); cudaFree(s.dCand);
+    cudaFree(s.dPus); cudaFree(s.dSatd); cudaFree(s.dCand); cudaFree(s.dCtuCnt); cudaFree(s.dCtrl); cudaFree(s.dItems);
     cudaFreeHost(s.hPlanes); cudaFreeHost(s.hLabels); cudaFreeHost(s.hLogits); cudaFreeHost(s.hCtuOff);
     cudaFreeHost(s.hPus); cudaFreeHost(s.hSatd); cudaFreeHost(s.hCand);
     if (s.evLabels) cudaEventDestroy(s.evLabels);

@@ -16,12 +16,7 @@
 
 namespace hevcdl {
 
-constexpr int RMD_THREADS = 256;
 constexpr int MAX_PU_CTU = 320;                 // 64 8x8 CUs x (1 + 4 NxN PUs)
-constexpr int TILE_P = 144;                     // staged luma pitch: x0-16 .. x0+127
-constexpr int TILE_H = 65;                      // y0-1 .. y0+63
-constexpr int LINE_POOL = 2 * (64 * 33 + 256 * 17);  // worst case: unfiltered + filtered lines of a CTU
-constexpr int MAX_SLABS = 64 * 18 * 2;          // 64 8x8 CUs x (2Nx2N + NxN) x 36 units / 2
 
 __device__ __forceinline__ int zidx4(int ux, int uy) {   // z-order of a 4x4 unit in a CTU (TComRom.cpp:284)
   int z = 0;
@@ -38,96 +33,6 @@ __device__ __forceinline__ bool unit_available(int xn, int yn, int xc, int yc, i
   const int on = ((yn >> 6) * ctu_w + (xn >> 6)) * 256 + zidx4((xn & 63) >> 2, (yn & 63) >> 2);
   const int oc = ((yc >> 6) * ctu_w + (xc >> 6)) * 256 + zidx4((xc & 63) >> 2, (yc & 63) >> 2);
   return on < oc;
-}
-
-// ---- PU enumeration ------------------------------------------------------------------------
-// Visits the pruned quadtree of one CTU exactly as TEncCu::xCompressCU does (HM
-// TLibEncoder/TEncCu.cpp:496-520: evaluate a CU only where label == depth, descend only where
-// label > depth; :574-576 CUs crossing the picture edge are never evaluated; :929-946 children
-// starting outside the picture are skipped; :819-826 8x8 CUs also try NxN = four 4x4 PUs).
-// emit == nullptr: count only.
-__device__ inline int enum_ctu_pus(const uint8_t *label, int ctu, int ctu_x, int ctu_y, int W, int H, hevcdl_pu *emit) {
-  int cnt = 0;
-  // explicit z-order walk: depth-3 index i3 in 0..63 enumerates 8x8 blocks in z-order
-  for (int i3 = 0; i3 < 64;) {
-    // position of this 8x8 block
-    int bx = 0, by = 0;
-#pragma unroll
-    for (int b = 0; b < 3; b++) { bx |= ((i3 >> (2 * b)) & 1) << b; by |= ((i3 >> (2 * b + 1)) & 1) << b; }
-    const int x = ctu_x * 64 + bx * 8, y = ctu_y * 64 + by * 8;
-    // largest aligned CU starting here: depth d is possible iff i3 % (64 >> 2d) == 0
-    int step = 1;
-    bool done = false;
-    for (int d = 0; d < 4 && !done; d++) {
-      const int span = 64 >> (2 * d);             // number of 8x8 blocks covered by a depth-d CU
-      if (i3 % span) continue;
-      const int size = 64 >> d;
-      if (x >= W || y >= H) { step = span; done = true; break; }   // whole CU outside: skipped
-      const int p = label[4 * ((y & 63) >> 4) + ((x & 63) >> 4)];
-      const bool boundary = (x + size > W) || (y + size > H);
-      if (p == d && !boundary) {
-        if (emit) emit[cnt] = hevcdl_pu{(uint16_t)x, (uint16_t)y, (uint8_t)size, 0, (uint16_t)ctu};
-        cnt++;
-        if (d == 3) {
-          for (int k = 0; k < 4; k++) {
-            if (emit) emit[cnt] = hevcdl_pu{(uint16_t)(x + (k & 1) * 4), (uint16_t)(y + (k >> 1) * 4), 4, (uint8_t)(k + 1), (uint16_t)ctu};
-            cnt++;
-          }
-        }
-        step = span; done = true;
-      } else if (p > d && d < 3) {
-        continue;                                  // descend: try the next depth at the same origin
-      } else {
-        step = span; done = true;                  // pruned: nothing evaluated inside this CU
-      }
-    }
-    i3 += step;
-  }
-  return cnt;
-}
-
-// per-CTU PU counts -> exclusive offsets (one block; nctu <= 8160 at 8K).  The descriptors themselves are
-// written by k_rmd_batched, which enumerates its CTU again with one thread per 8x8 position.
-__global__ void __launch_bounds__(1024, 1)
-k_enum_pus(const uint8_t *__restrict__ labels, FrameGeom geo, int *__restrict__ ctu_off /* nctu+1 */) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < geo.nctu; base += blockDim.x) {
-    const int ctu = base + threadIdx.x;
-    int cnt = 0;
-    if (ctu < geo.nctu) {
-      uint8_t lab[16];
-      *reinterpret_cast<uint4 *>(lab) = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
-      cnt = enum_ctu_pus(lab, ctu, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H, nullptr);
-    }
-    int v = cnt;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += t;
-    }
-    if (lane == 31) warp_tot[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      int t = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += u;
-      }
-      warp_tot[lane] = t;
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    if (ctu < geo.nctu) ctu_off[ctu] = carry + (warp ? warp_tot[warp - 1] : 0) + v - cnt;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[31];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) ctu_off[geo.nctu] = carry_s;
 }
 
 // ---- reference samples ----------------------------------------------------------------------
@@ -289,28 +194,7 @@ __device__ inline int cand_list(const uint32_t *satd, const uint32_t *bits, doub
 
 __device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
 
-// ---- K6 (batched, references taken from the staged picture itself) ---------------------------
-// Work decomposition: a "unit" is one 8x8 block of one PU for one mode (for the four 4x4 PUs of an
-// 8x8 CU: the CU's 8x8 area for one mode, each quadrant predicted from its own PU's references);
-// a warp processes "slabs" of two units.  Each lane predicts two neighbouring pixels per unit
-// with one packed 16-bit interpolation, forms the residual as an exact fp16 pair, and the 2-D
-// Hadamard transform of both units is two chained mma.sync (A = diag(H8,H8) or diag(H4 x4), entries
-// +-1): stage 1 gives H*D (|v| <= 2040, exact in fp16), the accumulator fragment re-read as the
-// next B operand is its transpose, stage 2 gives (H*D*H^T)^T (|v| <= 16320, exact in fp32).
-// Sum of magnitudes and the per-block rounding are those of TComRdCost.cpp:1549-1750.
-struct RmdSmem {
-  uint8_t tile[TILE_H * TILE_P];                // luma rows y0-1..y0+63, cols x0-16..x0+127
-  int16_t lines[LINE_POOL + 8];
-  uint32_t satd[MAX_PU_CTU * 35];
-  hevcdl_pu pu[MAX_PU_CTU];
-  int line_off[MAX_PU_CTU + 1];
-  int unit_off[MAX_PU_CTU + 1];
-  int16_t dc[MAX_PU_CTU];
-  uint8_t avail[RMD_THREADS / 32][68];
-  int8_t src[RMD_THREADS / 32][68];
-  uint16_t slab_pu[MAX_SLABS];                  // PU owning each slab (slabs never straddle PUs: unit counts are padded to even)
-  int npu_w0;
-};
+// ---- device helpers of the batched path ----------------------------------------------------------
 
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                               uint32_t b1) {
@@ -424,23 +308,409 @@ __device__ __forceinline__ uint32_t predict_pair_k(const ModeK &k, int X, int Yc
   }
   return predict_pair(k.c, k.u, k.n, k.lg, k.mode, X, Yc, k.dc) | 0x64006400u;
 }
-// Residual pair (original - prediction) as an exact half2; org points at the first pixel in the staged tile.
-__device__ __forceinline__ uint32_t resid_pair(const uint8_t *org, bool hor, uint32_t Pm) {
+// Residual pair (original - prediction) as an exact half2; org points at the first pixel in the staged block (row pitch opitch).
+__device__ __forceinline__ uint32_t resid_pair(const uint8_t *org, int opitch, bool hor, uint32_t Pm) {
   uint32_t Om;
   if (!hor) Om = __byte_perm((uint32_t)*reinterpret_cast<const uint16_t *>(org), 0x64u, 0x4140);   // 0x64 b1 0x64 b0
-  else Om = ((uint32_t)org[0] | ((uint32_t)org[TILE_P] << 16)) | 0x64006400u;
+  else Om = ((uint32_t)org[0] | ((uint32_t)org[opitch] << 16)) | 0x64006400u;
   const __half2 d = __hsub2(*reinterpret_cast<__half2 *>(&Om), *reinterpret_cast<__half2 *>(&Pm));
   return *reinterpret_cast<const uint32_t *>(&d);
 }
 
-__global__ void __launch_bounds__(RMD_THREADS, 2)
-k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uint8_t *__restrict__ labels,
-              const int *__restrict__ ctu_off, hevcdl_pu *__restrict__ pus_out, uint32_t *__restrict__ satd_out,
-              uint8_t *__restrict__ cand_out) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  RmdSmem &S = *reinterpret_cast<RmdSmem *>(smraw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+// ---- K6 (batched, references taken from the original picture) --------------------------------
+// Three launches per frame, no block-level barriers in the hot kernel:
+//
+//   k_rmd_plan  : one warp per CTU walks the pruned quadtree (TEncCu.cpp:496-520) and writes the PU
+//                 descriptors in encoder visiting order plus a list of WORK ITEMS:
+//                   64x64 PU -> 16 items (quadrant x 9-mode group), 32x32 PU -> 5 items (7-mode group),
+//                   16x16 PU -> 1 item (35 modes), 8x8 CU -> 1 item (2Nx2N 8x8 + its four NxN 4x4 PUs).
+//                 Offsets come from the per-CTU counts the label kernel wrote (ctu_plan_counts()).
+//   k_rmd_items : persistent warps pull items from a global counter.  A warp stages its PU (or PU
+//                 quadrant) and its transpose in its own shared-memory slice, builds the reference
+//                 lines straight from the picture in L2, and evaluates its modes.  A "unit" is one 8x8
+//                 block for one mode; a "slab" is two units.  Each lane predicts two neighbouring
+//                 pixels per unit with one packed 16-bit interpolation, forms the residual as an exact
+//                 fp16 pair, and the 2-D Hadamard transform of both units is two chained mma.sync
+//                 (A = diag(H8,H8) or diag(H4 x4), entries +-1): stage 1 gives H*D (|v| <= 2040, exact in
+//                 fp16), the accumulator fragment re-read as the next B operand is its transpose, stage
+//                 2 gives (H*D*H^T)^T (|v| <= 16320, exact in fp32).  Sum of magnitudes and the per-block
+//                 rounding are those of TComRdCost.cpp:1549-1750.
+//                 PUs >= 16: per mode the warp first writes the mode's main reference array -- projected
+//                 side samples included (TComPrediction.cpp:278-300) -- as a table of sample PAIRS, so the
+//                 per-pixel work is two 32-bit loads and one packed multiply-add; horizontal modes run
+//                 the same code on the transposed block with the roles of the two reference arms
+//                 swapped (SATD is transpose-invariant).
+//   k_rmd_rank  : one warp per PU ranks the 35 SATDs (ties -> lower mode, TEncSearch.cpp:5562-5585).
+struct RmdItem {
+  uint32_t pu;          // index of the PU in the frame's list (kind 1: the 2Nx2N 8x8 PU; its 4x4 PUs follow)
+  uint8_t m0, m1;       // modes [m0, m1)
+  uint8_t quad;         // 64x64 PUs: 32x32 quadrant handled by this item
+  uint8_t kind;         // 0: PU >= 16 (table path), 1: 8x8 CU
+};
+constexpr int MAX_ITEMS_CTU = 64;
+constexpr int RMD_WARPS = 8;
+constexpr int ORG_P = 36;                       // row pitch of the staged block: 9 words -> conflict-free 16-bit reads
+
+// ctrl[0] = work counter of k_rmd_items, ctrl[1] = number of items of the frame
+__global__ void __launch_bounds__(256)
+k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_cnt, FrameGeom geo, int *__restrict__ ctu_off,
+           hevcdl_pu *__restrict__ pus, RmdItem *__restrict__ items, uint32_t *__restrict__ satd, int *__restrict__ ctrl) {
+  const int lane = threadIdx.x & 31, ctu = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = 0;
+  if (ctu >= geo.nctu) return;
+  uint32_t pu0 = 0, it0 = 0;
+  for (int c = lane; c < ctu; c += 32) { const uint32_t v = __ldg(ctu_cnt + c); pu0 += v & 0xFFFFu; it0 += v >> 16; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { pu0 += __shfl_xor_sync(0xffffffffu, pu0, o); it0 += __shfl_xor_sync(0xffffffffu, it0, o); }
+  if (lane == 0) {
+    ctu_off[ctu] = (int)pu0;
+    if (ctu == geo.nctu - 1) {
+      const uint32_t mine = __ldg(ctu_cnt + ctu);
+      ctu_off[geo.nctu] = (int)(pu0 + (mine & 0xFFFFu));
+      ctrl[1] = (int)(it0 + (mine >> 16));
+    }
+  }
   const int W = geo.W, H = geo.H;
+  const int x0 = (ctu % geo.ctu_w) * 64, y0 = (ctu / geo.ctu_w) * 64;
+  const uint4 pk = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
+  const uint32_t lw[4] = {pk.x, pk.y, pk.z, pk.w};
+  for (int round = 0; round < 2; round++) {
+    const int i3 = round * 32 + lane;                                  // z-order index of an 8x8 position
+    int esize = 0, ex = 0, ey = 0;
+    for (int d = 0; d < 4; d++) {
+      const int span = 64 >> (2 * d), o = i3 & ~(span - 1);
+      int bx = 0, by = 0;
+#pragma unroll
+      for (int b = 0; b < 3; b++) { bx |= ((o >> (2 * b)) & 1) << b; by |= ((o >> (2 * b + 1)) & 1) << b; }
+      const int x = x0 + bx * 8, y = y0 + by * 8, size = 64 >> d;
+      if (x >= W || y >= H) break;                                     // CU outside the picture: skipped (TEncCu.cpp:929-946)
+      const int li = 4 * ((y & 63) >> 4) + ((x & 63) >> 4);
+      const int pl = (lw[li >> 2] >> (8 * (li & 3))) & 255;
+      const bool boundary = (x + size > W) || (y + size > H);          // never evaluated (TEncCu.cpp:574-576)
+      if (pl == d && !boundary) {
+        if (o == i3) { esize = size; ex = x; ey = y; }
+        break;
+      }
+      if (!(pl > d && d < 3)) break;                                   // pruned
+    }
+    const int np = esize == 0 ? 0 : (esize == 8 ? 5 : 1);
+    const int ni = esize == 0 ? 0 : (esize == 64 ? 16 : (esize == 32 ? 5 : 1));
+    int sp = np, si = ni;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, sp, o), b = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) { sp += a; si += b; }
+    }
+    const uint32_t ppos = pu0 + sp - np, ipos = it0 + si - ni;
+    if (esize) {
+      pus[ppos] = hevcdl_pu{(uint16_t)ex, (uint16_t)ey, (uint8_t)esize, 0, (uint16_t)ctu};
+      if (esize == 8) {
+        for (int k = 0; k < 4; k++)
+          pus[ppos + 1 + k] = hevcdl_pu{(uint16_t)(ex + (k & 1) * 4), (uint16_t)(ey + (k >> 1) * 4), 4, (uint8_t)(k + 1), (uint16_t)ctu};
+        items[ipos] = RmdItem{ppos, 0, 35, 0, 1};
+      } else if (esize == 16) {
+        items[ipos] = RmdItem{ppos, 0, 35, 0, 0};
+      } else if (esize == 32) {
+        for (int k = 0; k < 5; k++) items[ipos + k] = RmdItem{ppos, (uint8_t)(7 * k), (uint8_t)(7 * k + 7), 0, 0};
+      } else {
+        for (int k = 0; k < 16; k++)
+          items[ipos + k] = RmdItem{ppos, (uint8_t)(9 * (k & 3)), (uint8_t)((k & 3) == 3 ? 35 : 9 * (k & 3) + 9), (uint8_t)(k >> 2), 0};
+        for (int m = 0; m < 35; m++) satd[(size_t)ppos * 35 + m] = 0;   // quadrant items accumulate with atomicAdd
+      }
+    }
+    pu0 += __shfl_sync(0xffffffffu, sp, 31);
+    it0 += __shfl_sync(0xffffffffu, si, 31);
+  }
+}
+
+// per-warp shared-memory slice of k_rmd_items
+struct RmdWarp {
+  uint8_t org[32 * ORG_P];        // the PU (or 32x32 quadrant of a 64x64 PU), row pitch ORG_P
+  uint8_t orgT[32 * ORG_P];       // its transpose (horizontal modes)
+  int16_t line[2][260];           // [0] unfiltered, [1] filtered reference line (kind 1: see item_small)
+  uint32_t tab[200];              // pair table of the current mode: tab[k + n] = ext[k] | ext[k+1] << 16
+  uint8_t avail[68];
+  int8_t src[68];
+  int16_t dcs[8];
+};
+
+// Reference line of one PU from the ORIGINAL picture, with HM's availability rule and substitution scan
+// (TComPattern.cpp:326-543); one warp.  line: 4n+1 entries.
+__device__ __forceinline__ void build_line_warp(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, int W, int H, int ctu_w,
+                                                int px, int py, int n, int16_t *line, int lane) {
+  const int nu = n >> 2;                        // units: [0,2nu) left bottom-up, 2nu corner, (2nu, 4nu] above
+  for (int u = lane; u <= 4 * nu; u += 32) {
+    int xn, yn;
+    if (u < 2 * nu) { xn = px - 1; yn = py + (2 * nu - 1 - u) * 4; }
+    else if (u == 2 * nu) { xn = px - 1; yn = py - 1; }
+    else { xn = px + (u - 2 * nu - 1) * 4; yn = py - 1; }
+    S.avail[u] = unit_available(xn, yn, px, py, W, H, ctu_w);
+  }
+  __syncwarp();
+  for (int u = lane; u <= 4 * nu; u += 32) {
+    int s = -1;
+    for (int v = u; v >= 0; v--) if (S.avail[v]) { s = v; break; }
+    if (s < 0) for (int v = u + 1; v <= 4 * nu; v++) if (S.avail[v]) { s = v; break; }
+    S.src[u] = (int8_t)s;
+  }
+  __syncwarp();
+  auto sample = [&](int i) -> int {             // picture sample at line index i (only called for available units)
+    int gx, gy;
+    if (i < 2 * n) { gx = px - 1; gy = py + 2 * n - 1 - i; }
+    else if (i == 2 * n) { gx = px - 1; gy = py - 1; }
+    else { gx = px + i - 2 * n - 1; gy = py - 1; }
+    return Y[(size_t)gy * pitch + gx];
+  };
+  for (int i = lane; i < 4 * n + 1; i += 32) {
+    const int u = i < 2 * n ? (i >> 2) : (i == 2 * n ? 2 * nu : 2 * nu + 1 + ((i - 2 * n - 1) >> 2));
+    const int s = S.src[u];
+    int v;
+    if (s < 0) v = 128;
+    else if (s == u) v = sample(i);
+    else {
+      // last sample (scan order) of an earlier unit, first sample of a later one
+      const int firsti = s < 2 * nu ? 4 * s : (s == 2 * nu ? 2 * n : 2 * n + 1 + 4 * (s - 2 * nu - 1));
+      const int lasti = s == 2 * nu ? 2 * n : firsti + 3;
+      v = sample(s < u ? lasti : firsti);
+    }
+    line[i] = (int16_t)v;
+  }
+  __syncwarp();
+}
+
+// DC value of a line (TComPrediction.cpp:183-201); all lanes return it.
+__device__ __forceinline__ int line_dc_warp(const int16_t *line, int n, int lane) {
+  int sum = 0;
+  for (int i = lane; i < n; i += 32) sum += line[2 * n + 1 + i] + line[2 * n - 1 - i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  return (sum + n) / (2 * n);
+}
+
+// Sum of v[e] over the 32 lanes for e in [0,16): every lane l returns the total of element l & 15.
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int j = 0; j < n / 2; j++) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// Everything about (PU, mode) the pixel loop of the table path needs; warp-uniform.
+struct TabMode {
+  const int16_t *c, *u;     // centre of the line chosen for this mode / of the unfiltered line
+  const uint8_t *o;         // staged block to read: org (planar, DC, vertical modes) or orgT (horizontal modes)
+  int mode, angle, sg, i0, j0;
+  bool edge;
+};
+
+// PUs >= 16.  RS = side of the staged region (16: the 16x16 PU; 32: a 32x32 PU or one quadrant of a 64x64 PU).
+template <int RS>
+__device__ __forceinline__ void item_large(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
+                                           const RmdItem item, uint32_t a8, int lane, uint32_t *__restrict__ satd_out) {
+  constexpr int NB = RS / 8, LGNB = RS == 32 ? 2 : 1;
+  const int n = pu.size, px = pu.x, py = pu.y, lg = ilog2(n);
+  const int rx0 = n == 64 ? (item.quad & 1) * 32 : 0, ry0 = n == 64 ? (item.quad >> 1) * 32 : 0;
+  const int g = lane >> 2, t = lane & 3;
+  // stage the region and its transpose
+  {
+    constexpr int WPR = RS / 4;
+    const uint8_t *src = Y + (size_t)(py + ry0) * pitch + px + rx0;
+#pragma unroll
+    for (int i = lane; i < RS * WPR; i += 32) {
+      const int r = i / WPR, cw = i % WPR;
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * pitch + 4 * cw));
+      *reinterpret_cast<uint32_t *>(&S.org[r * ORG_P + 4 * cw]) = v;
+#pragma unroll
+      for (int k = 0; k < 4; k++) S.orgT[(4 * cw + k) * ORG_P + r] = (uint8_t)(v >> (8 * k));
+    }
+  }
+  build_line_warp(S, Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, n, S.line[0], lane);
+  if (n == 16 || n == 32) filter_line_warp(S.line[0], S.line[1], n, lane);
+  const int dc = line_dc_warp(S.line[0], n, lane);
+  __syncwarp();
+
+  auto setup = [&](int mode) -> TabMode {
+    TabMode M;
+    const int16_t *L = mode_uses_filter(mode, n) ? S.line[1] : S.line[0];
+    M.c = L + 2 * n; M.u = S.line[0] + 2 * n;
+    M.mode = mode; M.angle = c_mode_angle[mode];
+    const bool hor = mode >= 2 && mode < 18;
+    M.sg = hor ? -1 : 1;
+    M.o = hor ? S.orgT : S.org;
+    M.i0 = hor ? ry0 : rx0; M.j0 = hor ? rx0 : ry0;
+    M.edge = mode >= 2 && M.angle == 0 && n <= 16;
+    __syncwarp();                               // readers of the previous mode's table are done
+    if (mode >= 2) {
+      const int inv = c_mode_inv[mode];
+      const int kmin = M.angle < 0 ? ((n * M.angle) >> 5) + 1 : 1, kend = M.angle < 0 ? n + 1 : 2 * n;
+      for (int k = kmin + lane; k < kend; k += 32) {
+        const int k1 = k + 1;
+        const int e0 = k >= 0 ? M.c[M.sg * k] : M.c[-M.sg * ((128 - k * inv) >> 8)];
+        const int e1 = k1 >= 0 ? M.c[M.sg * k1] : M.c[-M.sg * ((128 - k1 * inv) >> 8)];
+        S.tab[k + n] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+      }
+    }
+    __syncwarp();
+    return M;
+  };
+  // residual pair of this lane in block blk of the region, as an exact half2
+  auto unit = [&](const TabMode &M, int blk) -> uint32_t {
+    const int xr = (blk & (NB - 1)) * 8 + 2 * t, yr = (blk >> LGNB) * 8 + g;
+    const uint32_t o16 = *reinterpret_cast<const uint16_t *>(M.o + yr * ORG_P + xr);
+    uint32_t P;
+    if (M.mode >= 2) {
+      const int i = M.i0 + xr, j = M.j0 + yr;   // i: along the main reference, j: distance from it
+      const int pos = (j + 1) * M.angle, di = pos >> 5, df = pos & 31;
+      const int kk = i + di + 1 + n;
+      const uint32_t A = S.tab[kk], B = S.tab[kk + 1];
+      P = (((32 - df) * A + df * B + 0x00100010u) >> 5) & 0x07FF07FFu;
+      if (M.edge && i == 0) {                   // pure V/H edge filter on the first column along the reference
+        const int p0 = clip255((int)(P & 0xFFFF) + ((M.c[-M.sg * (j + 1)] - M.c[0]) >> 1));
+        P = (P & 0xFFFF0000u) | (uint32_t)p0;
+      }
+    } else {
+      P = predict_pair(M.c, M.u, n, lg, M.mode, rx0 + xr, ry0 + yr, dc);
+    }
+    const uint32_t Om = __byte_perm(o16, 0x64u, 0x4140), Pm = P | 0x64006400u;   // fp16 1024+v: exact difference
+    const __half2 d = __hsub2(*reinterpret_cast<const __half2 *>(&Om), *reinterpret_cast<const __half2 *>(&Pm));
+    return *reinterpret_cast<const uint32_t *>(&d);
+  };
+  auto slab = [&](const TabMode &M, int sl, float &sA, float &sB) {
+    const uint32_t b0 = unit(M, 2 * sl), b1 = unit(M, 2 * sl + 1);
+    float c1[4], c2[4];
+    mma_f16_16816(c1, a8, 0u, 0u, a8, b0, b1);
+    mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+    sA = fabsf(c2[0]) + fabsf(c2[1]); sB = fabsf(c2[2]) + fabsf(c2[3]);
+  };
+
+  if (RS == 32) {
+    // one mode = 16 blocks = 8 slabs = one transposing reduction
+    for (int mode = item.m0; mode < item.m1; mode++) {
+      const TabMode M = setup(mode);
+      float part[16];
+#pragma unroll
+      for (int sl = 0; sl < 8; sl++) slab(M, sl, part[2 * sl], part[2 * sl + 1]);
+      const float tot = warp_transpose_sum16(part, lane);          // lane l: block l & 15
+      uint32_t v = ((uint32_t)tot + 2) >> 2;                       // per-block rounding (TComRdCost.cpp:1739-1749)
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) {
+        if (n == 64) atomicAdd(&satd_out[(size_t)item.pu * 35 + mode], v);
+        else satd_out[(size_t)item.pu * 35 + mode] = v;
+      }
+    }
+  } else {
+    // 16x16: one mode = 4 blocks = 2 slabs; four modes per transposing reduction
+    for (int mb = item.m0; mb < item.m1; mb += 4) {
+      float part[16];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        part[4 * mi] = 0.f; part[4 * mi + 1] = 0.f; part[4 * mi + 2] = 0.f; part[4 * mi + 3] = 0.f;
+        if (mb + mi < item.m1) {                                   // warp-uniform
+          const TabMode M = setup(mb + mi);
+          slab(M, 0, part[4 * mi], part[4 * mi + 1]);
+          slab(M, 1, part[4 * mi + 2], part[4 * mi + 3]);
+        }
+      }
+      const float tot = warp_transpose_sum16(part, lane);          // lane l: block (l & 3) of mode mb + ((l & 15) >> 2)
+      uint32_t v = ((uint32_t)tot + 2) >> 2;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      const int mode = mb + (lane >> 2);
+      if (lane < 16 && (lane & 3) == 0 && mode < item.m1) satd_out[(size_t)item.pu * 35 + mode] = v;
+    }
+  }
+}
+
+// One 8x8 CU: the 2Nx2N 8x8 PU and the four 4x4 PUs of its NxN trial (TEncCu.cpp:819-826).  A slab is one 8x8
+// area for two modes; in the NxN slabs every 4x4 quadrant is predicted from its own PU's references and
+// transformed with diag(H4 x4).
+__device__ __forceinline__ void item_small(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
+                                           const RmdItem item, uint32_t a8, uint32_t a4, int lane, uint32_t *__restrict__ satd_out) {
+  const int px = pu.x, py = pu.y;
+  const int g = lane >> 2, t = lane & 3;
+  if (lane < 16) {
+    const int r = lane >> 1, cw = lane & 1;
+    *reinterpret_cast<uint32_t *>(&S.org[r * ORG_P + 4 * cw]) =
+        __ldg(reinterpret_cast<const uint32_t *>(Y + (size_t)(py + r) * pitch + px + 4 * cw));
+  }
+  // lines: 8x8 at line[0][0..33), its filtered copy at [34..67) (make_modek's convention), 4x4 PU k at [68 + 20k ..)
+  int16_t *L = S.line[0];
+  build_line_warp(S, Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, 8, L, lane);
+  filter_line_warp(L, L + 34, 8, lane);
+  { const int dc = line_dc_warp(L, 8, lane); if (lane == 0) S.dcs[0] = (int16_t)dc; }
+  for (int k = 0; k < 4; k++) {
+    build_line_warp(S, Y, pitch, geo.W, geo.H, geo.ctu_w, px + (k & 1) * 4, py + (k >> 1) * 4, 4, L + 68 + 20 * k, lane);
+    const int dc = line_dc_warp(L + 68 + 20 * k, 4, lane);
+    if (lane == 0) S.dcs[1 + k] = (int16_t)dc;
+  }
+  __syncwarp();
+  const size_t p = item.pu;
+  for (int r = 0; r < 18; r++) {
+#pragma unroll
+    for (int small = 0; small < 2; small++) {
+      uint32_t bf[2] = {0u, 0u};
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int mode = 2 * r + e;
+        if (mode >= 35) continue;               // warp-uniform
+        const bool hor = mode >= 2 && mode < 18;
+        const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
+        const int sub = (uy >> 2) * 2 + (ux >> 2);
+        const ModeK k = small ? make_modek(L + 68 + 20 * sub, 4, mode, S.dcs[1 + sub]) : make_modek(L, 8, mode, S.dcs[0]);
+        const int X = small ? ux & 3 : ux, Yc = small ? uy & 3 : uy;
+        bf[e] = resid_pair(&S.org[uy * ORG_P + ux], ORG_P, hor, predict_pair_k(k, X, Yc));
+      }
+      const uint32_t a = small ? a4 : a8;
+      float c1[4], c2[4];
+      mma_f16_16816(c1, a, 0u, 0u, a, bf[0], bf[1]);
+      mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+      float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
+      if (!small) {
+        const bool upper = lane & 16;
+        float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int mode = 2 * r + (upper ? 1 : 0);
+        if ((lane & 15) == 0 && mode < 35) satd_out[p * 35 + mode] = ((uint32_t)v + 2) >> 2;
+      } else {
+        // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
+#pragma unroll
+        for (int o = 1; o <= 8; o <<= 1) {
+          if (o == 2) continue;
+          sA += __shfl_xor_sync(0xffffffffu, sA, o);
+          sB += __shfl_xor_sync(0xffffffffu, sB, o);
+        }
+        if ((lane & 13) == 0) {                 // lanes 0, 2, 16, 18
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int mode = 2 * r + e;
+            if (mode >= 35) continue;
+            // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
+            const bool hor = mode >= 2 && mode < 18;
+            const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
+            satd_out[(p + 1 + sub) * 35 + mode] = ((uint32_t)(e ? sB : sA) + 1) >> 1;   // TComRdCost.cpp:1636-1640
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RMD_WARPS * 32, 3)
+k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcdl_pu *__restrict__ pus,
+            const RmdItem *__restrict__ items, int *__restrict__ ctrl, uint32_t *__restrict__ satd_out) {
+  __shared__ __align__(16) RmdWarp smw[RMD_WARPS];
+  const int lane = threadIdx.x & 31;
+  RmdWarp &S = smw[threadIdx.x >> 5];
   const int g = lane >> 2, t = lane & 3;
   // A fragments (m16n8k16 row-major A): only the diagonal 8x8 blocks are non-zero
   uint32_t a8, a4;
@@ -451,249 +721,51 @@ k_rmd_batched(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const uin
     const bool on = (g >> 2) == (t >> 1);
     a4 = on ? (((__popc((g & 3) & (c0 & 3)) & 1) ? neg : one) | (((__popc((g & 3) & (c1 & 3)) & 1) ? neg : one) << 16)) : 0u;
   }
+  const int nitems = ctrl[1];
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(&ctrl[0], 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= nitems) break;
+    const RmdItem item = items[it];
+    const hevcdl_pu pu = pus[item.pu];
+    if (item.kind == 1) item_small(S, Y, pitch, geo, pu, item, a8, a4, lane, satd_out);
+    else if (pu.size == 16) item_large<16>(S, Y, pitch, geo, pu, item, a8, lane, satd_out);
+    else item_large<32>(S, Y, pitch, geo, pu, item, a8, lane, satd_out);
+    __syncwarp();
+  }
+}
 
-  for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x) {
-    const int first = ctu_off[ctu], npu = ctu_off[ctu + 1] - first;
-    if (npu == 0) continue;                     // uniform per block
-    const int ctu_x = ctu % geo.ctu_w, ctu_y = ctu / geo.ctu_w;
-    const int x0 = ctu_x * 64, y0 = ctu_y * 64;
-    // stage luma: 16-byte vectors, zero outside the picture (never read: availability masks it)
-    for (int i = tid; i < TILE_H * (TILE_P / 16); i += RMD_THREADS) {
-      const int r = i / (TILE_P / 16), cv = i % (TILE_P / 16);
-      const int gy = y0 - 1 + r, gx = x0 - 16 + cv * 16;
-      uint4 v = make_uint4(0, 0, 0, 0);       // rows are pitch-aligned (128 B): whole vectors stay inside the row
-      if (gy >= 0 && gy < H && gx >= 0 && gx < pitch) v = *reinterpret_cast<const uint4 *>(Y + (size_t)gy * pitch + gx);
-      *reinterpret_cast<uint4 *>(&S.tile[r * TILE_P + cv * 16]) = v;
-    }
-    // ---- PU enumeration: one thread per 8x8 position (z-order index), TEncCu.cpp:496-520 ----------
-    if (tid < 64) {
-      const int i3 = tid;
-      const uint4 pk = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
-      const uint32_t lw[4] = {pk.x, pk.y, pk.z, pk.w};
-      int emit = 0, esize = 0, ex = 0, ey = 0;
-      for (int d = 0; d < 4; d++) {
-        const int span = 64 >> (2 * d), o = i3 & ~(span - 1);
-        int bx = 0, by = 0;
+// SATD-ranked candidates of every PU: cand[8], the first 3 (size >= 16) or 8 valid, the rest 255.  Rank by
+// (satd, mode): the strict '<' insertion from the worst slot of xUpdateCandList (TEncSearch.cpp:5562-5585)
+// keeps the earlier (lower) mode ahead on equal cost.
+__global__ void __launch_bounds__(256)
+k_rmd_rank(const int *__restrict__ ctu_off, int nctu, const hevcdl_pu *__restrict__ pus, const uint32_t *__restrict__ satd,
+           uint8_t *__restrict__ cand) {
+  const int lane = threadIdx.x & 31;
+  const int npu = ctu_off[nctu];
+  for (int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < npu; p += gridDim.x * 8) {
+    const uint32_t s0 = satd[(size_t)p * 35 + lane];
+    const uint32_t s1 = lane < 3 ? satd[(size_t)p * 35 + 32 + lane] : 0xFFFFFFFFu;
+    int r0 = 0, r1 = 0;
 #pragma unroll
-        for (int b = 0; b < 3; b++) { bx |= ((o >> (2 * b)) & 1) << b; by |= ((o >> (2 * b + 1)) & 1) << b; }
-        const int x = x0 + bx * 8, y = y0 + by * 8, size = 64 >> d;
-        if (x >= W || y >= H) break;                                   // CU outside the picture: skipped
-        const int li = 4 * ((y & 63) >> 4) + ((x & 63) >> 4);
-        const int pl = (lw[li >> 2] >> (8 * (li & 3))) & 255;
-        const bool boundary = (x + size > W) || (y + size > H);
-        if (pl == d && !boundary) {
-          if (o == i3) { emit = d == 3 ? 5 : 1; esize = size; ex = x; ey = y; }
-          break;
-        }
-        if (!(pl > d && d < 3)) break;                                 // pruned
-      }
-      const uint32_t m1 = __ballot_sync(0xffffffffu, emit >= 1), m5 = __ballot_sync(0xffffffffu, emit == 5);
-      const uint32_t lt = (1u << lane) - 1;
-      int pos = __popc(m1 & lt) + 4 * __popc(m5 & lt);
-      if (tid == 31) S.npu_w0 = pos + emit;
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      if (warp == 1) pos += S.npu_w0;
-      if (emit) {
-        S.pu[pos] = hevcdl_pu{(uint16_t)ex, (uint16_t)ey, (uint8_t)esize, 0, (uint16_t)ctu};
-        if (emit == 5)
-          for (int k = 0; k < 4; k++)
-            S.pu[pos + 1 + k] = hevcdl_pu{(uint16_t)(ex + (k & 1) * 4), (uint16_t)(ey + (k >> 1) * 4), 4, (uint8_t)(k + 1), (uint16_t)ctu};
+    for (int j = 0; j < 35; j++) {
+      const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, s0, j) : __shfl_sync(0xffffffffu, s1, j - 32);
+      r0 += (cj < s0) || (cj == s0 && j < lane);
+      r1 += (cj < s1) || (cj == s1 && j < 32 + lane);
+    }
+    const int keep = num_rd_modes(pus[p].size);
+    uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t m0 = __ballot_sync(0xffffffffu, r0 == k), m1 = __ballot_sync(0xffffffffu, lane < 3 && r1 == k);
+      if (k < keep) {
+        const uint32_t mode = m0 ? (uint32_t)(__ffs(m0) - 1) : (uint32_t)(32 + __ffs(m1) - 1);
+        if (k < 4) lo = (lo & ~(0xFFu << (8 * k))) | (mode << (8 * k));
+        else hi = (hi & ~(0xFFu << (8 * (k - 4)))) | (mode << (8 * (k - 4)));
       }
     }
-    __syncthreads();
-    if (warp == 0) {                            // offsets of each PU's lines and SATD units (warp scan)
-      int lo_run = 0, uo_run = 0;
-      for (int base = 0; base < npu; base += 32) {
-        const int i = base + lane;
-        int lo = 0, uo = 0;
-        if (i < npu) {
-          const int n = S.pu[i].size;
-          lo = (4 * n + 1 + 1) & ~1;
-          if (n == 8 || n == 16 || n == 32) lo *= 2;
-          uo = n >= 16 ? 35 : ((n == 8 || S.pu[i].part == 1) ? 18 : 0);   // work items: (PU, mode) or (PU, mode pair)
-        }
-        int li = lo, ui = uo;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int a = __shfl_up_sync(0xffffffffu, li, o), b = __shfl_up_sync(0xffffffffu, ui, o);
-          if (lane >= o) { li += a; ui += b; }
-        }
-        if (i < npu) { S.line_off[i] = lo_run + li - lo; S.unit_off[i] = uo_run + ui - uo; }
-        lo_run += __shfl_sync(0xffffffffu, li, 31);
-        uo_run += __shfl_sync(0xffffffffu, ui, 31);
-      }
-      if (lane == 0) { S.line_off[npu] = lo_run; S.unit_off[npu] = uo_run; }
-    }
-    __syncthreads();
-    for (int p = warp; p < npu; p += RMD_THREADS / 32)
-      for (int sl = S.unit_off[p] + lane; sl < S.unit_off[p + 1]; sl += 32) S.slab_pu[sl] = (uint16_t)p;
-    auto pix = [&](int gx, int gy) -> int { return S.tile[(gy - (y0 - 1)) * TILE_P + gx - (x0 - 16)]; };
-
-    // reference lines: one warp per PU (HM TComPattern.cpp:326-543)
-    for (int p = warp; p < npu; p += RMD_THREADS / 32) {
-      const int n = S.pu[p].size, px = S.pu[p].x, py = S.pu[p].y;
-      const int nu = n >> 2;                    // units: [0,2nu) left bottom-up, 2nu corner, (2nu, 4nu] above
-      int16_t *line = S.lines + S.line_off[p];
-      for (int u = lane; u <= 4 * nu; u += 32) {
-        int xn, yn;
-        if (u < 2 * nu) { xn = px - 1; yn = py + (2 * nu - 1 - u) * 4; }
-        else if (u == 2 * nu) { xn = px - 1; yn = py - 1; }
-        else { xn = px + (u - 2 * nu - 1) * 4; yn = py - 1; }
-        S.avail[warp][u] = unit_available(xn, yn, px, py, W, H, geo.ctu_w);
-      }
-      __syncwarp();
-      for (int u = lane; u <= 4 * nu; u += 32) {
-        int s = -1;
-        for (int v = u; v >= 0; v--) if (S.avail[warp][v]) { s = v; break; }
-        if (s < 0) for (int v = u + 1; v <= 4 * nu; v++) if (S.avail[warp][v]) { s = v; break; }
-        S.src[warp][u] = (int8_t)s;
-      }
-      __syncwarp();
-      auto sample = [&](int i) -> int {         // picture sample at line index i
-        if (i < 2 * n) return pix(px - 1, py + 2 * n - 1 - i);
-        if (i == 2 * n) return pix(px - 1, py - 1);
-        return pix(px + i - 2 * n - 1, py - 1);
-      };
-      for (int i = lane; i < 4 * n + 1; i += 32) {
-        const int u = i < 2 * n ? (i >> 2) : (i == 2 * n ? 2 * nu : 2 * nu + 1 + ((i - 2 * n - 1) >> 2));
-        const int s = S.src[warp][u];
-        int v;
-        if (s < 0) v = 128;
-        else if (s == u) v = sample(i);
-        else {
-          // last sample (scan order) of an earlier unit, first sample of a later one
-          const int firsti = s < 2 * nu ? 4 * s : (s == 2 * nu ? 2 * n : 2 * n + 1 + 4 * (s - 2 * nu - 1));
-          const int lasti = s == 2 * nu ? 2 * n : firsti + 3;
-          v = sample(s < u ? lasti : firsti);
-        }
-        line[i] = (int16_t)v;
-      }
-      __syncwarp();
-      if (n == 8 || n == 16 || n == 32) filter_line_warp(line, line + ((4 * n + 2) & ~1), n, lane);
-      // DC value (TComPrediction.cpp:183-201)
-      int sum = 0;
-      for (int i = lane; i < n; i += 32) sum += line[2 * n + 1 + i] + line[2 * n - 1 - i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0) S.dc[p] = (int16_t)((sum + n) / (2 * n));
-      __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- SATD: work items (PU, mode) for PUs >= 16, (PU, mode pair) for 8x8 PUs and 4x4 groups ---------
-    const int nitems = S.unit_off[npu];
-    for (int item = warp; item < nitems; item += RMD_THREADS / 32) {
-      const int p = S.slab_pu[item], n = S.pu[p].size;
-      const int r = item - S.unit_off[p];
-      const uint8_t *porg = &S.tile[(S.pu[p].y - (y0 - 1)) * TILE_P + S.pu[p].x - (x0 - 16)];
-      if (n >= 16) {
-        // one mode, all 8x8 blocks of the PU, two per slab
-        const ModeK k = make_modek(S.lines + S.line_off[p], n, r, S.dc[p]);
-        const int ux = k.hor ? g : 2 * t, uy = k.hor ? 2 * t : g;
-        const int lgnb = k.lg - 3, nb = 1 << lgnb, nslabs = 1 << (2 * lgnb - 1);
-        auto slab = [&](int sl, float &sA, float &sB) {
-          uint32_t bf[2];
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int blk = 2 * sl + e;
-            const int X = ux + (blk & (nb - 1)) * 8, Yc = uy + (blk >> lgnb) * 8;
-            bf[e] = resid_pair(porg + Yc * TILE_P + X, k.hor, predict_pair_k(k, X, Yc));
-          }
-          float c1[4], c2[4];
-          mma_f16_16816(c1, a8, 0u, 0u, a8, bf[0], bf[1]);
-          mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-          sA = fabsf(c2[0]) + fabsf(c2[1]); sB = fabsf(c2[2]) + fabsf(c2[3]);
-        };
-        uint32_t acc = 0;
-        if (n == 16) {
-#pragma unroll
-          for (int sl = 0; sl < 2; sl++) {
-            float sA, sB;
-            slab(sl, sA, sB);
-            const bool upper = lane & 16;
-            float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc += ((uint32_t)v + 2) >> 2;        // lanes 0-15 hold block A's total, 16-31 block B's
-          }
-          acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        } else {
-          for (int ch = 0; ch < nslabs; ch += 16) {
-            float part[32];
-#pragma unroll
-            for (int sl = 0; sl < 16; sl++) {
-              part[2 * sl] = 0.f; part[2 * sl + 1] = 0.f;
-              if (ch + sl < nslabs) slab(ch + sl, part[2 * sl], part[2 * sl + 1]);   // warp-uniform
-            }
-            const float tot = warp_transpose_sum32(part, lane);                     // lane l: total of block l of this chunk
-            acc += ((uint32_t)tot + 2) >> 2;                                        // per-block rounding (0 for unused slots)
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        }
-        if (lane == 0) S.satd[p * 35 + r] = acc;
-      } else {
-        // two modes of one 8x8 PU, or of the four 4x4 PUs of one CU (p is part 1, parts 2-4 follow)
-        const bool small = n < 8;
-        uint32_t bf[2] = {0u, 0u};
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int mode = 2 * r + e;
-          if (mode >= 35) continue;               // warp-uniform
-          const bool hor = mode >= 2 && mode < 18;
-          const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
-          const int q = small ? p + (uy >> 2) * 2 + (ux >> 2) : p;
-          const ModeK k = make_modek(S.lines + S.line_off[q], small ? 4 : 8, mode, S.dc[q]);
-          const int X = small ? ux & 3 : ux, Yc = small ? uy & 3 : uy;
-          bf[e] = resid_pair(porg + uy * TILE_P + ux, hor, predict_pair_k(k, X, Yc));
-        }
-        const uint32_t a = small ? a4 : a8;
-        float c1[4], c2[4];
-        mma_f16_16816(c1, a, 0u, 0u, a, bf[0], bf[1]);
-        mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-        float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
-        if (!small) {
-          const bool upper = lane & 16;
-          float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          const int mode = 2 * r + (upper ? 1 : 0);
-          if ((lane & 15) == 0 && mode < 35) S.satd[p * 35 + mode] = ((uint32_t)v + 2) >> 2;
-        } else {
-          // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
-#pragma unroll
-          for (int o = 1; o <= 8; o <<= 1) {
-            if (o == 2) continue;
-            sA += __shfl_xor_sync(0xffffffffu, sA, o);
-            sB += __shfl_xor_sync(0xffffffffu, sB, o);
-          }
-          if ((lane & 13) == 0) {                 // lanes 0, 2, 16, 18
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const int mode = 2 * r + e;
-              if (mode >= 35) continue;
-              // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
-              const bool hor = mode >= 2 && mode < 18;
-              const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
-              S.satd[(p + sub) * 35 + mode] = ((uint32_t)(e ? sB : sA) + 1) >> 1;
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < npu; i += RMD_THREADS) pus_out[first + i] = S.pu[i];
-    for (int i = tid; i < npu * 35; i += RMD_THREADS) satd_out[(size_t)first * 35 + i] = S.satd[i];
-    for (int p = tid; p < npu; p += RMD_THREADS) {
-      uint8_t modes[10];
-      for (int i = 0; i < 8; i++) modes[i] = 255;
-      cand_list(&S.satd[p * 35], nullptr, 0.0, S.pu[p].size, nullptr, 0, modes);
-      uint2 pk;
-      pk.x = modes[0] | (modes[1] << 8) | (modes[2] << 16) | ((uint32_t)modes[3] << 24);
-      pk.y = modes[4] | (modes[5] << 8) | (modes[6] << 16) | ((uint32_t)modes[7] << 24);
-      *reinterpret_cast<uint2 *>(cand_out + (size_t)(first + p) * 8) = pk;
-    }
-    __syncthreads();
+    if (lane == 0) *reinterpret_cast<uint2 *>(cand + (size_t)p * 8) = make_uint2(lo, hi);
   }
 }
 
