@@ -350,7 +350,8 @@ struct RmdItem {
 };
 constexpr int MAX_ITEMS_CTU = 64;
 constexpr int RMD_WARPS = 8;
-constexpr int ORG_P = 36;                       // row pitch of the staged block: 9 words -> conflict-free 16-bit reads
+constexpr int ORG_P = 40;                       // row pitch of the staged block: 10 words -> conflict-free 16-bit reads
+constexpr int RED_P = 33;
 
 // ctrl[0] = work counter of k_rmd_items, ctrl[1] = number of items of the frame
 __global__ void __launch_bounds__(256)
@@ -430,6 +431,7 @@ struct RmdWarp {
   uint8_t orgT[32 * ORG_P];       // its transpose (horizontal modes)
   int16_t line[2][260];           // [0] unfiltered, [1] filtered reference line (kind 1: see item_small)
   uint32_t tab[200];              // pair table of the current mode: tab[k + n] = ext[k] | ext[k+1] << 16
+  float red[16][RED_P];           // per-lane block partial sums of one reduction group (16 blocks)
   uint8_t avail[68];
   int8_t src[68];
   int16_t dcs[8];
@@ -437,7 +439,7 @@ struct RmdWarp {
 
 // Reference line of one PU from the ORIGINAL picture, with HM's availability rule and substitution scan
 // (TComPattern.cpp:326-543); one warp.  line: 4n+1 entries.
-__device__ __forceinline__ void build_line_warp(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, int W, int H, int ctu_w,
+__device__ __noinline__ void build_line_warp(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, int W, int H, int ctu_w,
                                                 int px, int py, int n, int16_t *line, int lane) {
   const int nu = n >> 2;                        // units: [0,2nu) left bottom-up, 2nu corner, (2nu, 4nu] above
   for (int u = lane; u <= 4 * nu; u += 32) {
@@ -488,44 +490,31 @@ __device__ __forceinline__ int line_dc_warp(const int16_t *line, int n, int lane
   return (sum + n) / (2 * n);
 }
 
-// Sum of v[e] over the 32 lanes for e in [0,16): every lane l returns the total of element l & 15.
-__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
-    const bool up = lane & off;
-#pragma unroll
-    for (int j = 0; j < n / 2; j++) {
-      const float send = up ? v[j] : v[j + n / 2];
-      const float keep = up ? v[j + n / 2] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
-
 // Everything about (PU, mode) the pixel loop of the table path needs; warp-uniform.
 struct TabMode {
   const int16_t *c, *u;     // centre of the line chosen for this mode / of the unfiltered line
   const uint8_t *o;         // staged block to read: org (planar, DC, vertical modes) or orgT (horizontal modes)
   int mode, angle, sg, i0, j0;
-  bool edge;
+  bool slow;                // planar, DC, or pure H/V with the edge filter: generic per-pixel predictor
 };
 
-// PUs >= 16.  RS = side of the staged region (16: the 16x16 PU; 32: a 32x32 PU or one quadrant of a 64x64 PU).
-template <int RS>
+// PUs >= 16.  The staged region is the 16x16 PU, the 32x32 PU, or one 32x32 quadrant of a 64x64 PU.  Rolled loops on
+// purpose: the whole function is a few KB of code, so the warps of an SM share the instruction cache.
 __device__ __forceinline__ void item_large(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
                                            const RmdItem item, uint32_t a8, int lane, uint32_t *__restrict__ satd_out) {
-  constexpr int NB = RS / 8, LGNB = RS == 32 ? 2 : 1;
   const int n = pu.size, px = pu.x, py = pu.y, lg = ilog2(n);
+  const int rs = n == 16 ? 16 : 32;             // region side
+  const int lgnb = rs == 32 ? 2 : 1;            // log2(8x8 blocks per region row)
+  const int spm = rs == 32 ? 8 : 2;             // slabs per mode; a reduction group is 8 slabs = 16 blocks
+  const int mpg = rs == 32 ? 1 : 4;             // modes per reduction group
   const int rx0 = n == 64 ? (item.quad & 1) * 32 : 0, ry0 = n == 64 ? (item.quad >> 1) * 32 : 0;
   const int g = lane >> 2, t = lane & 3;
   // stage the region and its transpose
   {
-    constexpr int WPR = RS / 4;
+    const int wpr = rs >> 2, lgw = rs == 32 ? 3 : 2;
     const uint8_t *src = Y + (size_t)(py + ry0) * pitch + px + rx0;
-#pragma unroll
-    for (int i = lane; i < RS * WPR; i += 32) {
-      const int r = i / WPR, cw = i % WPR;
+    for (int i = lane; i < rs * wpr; i += 32) {
+      const int r = i >> lgw, cw = i & (wpr - 1);
       const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * pitch + 4 * cw));
       *reinterpret_cast<uint32_t *>(&S.org[r * ORG_P + 4 * cw]) = v;
 #pragma unroll
@@ -537,96 +526,95 @@ __device__ __forceinline__ void item_large(RmdWarp &S, const uint8_t *__restrict
   const int dc = line_dc_warp(S.line[0], n, lane);
   __syncwarp();
 
-  auto setup = [&](int mode) -> TabMode {
-    TabMode M;
-    const int16_t *L = mode_uses_filter(mode, n) ? S.line[1] : S.line[0];
-    M.c = L + 2 * n; M.u = S.line[0] + 2 * n;
-    M.mode = mode; M.angle = c_mode_angle[mode];
-    const bool hor = mode >= 2 && mode < 18;
-    M.sg = hor ? -1 : 1;
-    M.o = hor ? S.orgT : S.org;
-    M.i0 = hor ? ry0 : rx0; M.j0 = hor ? rx0 : ry0;
-    M.edge = mode >= 2 && M.angle == 0 && n <= 16;
-    __syncwarp();                               // readers of the previous mode's table are done
-    if (mode >= 2) {
-      const int inv = c_mode_inv[mode];
-      const int kmin = M.angle < 0 ? ((n * M.angle) >> 5) + 1 : 1, kend = M.angle < 0 ? n + 1 : 2 * n;
-      for (int k = kmin + lane; k < kend; k += 32) {
-        const int k1 = k + 1;
-        const int e0 = k >= 0 ? M.c[M.sg * k] : M.c[-M.sg * ((128 - k * inv) >> 8)];
-        const int e1 = k1 >= 0 ? M.c[M.sg * k1] : M.c[-M.sg * ((128 - k1 * inv) >> 8)];
-        S.tab[k + n] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+  for (int mb = item.m0; mb < item.m1; mb += mpg) {
+    for (int mi = 0; mi < mpg; mi++) {
+      const int mode = mb + mi;
+      if (mode >= item.m1) break;               // warp-uniform (last group of a 16x16 PU holds modes 32..34)
+      // ---- per-mode setup: which line, which orientation, and the table of reference sample pairs ------------
+      TabMode M;
+      {
+        const int16_t *L = mode_uses_filter(mode, n) ? S.line[1] : S.line[0];
+        M.c = L + 2 * n; M.u = S.line[0] + 2 * n;
+        M.mode = mode; M.angle = c_mode_angle[mode];
+        const bool hor = mode >= 2 && mode < 18;
+        M.sg = hor ? -1 : 1;
+        M.o = (hor ? S.orgT : S.org) + g * ORG_P + 2 * t;
+        M.i0 = (hor ? ry0 : rx0) + 2 * t; M.j0 = (hor ? rx0 : ry0) + g;
+        M.slow = mode < 2 || (M.angle == 0 && n <= 16);
+        __syncwarp();                           // readers of the previous mode's table are done
+        if (mode >= 2) {
+          const int inv = c_mode_inv[mode];
+          const int kmin = M.angle < 0 ? ((n * M.angle) >> 5) + 1 : 1, kend = M.angle < 0 ? n + 1 : 2 * n;
+          for (int k = kmin + lane; k < kend; k += 32) {
+            const int k1 = k + 1;
+            const int e0 = k >= 0 ? M.c[M.sg * k] : M.c[-M.sg * ((128 - k * inv) >> 8)];
+            const int e1 = k1 >= 0 ? M.c[M.sg * k1] : M.c[-M.sg * ((128 - k1 * inv) >> 8)];
+            S.tab[k + n] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- slabs: two horizontally adjacent 8x8 blocks each ------------------------------------------------
+#pragma unroll 2
+      for (int sl = 0; sl < spm; sl++) {
+        const int by8 = (sl >> (lgnb - 1)) * 8, bx8 = ((2 * sl) & ((1 << lgnb) - 1)) * 8;
+        const uint8_t *op = M.o + by8 * ORG_P + bx8;
+        const uint32_t oa = *reinterpret_cast<const uint16_t *>(op), ob = *reinterpret_cast<const uint16_t *>(op + 8);
+        uint32_t Pa, Pb;
+        if (!M.slow) {
+          const int pos = (M.j0 + by8 + 1) * M.angle, di = pos >> 5, df = pos & 31;   // shared by the row of blocks
+          const uint32_t *tp = S.tab + (M.i0 + bx8 + di + 1 + n);
+          const uint32_t w0 = 32 - df;
+          Pa = ((w0 * tp[0] + df * tp[1] + 0x00100010u) >> 5) & 0x07FF07FFu;
+          Pb = ((w0 * tp[8] + df * tp[9] + 0x00100010u) >> 5) & 0x07FF07FFu;
+        } else if (mode < 2) {
+          Pa = predict_pair(M.c, M.u, n, lg, mode, (rx0 + 2 * t) + bx8, (ry0 + g) + by8, dc);
+          Pb = predict_pair(M.c, M.u, n, lg, mode, (rx0 + 2 * t) + bx8 + 8, (ry0 + g) + by8, dc);
+        } else {                                // pure H/V (angle 0, no interpolation) with the edge filter (n <= 16)
+          const int i = M.i0 + bx8, j = M.j0 + by8;
+          Pa = S.tab[i + 1 + n]; Pb = S.tab[i + 9 + n];
+          if (i == 0) {
+            const int p0 = clip255((int)(Pa & 0xFFFF) + ((M.c[-M.sg * (j + 1)] - M.c[0]) >> 1));
+            Pa = (Pa & 0xFFFF0000u) | (uint32_t)p0;
+          }
+        }
+        // residuals as exact half2 (fp16 1024+v on both sides)
+        const uint32_t Oa = __byte_perm(oa, 0x64u, 0x4140), Ob = __byte_perm(ob, 0x64u, 0x4140);
+        Pa |= 0x64006400u; Pb |= 0x64006400u;
+        const __half2 da = __hsub2(*reinterpret_cast<const __half2 *>(&Oa), *reinterpret_cast<const __half2 *>(&Pa));
+        const __half2 db = __hsub2(*reinterpret_cast<const __half2 *>(&Ob), *reinterpret_cast<const __half2 *>(&Pb));
+        float c1[4], c2[4];
+        mma_f16_16816(c1, a8, 0u, 0u, a8, *reinterpret_cast<const uint32_t *>(&da), *reinterpret_cast<const uint32_t *>(&db));
+        mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+        float *rr = &S.red[(mi * spm + sl) * 2][lane];
+        rr[0] = fabsf(c2[0]) + fabsf(c2[1]);
+        rr[RED_P] = fabsf(c2[2]) + fabsf(c2[3]);
       }
     }
     __syncwarp();
-    return M;
-  };
-  // residual pair of this lane in block blk of the region, as an exact half2
-  auto unit = [&](const TabMode &M, int blk) -> uint32_t {
-    const int xr = (blk & (NB - 1)) * 8 + 2 * t, yr = (blk >> LGNB) * 8 + g;
-    const uint32_t o16 = *reinterpret_cast<const uint16_t *>(M.o + yr * ORG_P + xr);
-    uint32_t P;
-    if (M.mode >= 2) {
-      const int i = M.i0 + xr, j = M.j0 + yr;   // i: along the main reference, j: distance from it
-      const int pos = (j + 1) * M.angle, di = pos >> 5, df = pos & 31;
-      const int kk = i + di + 1 + n;
-      const uint32_t A = S.tab[kk], B = S.tab[kk + 1];
-      P = (((32 - df) * A + df * B + 0x00100010u) >> 5) & 0x07FF07FFu;
-      if (M.edge && i == 0) {                   // pure V/H edge filter on the first column along the reference
-        const int p0 = clip255((int)(P & 0xFFFF) + ((M.c[-M.sg * (j + 1)] - M.c[0]) >> 1));
-        P = (P & 0xFFFF0000u) | (uint32_t)p0;
-      }
-    } else {
-      P = predict_pair(M.c, M.u, n, lg, M.mode, rx0 + xr, ry0 + yr, dc);
-    }
-    const uint32_t Om = __byte_perm(o16, 0x64u, 0x4140), Pm = P | 0x64006400u;   // fp16 1024+v: exact difference
-    const __half2 d = __hsub2(*reinterpret_cast<const __half2 *>(&Om), *reinterpret_cast<const __half2 *>(&Pm));
-    return *reinterpret_cast<const uint32_t *>(&d);
-  };
-  auto slab = [&](const TabMode &M, int sl, float &sA, float &sB) {
-    const uint32_t b0 = unit(M, 2 * sl), b1 = unit(M, 2 * sl + 1);
-    float c1[4], c2[4];
-    mma_f16_16816(c1, a8, 0u, 0u, a8, b0, b1);
-    mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-    sA = fabsf(c2[0]) + fabsf(c2[1]); sB = fabsf(c2[2]) + fabsf(c2[3]);
-  };
-
-  if (RS == 32) {
-    // one mode = 16 blocks = 8 slabs = one transposing reduction
-    for (int mode = item.m0; mode < item.m1; mode++) {
-      const TabMode M = setup(mode);
-      float part[16];
+    // ---- block totals: lane l sums half of row (l & 15), the two halves meet through one shuffle -------------
+    {
+      const float *row = &S.red[lane & 15][(lane >> 4) * 16];
+      float acc = 0.f;
 #pragma unroll
-      for (int sl = 0; sl < 8; sl++) slab(M, sl, part[2 * sl], part[2 * sl + 1]);
-      const float tot = warp_transpose_sum16(part, lane);          // lane l: block l & 15
-      uint32_t v = ((uint32_t)tot + 2) >> 2;                       // per-block rounding (TComRdCost.cpp:1739-1749)
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) {
-        if (n == 64) atomicAdd(&satd_out[(size_t)item.pu * 35 + mode], v);
-        else satd_out[(size_t)item.pu * 35 + mode] = v;
-      }
-    }
-  } else {
-    // 16x16: one mode = 4 blocks = 2 slabs; four modes per transposing reduction
-    for (int mb = item.m0; mb < item.m1; mb += 4) {
-      float part[16];
-#pragma unroll
-      for (int mi = 0; mi < 4; mi++) {
-        part[4 * mi] = 0.f; part[4 * mi + 1] = 0.f; part[4 * mi + 2] = 0.f; part[4 * mi + 3] = 0.f;
-        if (mb + mi < item.m1) {                                   // warp-uniform
-          const TabMode M = setup(mb + mi);
-          slab(M, 0, part[4 * mi], part[4 * mi + 1]);
-          slab(M, 1, part[4 * mi + 2], part[4 * mi + 3]);
-        }
-      }
-      const float tot = warp_transpose_sum16(part, lane);          // lane l: block (l & 3) of mode mb + ((l & 15) >> 2)
-      uint32_t v = ((uint32_t)tot + 2) >> 2;
+      for (int k = 0; k < 16; k++) acc += row[k];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      uint32_t v = ((uint32_t)acc + 2) >> 2;    // per-block rounding (TComRdCost.cpp:1739-1749)
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
-      const int mode = mb + (lane >> 2);
-      if (lane < 16 && (lane & 3) == 0 && mode < item.m1) satd_out[(size_t)item.pu * 35 + mode] = v;
+      if (rs == 32) {
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if (lane == 0) {
+          if (n == 64) atomicAdd(&satd_out[(size_t)item.pu * 35 + mb], v);
+          else satd_out[(size_t)item.pu * 35 + mb] = v;
+        }
+      } else {
+        const int mode = mb + (lane >> 2);      // lanes 4m..4m+3 hold the four blocks of mode mb + m
+        if (lane < 16 && (lane & 3) == 0 && mode < item.m1) satd_out[(size_t)item.pu * 35 + mode] = v;
+      }
     }
+    __syncwarp();
   }
 }
 
@@ -705,10 +693,11 @@ __device__ __forceinline__ void item_small(RmdWarp &S, const uint8_t *__restrict
   }
 }
 
-__global__ void __launch_bounds__(RMD_WARPS * 32, 3)
+__global__ void __launch_bounds__(RMD_WARPS * 32, 4)
 k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcdl_pu *__restrict__ pus,
             const RmdItem *__restrict__ items, int *__restrict__ ctrl, uint32_t *__restrict__ satd_out) {
-  __shared__ __align__(16) RmdWarp smw[RMD_WARPS];
+  extern __shared__ __align__(16) unsigned char smraw[];
+  RmdWarp *smw = reinterpret_cast<RmdWarp *>(smraw);
   const int lane = threadIdx.x & 31;
   RmdWarp &S = smw[threadIdx.x >> 5];
   const int g = lane >> 2, t = lane & 3;
@@ -722,17 +711,18 @@ k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcd
     a4 = on ? (((__popc((g & 3) & (c0 & 3)) & 1) ? neg : one) | (((__popc((g & 3) & (c1 & 3)) & 1) ? neg : one) << 16)) : 0u;
   }
   const int nitems = ctrl[1];
-  for (;;) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(&ctrl[0], 1);
-    it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= nitems) break;
+  int it = 0;
+  if (lane == 0) it = atomicAdd(&ctrl[0], 1);
+  it = __shfl_sync(0xffffffffu, it, 0);
+  while (it < nitems) {
+    int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&ctrl[0], 1);    // claim the next item now: its latency hides behind this one
     const RmdItem item = items[it];
     const hevcdl_pu pu = pus[item.pu];
     if (item.kind == 1) item_small(S, Y, pitch, geo, pu, item, a8, a4, lane, satd_out);
-    else if (pu.size == 16) item_large<16>(S, Y, pitch, geo, pu, item, a8, lane, satd_out);
-    else item_large<32>(S, Y, pitch, geo, pu, item, a8, lane, satd_out);
+    else item_large(S, Y, pitch, geo, pu, item, a8, lane, satd_out);
     __syncwarp();
+    it = __shfl_sync(0xffffffffu, nxt, 0);
   }
 }
 

@@ -45,6 +45,11 @@ def main():
     ti = sum(a["inst"] for a in agg.values()) or 1
     ts = sum(a["samp"] for a in agg.values()) or 1
     print("kernel %s: %d warp instructions, %d samples" % (kern, ti, ts))
+    tot = defaultdict(int)
+    for a in agg.values():
+        for k, v in a["stall"].items():
+            tot[k] += v
+    print("stall samples: " + ", ".join("%s %.1f%%" % (k, 100.0 * v / ts) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:10]))
     print("| file:line | inst %% | samples %% | smem excess wavefronts | top stalls | source |\n|---|---|---|---|---|---|")
     for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1]["samp"])[:top]:
         st = ", ".join("%s %d" % kv for kv in sorted(a["stall"].items(), key=lambda kv: -kv[1])[:3])
