@@ -89,31 +89,32 @@ __device__ __forceinline__ void logits_to_labels(const float *lg, uint8_t *label
 }
 
 // PU and work-item counts of one CTU, closed form of the walk in k_rmd_plan (rmd.cuh) (one thread; called by the
-// label kernels).  Returns npu | nitems << 16.
+// label kernels).  Returns npu | nbig << 16 | nsmall << 20 (big items: 32x32 PUs and 64x64 quadrants;
+// small items: 16x16 PUs and 8x8 CUs).
 __device__ inline uint32_t ctu_plan_counts(const uint8_t *lab, int ctu_x, int ctu_y, int W, int H) {
   const int x0 = ctu_x * 64, y0 = ctu_y * 64;
-  if (lab[0] == 0) return (x0 + 64 <= W && y0 + 64 <= H) ? (1u | (16u << 16)) : 0u;
-  uint32_t npu = 0, nit = 0;
+  if (lab[0] == 0) return (x0 + 64 <= W && y0 + 64 <= H) ? (1u | (4u << 16)) : 0u;
+  uint32_t npu = 0, nbig = 0, nsm = 0;
   for (int q = 0; q < 4; q++) {
     const int qx = x0 + (q & 1) * 32, qy = y0 + (q >> 1) * 32;
     if (qx >= W || qy >= H) continue;
     const int lq = lab[8 * (q >> 1) + 2 * (q & 1)];
-    if (lq == 1) { if (qx + 32 <= W && qy + 32 <= H) { npu += 1; nit += 5; } continue; }
+    if (lq == 1) { if (qx + 32 <= W && qy + 32 <= H) { npu += 1; nbig += 1; } continue; }
     if (lq < 1) continue;
     for (int s = 0; s < 4; s++) {
       const int bx = qx + (s & 1) * 16, by = qy + (s >> 1) * 16;
       if (bx >= W || by >= H) continue;
       const int l = lab[4 * ((by & 63) >> 4) + ((bx & 63) >> 4)];
-      if (l == 2) { if (bx + 16 <= W && by + 16 <= H) { npu += 1; nit += 1; } continue; }
+      if (l == 2) { if (bx + 16 <= W && by + 16 <= H) { npu += 1; nsm += 1; } continue; }
       if (l < 2) continue;
       for (int e = 0; e < 4; e++) {
         const int ex = bx + (e & 1) * 8, ey = by + (e >> 1) * 8;
         if (ex >= W || ey >= H) continue;
-        if (l == 3) { npu += 5; nit += 1; }       // W, H are multiples of 8: an 8x8 CU never straddles the edge
+        if (l == 3) { npu += 5; nsm += 1; }       // W, H are multiples of 8: an 8x8 CU never straddles the edge
       }
     }
   }
-  return npu | (nit << 16);
+  return npu | (nbig << 16) | (nsm << 20);
 }
 
 }  // namespace hevcdl

@@ -207,10 +207,10 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot &s, bool timed) {
   }
   if (timed) cudaEventRecord(s.evT1, ctx->stream);
   if (ctx->cfg.rmd) {
-    k_rmd_plan<<<(g.nctu + 7) / 8, 256, 0, ctx->stream>>>(s.dLabels, s.dCtuCnt, gd, s.dCtuOff, s.dPus, s.dItems, s.dSatd, s.dCtrl);
-    k_rmd_items<<<ctx->rmdBlocks, RMD_WARPS * 32, RMD_WARPS * sizeof(RmdWarp), ctx->stream>>>(s.dY, gd, ctx->pitch, s.dPus, s.dItems, s.dCtrl, s.dSatd);
-    k_rmd_rank<<<2 * ctx->numSMs, 256, 0, ctx->stream>>>(s.dCtuOff, g.nctu, s.dPus, s.dSatd, s.dCand);
-    launches += 3;
+    k_rmd_plan<<<(g.nctu + 7) / 8, 256, 0, ctx->stream>>>(s.dLabels, s.dCtuCnt, gd, ctx->rmdBlocks, s.dCtuOff, s.dPus, s.dItems, s.dSatd,
+                                                          s.dCand, s.dCtrl);
+    k_rmd_items<<<ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream>>>(s.dY, gd, ctx->pitch, s.dPus, s.dItems, s.dCtrl, s.dSatd, s.dCand);
+    launches += 2;
   }
   if (timed) cudaEventRecord(s.evT2, ctx->stream);
   return launches;
@@ -358,12 +358,11 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   if ((rc = load_weights(ctx))) return fail(rc);
   ctx->cfg.weights_path = nullptr;
   if (cu(cudaFuncSetAttribute(k_cnn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_BYTES), "smem attr") ||
-      cu(cudaFuncSetAttribute(k_rmd_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RMD_WARPS * sizeof(RmdWarp))), "smem attr") ||
       cu(cudaFuncSetAttribute(k_rmd_items, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout"))
     return fail(HEVCDL_E_CUDA);
   {
     int per_sm = 0;
-    if (cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rmd_items, RMD_WARPS * 32, RMD_WARPS * sizeof(RmdWarp)), "occupancy") || per_sm < 1) {
+    if (cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rmd_items, RMD_BW * 32, 0), "occupancy") || per_sm < 1) {
       if (ctx->err.empty()) ctx->err = "k_rmd_items does not fit on an SM";
       return fail(HEVCDL_E_CUDA);
     }

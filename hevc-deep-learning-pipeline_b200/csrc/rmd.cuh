@@ -319,59 +319,74 @@ __device__ __forceinline__ uint32_t resid_pair(const uint8_t *org, int opitch, b
 
 
 // ---- K6 (batched, references taken from the original picture) --------------------------------
-// Three launches per frame, no block-level barriers in the hot kernel:
+// Two launches per frame:
 //
 //   k_rmd_plan  : one warp per CTU walks the pruned quadtree (TEncCu.cpp:496-520) and writes the PU
-//                 descriptors in encoder visiting order plus a list of WORK ITEMS:
-//                   64x64 PU -> 16 items (quadrant x 9-mode group), 32x32 PU -> 5 items (7-mode group),
-//                   16x16 PU -> 1 item (35 modes), 8x8 CU -> 1 item (2Nx2N 8x8 + its four NxN 4x4 PUs).
+//                 descriptors in encoder visiting order plus a queue of WORK ITEMS, big ones first:
+//                   64x64 PU -> 4 items (one per 32x32 quadrant), 32x32 PU -> 1 item   [front of the queue]
+//                   16x16 PU -> 1 item, 8x8 CU -> 1 item (2Nx2N 8x8 + its four NxN 4x4 PUs)
 //                 Offsets come from the per-CTU counts the label kernel wrote (ctu_plan_counts()).
-//   k_rmd_items : persistent warps pull items from a global counter.  A warp stages its PU (or PU
-//                 quadrant) and its transpose in its own shared-memory slice, builds the reference
-//                 lines straight from the picture in L2, and evaluates its modes.  A "unit" is one 8x8
-//                 block for one mode; a "slab" is two units.  Each lane predicts two neighbouring
-//                 pixels per unit with one packed 16-bit interpolation, forms the residual as an exact
-//                 fp16 pair, and the 2-D Hadamard transform of both units is two chained mma.sync
-//                 (A = diag(H8,H8) or diag(H4 x4), entries +-1): stage 1 gives H*D (|v| <= 2040, exact in
-//                 fp16), the accumulator fragment re-read as the next B operand is its transpose, stage
-//                 2 gives (H*D*H^T)^T (|v| <= 16320, exact in fp32).  Sum of magnitudes and the per-block
-//                 rounding are those of TComRdCost.cpp:1549-1750.
-//                 PUs >= 16: per mode the warp first writes the mode's main reference array -- projected
-//                 side samples included (TComPrediction.cpp:278-300) -- as a table of sample PAIRS, so the
-//                 per-pixel work is two 32-bit loads and one packed multiply-add; horizontal modes run
-//                 the same code on the transposed block with the roles of the two reference arms
-//                 swapped (SATD is transpose-invariant).
-//   k_rmd_rank  : one warp per PU ranks the 35 SATDs (ties -> lower mode, TEncSearch.cpp:5562-5585).
+//   k_rmd_items : persistent 4-warp blocks pull items from a global counter (first round static).  The
+//                 block stages the PU (or quadrant) and its transpose in shared memory, builds the
+//                 reference lines straight from the picture in L2, then its warps split the 35 modes.
+//                 A "unit" is one 8x8 block for one mode; a "slab" is two units.  Each lane predicts two
+//                 neighbouring pixels per unit with one packed 16-bit interpolation, forms the residual
+//                 as an exact fp16 pair, and the 2-D Hadamard transform of both units is two chained
+//                 mma.sync (A = diag(H8,H8) or diag(H4 x4), entries +-1): stage 1 gives H*D (|v| <= 2040,
+//                 exact in fp16), the accumulator fragment re-read as the next B operand is its
+//                 transpose, stage 2 gives (H*D*H^T)^T (|v| <= 16320, exact in fp32).  Sum of magnitudes
+//                 and the per-block rounding are those of TComRdCost.cpp:1549-1750.
+//                 PUs >= 16 read the main reference array as a table of sample PAIRS (two 32-bit loads and
+//                 one packed multiply-add per pixel pair): four block-wide tables (vertical/horizontal x
+//                 unfiltered/filtered) serve every mode with a non-negative angle; a negative-angle mode
+//                 gets a per-warp table with the projected side samples in front
+//                 (TComPrediction.cpp:278-300).  Horizontal modes run the same code on the transposed
+//                 block with the roles of the two reference arms swapped (SATD is transpose-invariant).
+//                 When a PU's 35 SATDs are complete the block ranks them (ties -> lower mode,
+//                 TEncSearch.cpp:5562-5585); for a 64x64 PU the last of its four quadrant items does.
 struct RmdItem {
   uint32_t pu;          // index of the PU in the frame's list (kind 1: the 2Nx2N 8x8 PU; its 4x4 PUs follow)
-  uint8_t m0, m1;       // modes [m0, m1)
   uint8_t quad;         // 64x64 PUs: 32x32 quadrant handled by this item
   uint8_t kind;         // 0: PU >= 16 (table path), 1: 8x8 CU
+  uint16_t pad;
 };
 constexpr int MAX_ITEMS_CTU = 64;
-constexpr int RMD_WARPS = 8;
+constexpr int RMD_BW = 4;                       // warps per block of k_rmd_items
 constexpr int ORG_P = 40;                       // row pitch of the staged block: 10 words -> conflict-free 16-bit reads
 constexpr int RED_P = 33;
+constexpr int PTAB_P = 132;
 
-// ctrl[0] = work counter of k_rmd_items, ctrl[1] = number of items of the frame
+// ctrl[0] = work counter of k_rmd_items (starts at its grid size: the first item of a block is blockIdx.x),
+// ctrl[1] = number of items of the frame
 __global__ void __launch_bounds__(256)
-k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_cnt, FrameGeom geo, int *__restrict__ ctu_off,
-           hevcdl_pu *__restrict__ pus, RmdItem *__restrict__ items, uint32_t *__restrict__ satd, int *__restrict__ ctrl) {
+k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_cnt, FrameGeom geo, int items_grid,
+           int *__restrict__ ctu_off, hevcdl_pu *__restrict__ pus, RmdItem *__restrict__ items, uint32_t *__restrict__ satd,
+           uint8_t *__restrict__ cand, int *__restrict__ ctrl) {
   const int lane = threadIdx.x & 31, ctu = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = items_grid;
   if (ctu >= geo.nctu) return;
-  uint32_t pu0 = 0, it0 = 0;
-  for (int c = lane; c < ctu; c += 32) { const uint32_t v = __ldg(ctu_cnt + c); pu0 += v & 0xFFFFu; it0 += v >> 16; }
+  // counts of the preceding CTUs (PUs, big items, small items) and the frame's total of big items
+  uint32_t pu0 = 0, big0 = 0, sm0 = 0, bigT = 0, smT = 0;
+  for (int c = lane; c < geo.nctu; c += 32) {
+    const uint32_t v = __ldg(ctu_cnt + c);
+    const uint32_t b = (v >> 16) & 15u, s = v >> 20;
+    bigT += b; smT += s;
+    if (c < ctu) { pu0 += v & 0xFFFFu; big0 += b; sm0 += s; }
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { pu0 += __shfl_xor_sync(0xffffffffu, pu0, o); it0 += __shfl_xor_sync(0xffffffffu, it0, o); }
+  for (int o = 16; o > 0; o >>= 1) {
+    pu0 += __shfl_xor_sync(0xffffffffu, pu0, o); big0 += __shfl_xor_sync(0xffffffffu, big0, o);
+    sm0 += __shfl_xor_sync(0xffffffffu, sm0, o); bigT += __shfl_xor_sync(0xffffffffu, bigT, o);
+    smT += __shfl_xor_sync(0xffffffffu, smT, o);
+  }
   if (lane == 0) {
     ctu_off[ctu] = (int)pu0;
     if (ctu == geo.nctu - 1) {
-      const uint32_t mine = __ldg(ctu_cnt + ctu);
-      ctu_off[geo.nctu] = (int)(pu0 + (mine & 0xFFFFu));
-      ctrl[1] = (int)(it0 + (mine >> 16));
+      ctu_off[geo.nctu] = (int)(pu0 + (__ldg(ctu_cnt + ctu) & 0xFFFFu));
+      ctrl[1] = (int)(bigT + smT);
     }
   }
+  uint32_t it_big = big0, it_small = bigT + sm0;
   const int W = geo.W, H = geo.H;
   const int x0 = (ctu % geo.ctu_w) * 64, y0 = (ctu / geo.ctu_w) * 64;
   const uint4 pk = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
@@ -396,67 +411,75 @@ k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_
       if (!(pl > d && d < 3)) break;                                   // pruned
     }
     const int np = esize == 0 ? 0 : (esize == 8 ? 5 : 1);
-    const int ni = esize == 0 ? 0 : (esize == 64 ? 16 : (esize == 32 ? 5 : 1));
-    int sp = np, si = ni;
+    const int nb = esize == 64 ? 4 : (esize == 32 ? 1 : 0);
+    const int ns = (esize == 16 || esize == 8) ? 1 : 0;
+    int sp = np, sb = nb, ss = ns;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, sp, o), b = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) { sp += a; si += b; }
+      const int a = __shfl_up_sync(0xffffffffu, sp, o), b = __shfl_up_sync(0xffffffffu, sb, o), c = __shfl_up_sync(0xffffffffu, ss, o);
+      if (lane >= o) { sp += a; sb += b; ss += c; }
     }
-    const uint32_t ppos = pu0 + sp - np, ipos = it0 + si - ni;
+    const uint32_t ppos = pu0 + sp - np, bpos = it_big + sb - nb, spos = it_small + ss - ns;
     if (esize) {
       pus[ppos] = hevcdl_pu{(uint16_t)ex, (uint16_t)ey, (uint8_t)esize, 0, (uint16_t)ctu};
       if (esize == 8) {
         for (int k = 0; k < 4; k++)
           pus[ppos + 1 + k] = hevcdl_pu{(uint16_t)(ex + (k & 1) * 4), (uint16_t)(ey + (k >> 1) * 4), 4, (uint8_t)(k + 1), (uint16_t)ctu};
-        items[ipos] = RmdItem{ppos, 0, 35, 0, 1};
+        items[spos] = RmdItem{ppos, 0, 1, 0};
       } else if (esize == 16) {
-        items[ipos] = RmdItem{ppos, 0, 35, 0, 0};
+        items[spos] = RmdItem{ppos, 0, 0, 0};
       } else if (esize == 32) {
-        for (int k = 0; k < 5; k++) items[ipos + k] = RmdItem{ppos, (uint8_t)(7 * k), (uint8_t)(7 * k + 7), 0, 0};
+        items[bpos] = RmdItem{ppos, 0, 0, 0};
       } else {
-        for (int k = 0; k < 16; k++)
-          items[ipos + k] = RmdItem{ppos, (uint8_t)(9 * (k & 3)), (uint8_t)((k & 3) == 3 ? 35 : 9 * (k & 3) + 9), (uint8_t)(k >> 2), 0};
+        for (int k = 0; k < 4; k++) items[bpos + k] = RmdItem{ppos, (uint8_t)k, 0, 0};
         for (int m = 0; m < 35; m++) satd[(size_t)ppos * 35 + m] = 0;   // quadrant items accumulate with atomicAdd
+        *reinterpret_cast<uint32_t *>(cand + (size_t)ppos * 8) = 0;     // ... and count themselves here until the last one ranks
       }
     }
     pu0 += __shfl_sync(0xffffffffu, sp, 31);
-    it0 += __shfl_sync(0xffffffffu, si, 31);
+    it_big += __shfl_sync(0xffffffffu, sb, 31);
+    it_small += __shfl_sync(0xffffffffu, ss, 31);
   }
 }
 
-// per-warp shared-memory slice of k_rmd_items
-struct RmdWarp {
+struct RmdWarpS {
+  uint32_t tab[200];              // pair table of a negative-angle mode: tab[k + n] = ext[k] | ext[k+1] << 16
+  float red[16][RED_P];           // per-lane block partial sums of one reduction group (16 blocks)
+};
+struct RmdBlockS {
   uint8_t org[32 * ORG_P];        // the PU (or 32x32 quadrant of a 64x64 PU), row pitch ORG_P
   uint8_t orgT[32 * ORG_P];       // its transpose (horizontal modes)
-  int16_t line[2][260];           // [0] unfiltered, [1] filtered reference line (kind 1: see item_small)
-  uint32_t tab[200];              // pair table of the current mode: tab[k + n] = ext[k] | ext[k+1] << 16
-  float red[16][RED_P];           // per-lane block partial sums of one reduction group (16 blocks)
-  uint8_t avail[68];
-  int8_t src[68];
+  int16_t line[2][260];           // [0] unfiltered, [1] filtered reference line (8x8 CU items: see block_small)
+  uint32_t ptab[4][PTAB_P];       // [hor*2 + filtered][k] = main[k] | main[k+1] << 16, k in [0, 2n)
+  uint32_t satd[5][36];           // finished SATDs of the item's PU(s), for the ranking
   int16_t dcs[8];
+  int next_item;
+  RmdWarpS w[RMD_BW];
 };
 
-// Reference line of one PU from the ORIGINAL picture, with HM's availability rule and substitution scan
-// (TComPattern.cpp:326-543); one warp.  line: 4n+1 entries.
-__device__ __noinline__ void build_line_warp(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, int W, int H, int ctu_w,
-                                                int px, int py, int n, int16_t *line, int lane) {
-  const int nu = n >> 2;                        // units: [0,2nu) left bottom-up, 2nu corner, (2nu, 4nu] above
-  for (int u = lane; u <= 4 * nu; u += 32) {
-    int xn, yn;
-    if (u < 2 * nu) { xn = px - 1; yn = py + (2 * nu - 1 - u) * 4; }
-    else if (u == 2 * nu) { xn = px - 1; yn = py - 1; }
-    else { xn = px + (u - 2 * nu - 1) * 4; yn = py - 1; }
-    S.avail[u] = unit_available(xn, yn, px, py, W, H, ctu_w);
+// Entries [e0, e1) of the reference line of one PU from the ORIGINAL picture, with HM's availability rule and
+// substitution scan (TComPattern.cpp:326-543): an unavailable 4-sample unit takes the last sample of the nearest
+// available unit before it in scan order, else the first sample of the first available unit after it.  One warp;
+// every calling warp evaluates the availability of all <= 65 units itself (ballots), then fills its own entries.
+__device__ __noinline__ void build_line_part(const uint8_t *__restrict__ Y, int pitch, int W, int H, int ctu_w, int px, int py, int n,
+                                                int16_t *line, int e0, int e1, int lane) {
+  const int nu = n >> 2, ntot = 4 * nu + 1;     // units: [0,2nu) left bottom-up, 2nu corner, (2nu, 4nu] above
+  unsigned long long mlo = 0;
+  bool top = false;
+  for (int base = 0; base < ntot; base += 32) {
+    const int u = base + lane;
+    bool a = false;
+    if (u < ntot) {
+      int xn, yn;
+      if (u < 2 * nu) { xn = px - 1; yn = py + (2 * nu - 1 - u) * 4; }
+      else if (u == 2 * nu) { xn = px - 1; yn = py - 1; }
+      else { xn = px + (u - 2 * nu - 1) * 4; yn = py - 1; }
+      a = unit_available(xn, yn, px, py, W, H, ctu_w);
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, a);
+    if (base < 64) mlo |= (unsigned long long)b << base;
+    else top = b & 1u;
   }
-  __syncwarp();
-  for (int u = lane; u <= 4 * nu; u += 32) {
-    int s = -1;
-    for (int v = u; v >= 0; v--) if (S.avail[v]) { s = v; break; }
-    if (s < 0) for (int v = u + 1; v <= 4 * nu; v++) if (S.avail[v]) { s = v; break; }
-    S.src[u] = (int8_t)s;
-  }
-  __syncwarp();
   auto sample = [&](int i) -> int {             // picture sample at line index i (only called for available units)
     int gx, gy;
     if (i < 2 * n) { gx = px - 1; gy = py + 2 * n - 1 - i; }
@@ -464,21 +487,27 @@ __device__ __noinline__ void build_line_warp(RmdWarp &S, const uint8_t *__restri
     else { gx = px + i - 2 * n - 1; gy = py - 1; }
     return Y[(size_t)gy * pitch + gx];
   };
-  for (int i = lane; i < 4 * n + 1; i += 32) {
+  for (int i = e0 + lane; i < e1; i += 32) {
     const int u = i < 2 * n ? (i >> 2) : (i == 2 * n ? 2 * nu : 2 * nu + 1 + ((i - 2 * n - 1) >> 2));
-    const int s = S.src[u];
+    int s;
+    {
+      const unsigned long long upto = u >= 63 ? ~0ull : ((2ull << u) - 1);
+      const unsigned long long below = mlo & upto, above = mlo & ~upto;
+      if (u == 64 && top) s = 64;
+      else if (below) s = 63 - __clzll((long long)below);
+      else if (above) s = __ffsll((long long)above) - 1;
+      else s = top ? 64 : -1;
+    }
     int v;
     if (s < 0) v = 128;
     else if (s == u) v = sample(i);
     else {
-      // last sample (scan order) of an earlier unit, first sample of a later one
       const int firsti = s < 2 * nu ? 4 * s : (s == 2 * nu ? 2 * n : 2 * n + 1 + 4 * (s - 2 * nu - 1));
       const int lasti = s == 2 * nu ? 2 * n : firsti + 3;
       v = sample(s < u ? lasti : firsti);
     }
     line[i] = (int16_t)v;
   }
-  __syncwarp();
 }
 
 // DC value of a line (TComPrediction.cpp:183-201); all lanes return it.
@@ -490,91 +519,137 @@ __device__ __forceinline__ int line_dc_warp(const int16_t *line, int n, int lane
   return (sum + n) / (2 * n);
 }
 
-// Everything about (PU, mode) the pixel loop of the table path needs; warp-uniform.
-struct TabMode {
-  const int16_t *c, *u;     // centre of the line chosen for this mode / of the unfiltered line
-  const uint8_t *o;         // staged block to read: org (planar, DC, vertical modes) or orgT (horizontal modes)
-  int mode, angle, sg, i0, j0;
-  bool slow;                // planar, DC, or pure H/V with the edge filter: generic per-pixel predictor
-};
+// SATD-ranked candidates of one PU: cand[8], the first 3 (size >= 16) or 8 valid, the rest 255.  Rank by
+// (satd, mode): the strict '<' insertion from the worst slot of xUpdateCandList (TEncSearch.cpp:5562-5585)
+// keeps the earlier (lower) mode ahead on equal cost.  s0: SATD of mode `lane`; s1: of mode 32 + lane (lane < 3).
+__device__ __noinline__ void rank35_warp(uint32_t s0, uint32_t s1, int keep, uint8_t *__restrict__ cand8, int lane) {
+  int r0 = 0, r1 = 0;
+#pragma unroll 5
+  for (int j = 0; j < 35; j++) {
+    const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, s0, j & 31) : __shfl_sync(0xffffffffu, s1, j & 31);
+    r0 += (cj < s0) || (cj == s0 && j < lane);
+    r1 += (cj < s1) || (cj == s1 && j < 32 + lane);
+  }
+  uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t m0 = __ballot_sync(0xffffffffu, r0 == k), m1 = __ballot_sync(0xffffffffu, lane < 3 && r1 == k);
+    if (k < keep) {
+      const uint32_t mode = m0 ? (uint32_t)(__ffs(m0) - 1) : (uint32_t)(32 + __ffs(m1) - 1);
+      if (k < 4) lo = (lo & ~(0xFFu << (8 * k))) | (mode << (8 * k));
+      else hi = (hi & ~(0xFFu << (8 * (k - 4)))) | (mode << (8 * (k - 4)));
+    }
+  }
+  if (lane == 0) *reinterpret_cast<uint2 *>(cand8) = make_uint2(lo, hi);
+}
 
-// PUs >= 16.  The staged region is the 16x16 PU, the 32x32 PU, or one 32x32 quadrant of a 64x64 PU.  Rolled loops on
-// purpose: the whole function is a few KB of code, so the warps of an SM share the instruction cache.
-__device__ __forceinline__ void item_large(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
-                                           const RmdItem item, uint32_t a8, int lane, uint32_t *__restrict__ satd_out) {
+// PUs >= 16: the staged region is the 16x16 PU, the 32x32 PU, or one 32x32 quadrant of a 64x64 PU.  Rolled loops
+// on purpose: the hot loop is a few hundred instructions, so the warps of an SM share the instruction cache.
+__device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
+                                            const RmdItem item, uint32_t a8, uint32_t *__restrict__ satd_out, uint8_t *__restrict__ cand_out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  RmdWarpS &Wp = S.w[wid];
   const int n = pu.size, px = pu.x, py = pu.y, lg = ilog2(n);
   const int rs = n == 16 ? 16 : 32;             // region side
   const int lgnb = rs == 32 ? 2 : 1;            // log2(8x8 blocks per region row)
-  const int spm = rs == 32 ? 8 : 2;             // slabs per mode; a reduction group is 8 slabs = 16 blocks
+  const int spm = rs == 32 ? 8 : 2;             // slabs per mode; a reduction group is up to 8 slabs = 16 blocks
   const int mpg = rs == 32 ? 1 : 4;             // modes per reduction group
   const int rx0 = n == 64 ? (item.quad & 1) * 32 : 0, ry0 = n == 64 ? (item.quad >> 1) * 32 : 0;
   const int g = lane >> 2, t = lane & 3;
-  // stage the region and its transpose
+  const bool has_flt = n == 16 || n == 32;
+  // ---- phase 1: stage the region and its transpose; every warp fills a quarter of the reference line ----------
   {
     const int wpr = rs >> 2, lgw = rs == 32 ? 3 : 2;
     const uint8_t *src = Y + (size_t)(py + ry0) * pitch + px + rx0;
-    for (int i = lane; i < rs * wpr; i += 32) {
+    for (int i = tid; i < rs * wpr; i += RMD_BW * 32) {
       const int r = i >> lgw, cw = i & (wpr - 1);
       const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * pitch + 4 * cw));
       *reinterpret_cast<uint32_t *>(&S.org[r * ORG_P + 4 * cw]) = v;
 #pragma unroll
       for (int k = 0; k < 4; k++) S.orgT[(4 * cw + k) * ORG_P + r] = (uint8_t)(v >> (8 * k));
     }
+    const int len = 4 * n + 1, q = (len + RMD_BW - 1) / RMD_BW;
+    build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, n, S.line[0], wid * q, min(len, wid * q + q), lane);
   }
-  build_line_warp(S, Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, n, S.line[0], lane);
-  if (n == 16 || n == 32) filter_line_warp(S.line[0], S.line[1], n, lane);
+  __syncthreads();
+  if (has_flt) {                                // [1 2 1] / strong smoothing (TComPattern.cpp:203-294), whole block
+    const int16_t *line = S.line[0];
+    const int len = 4 * n + 1;
+    const int bl = line[0], tl = line[2 * n], tr = line[4 * n];
+    const bool strong = n == 32 && (abs(bl + tl - 2 * line[n]) < 8) && (abs(tl + tr - 2 * line[3 * n]) < 8);
+    for (int i = tid; i < len; i += RMD_BW * 32) {
+      int v;
+      if (i == 0 || i == len - 1) v = line[i];
+      else if (!strong) v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
+      else if (i < 2 * n) v = ((2 * n - i) * bl + i * tl + n) >> 6;
+      else if (i == 2 * n) v = tl;
+      else v = ((4 * n - i) * tl + (i - 2 * n) * tr + n) >> 6;
+      S.line[1][i] = (int16_t)v;
+    }
+  }
   const int dc = line_dc_warp(S.line[0], n, lane);
-  __syncwarp();
+  __syncthreads();
+  // pair tables of the non-negative angles: main[k] | main[k+1] << 16 for the four (orientation, filter) variants
+  for (int idx = tid; idx < 8 * n; idx += RMD_BW * 32) {
+    const int v = idx / (2 * n), k = idx - v * 2 * n;
+    if ((v & 1) && !has_flt) continue;
+    const int16_t *c = S.line[v & 1] + 2 * n;
+    const int sg = (v & 2) ? -1 : 1;
+    S.ptab[v][k] = (uint32_t)c[sg * k] | ((uint32_t)c[sg * (k + 1)] << 16);
+  }
+  __syncthreads();
 
-  for (int mb = item.m0; mb < item.m1; mb += mpg) {
+  // ---- phase 2: warp wid evaluates modes wid, wid + 4, ... ---------------------------------------------------
+  for (int mfirst = wid; mfirst < 35; mfirst += RMD_BW * mpg) {
     for (int mi = 0; mi < mpg; mi++) {
-      const int mode = mb + mi;
-      if (mode >= item.m1) break;               // warp-uniform (last group of a 16x16 PU holds modes 32..34)
-      // ---- per-mode setup: which line, which orientation, and the table of reference sample pairs ------------
-      TabMode M;
-      {
-        const int16_t *L = mode_uses_filter(mode, n) ? S.line[1] : S.line[0];
-        M.c = L + 2 * n; M.u = S.line[0] + 2 * n;
-        M.mode = mode; M.angle = c_mode_angle[mode];
-        const bool hor = mode >= 2 && mode < 18;
-        M.sg = hor ? -1 : 1;
-        M.o = (hor ? S.orgT : S.org) + g * ORG_P + 2 * t;
-        M.i0 = (hor ? ry0 : rx0) + 2 * t; M.j0 = (hor ? rx0 : ry0) + g;
-        M.slow = mode < 2 || (M.angle == 0 && n <= 16);
-        __syncwarp();                           // readers of the previous mode's table are done
-        if (mode >= 2) {
-          const int inv = c_mode_inv[mode];
-          const int kmin = M.angle < 0 ? ((n * M.angle) >> 5) + 1 : 1, kend = M.angle < 0 ? n + 1 : 2 * n;
-          for (int k = kmin + lane; k < kend; k += 32) {
+      const int mode = mfirst + RMD_BW * mi;
+      if (mode >= 35) break;                    // warp-uniform
+      const bool flt = mode_uses_filter(mode, n), hor = mode >= 2 && mode < 18;
+      const int16_t *c = S.line[flt ? 1 : 0] + 2 * n;
+      const int angle = c_mode_angle[mode], sg = hor ? -1 : 1;
+      const uint8_t *o = (hor ? S.orgT : S.org) + g * ORG_P + 2 * t;
+      const int i0 = (hor ? ry0 : rx0) + 2 * t, j0 = (hor ? rx0 : ry0) + g;
+      const bool slow = mode < 2 || (angle == 0 && n <= 16);
+      const uint32_t *tbase = S.ptab[(hor ? 2 : 0) + (flt ? 1 : 0)];
+      if (angle < 0) {                          // projected side samples in front of the main array
+        const int inv = c_mode_inv[mode];
+        const int kmin = ((n * angle) >> 5) + 1;
+        __syncwarp();                           // readers of the previous table are done
+        for (int k = kmin + lane; k <= n; k += 32) {
+          uint32_t e;
+          if (k >= 0) e = tbase[k];
+          else {
             const int k1 = k + 1;
-            const int e0 = k >= 0 ? M.c[M.sg * k] : M.c[-M.sg * ((128 - k * inv) >> 8)];
-            const int e1 = k1 >= 0 ? M.c[M.sg * k1] : M.c[-M.sg * ((128 - k1 * inv) >> 8)];
-            S.tab[k + n] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+            const int e0 = c[-sg * ((128 - k * inv) >> 8)];
+            const int e1 = k1 < 0 ? c[-sg * ((128 - k1 * inv) >> 8)] : c[0];
+            e = (uint32_t)e0 | ((uint32_t)e1 << 16);
           }
+          Wp.tab[k + n] = e;
         }
         __syncwarp();
+        tbase = Wp.tab + n;
       }
-      // ---- slabs: two horizontally adjacent 8x8 blocks each ------------------------------------------------
+      // slabs: two horizontally adjacent 8x8 blocks each
 #pragma unroll 2
       for (int sl = 0; sl < spm; sl++) {
         const int by8 = (sl >> (lgnb - 1)) * 8, bx8 = ((2 * sl) & ((1 << lgnb) - 1)) * 8;
-        const uint8_t *op = M.o + by8 * ORG_P + bx8;
+        const uint8_t *op = o + by8 * ORG_P + bx8;
         const uint32_t oa = *reinterpret_cast<const uint16_t *>(op), ob = *reinterpret_cast<const uint16_t *>(op + 8);
         uint32_t Pa, Pb;
-        if (!M.slow) {
-          const int pos = (M.j0 + by8 + 1) * M.angle, di = pos >> 5, df = pos & 31;   // shared by the row of blocks
-          const uint32_t *tp = S.tab + (M.i0 + bx8 + di + 1 + n);
+        if (!slow) {
+          const int pos = (j0 + by8 + 1) * angle, di = pos >> 5, df = pos & 31;   // shared by the row of blocks
+          const uint32_t *tp = tbase + (i0 + bx8 + di + 1);
           const uint32_t w0 = 32 - df;
           Pa = ((w0 * tp[0] + df * tp[1] + 0x00100010u) >> 5) & 0x07FF07FFu;
           Pb = ((w0 * tp[8] + df * tp[9] + 0x00100010u) >> 5) & 0x07FF07FFu;
         } else if (mode < 2) {
-          Pa = predict_pair(M.c, M.u, n, lg, mode, (rx0 + 2 * t) + bx8, (ry0 + g) + by8, dc);
-          Pb = predict_pair(M.c, M.u, n, lg, mode, (rx0 + 2 * t) + bx8 + 8, (ry0 + g) + by8, dc);
+          Pa = predict_pair(c, S.line[0] + 2 * n, n, lg, mode, (rx0 + 2 * t) + bx8, (ry0 + g) + by8, dc);
+          Pb = predict_pair(c, S.line[0] + 2 * n, n, lg, mode, (rx0 + 2 * t) + bx8 + 8, (ry0 + g) + by8, dc);
         } else {                                // pure H/V (angle 0, no interpolation) with the edge filter (n <= 16)
-          const int i = M.i0 + bx8, j = M.j0 + by8;
-          Pa = S.tab[i + 1 + n]; Pb = S.tab[i + 9 + n];
+          const int i = i0 + bx8, j = j0 + by8;
+          Pa = tbase[i + 1]; Pb = tbase[i + 9];
           if (i == 0) {
-            const int p0 = clip255((int)(Pa & 0xFFFF) + ((M.c[-M.sg * (j + 1)] - M.c[0]) >> 1));
+            const int p0 = clip255((int)(Pa & 0xFFFF) + ((c[-sg * (j + 1)] - c[0]) >> 1));
             Pa = (Pa & 0xFFFF0000u) | (uint32_t)p0;
           }
         }
@@ -586,15 +661,15 @@ __device__ __forceinline__ void item_large(RmdWarp &S, const uint8_t *__restrict
         float c1[4], c2[4];
         mma_f16_16816(c1, a8, 0u, 0u, a8, *reinterpret_cast<const uint32_t *>(&da), *reinterpret_cast<const uint32_t *>(&db));
         mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-        float *rr = &S.red[(mi * spm + sl) * 2][lane];
+        float *rr = &Wp.red[(mi * spm + sl) * 2][lane];
         rr[0] = fabsf(c2[0]) + fabsf(c2[1]);
         rr[RED_P] = fabsf(c2[2]) + fabsf(c2[3]);
       }
     }
     __syncwarp();
-    // ---- block totals: lane l sums half of row (l & 15), the two halves meet through one shuffle -------------
+    // block totals: lane l sums half of row (l & 15), the two halves meet through one shuffle
     {
-      const float *row = &S.red[lane & 15][(lane >> 4) * 16];
+      const float *row = &Wp.red[lane & 15][(lane >> 4) * 16];
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; k++) acc += row[k];
@@ -606,100 +681,129 @@ __device__ __forceinline__ void item_large(RmdWarp &S, const uint8_t *__restrict
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         if (lane == 0) {
-          if (n == 64) atomicAdd(&satd_out[(size_t)item.pu * 35 + mb], v);
-          else satd_out[(size_t)item.pu * 35 + mb] = v;
+          if (n == 64) atomicAdd(&satd_out[(size_t)item.pu * 35 + mfirst], v);
+          else { satd_out[(size_t)item.pu * 35 + mfirst] = v; S.satd[0][mfirst] = v; }
         }
       } else {
-        const int mode = mb + (lane >> 2);      // lanes 4m..4m+3 hold the four blocks of mode mb + m
-        if (lane < 16 && (lane & 3) == 0 && mode < item.m1) satd_out[(size_t)item.pu * 35 + mode] = v;
+        const int mode = mfirst + RMD_BW * (lane >> 2);   // lanes 4m..4m+3 hold the four blocks of the group's m-th mode
+        if (lane < 16 && (lane & 3) == 0 && mode < 35) { satd_out[(size_t)item.pu * 35 + mode] = v; S.satd[0][mode] = v; }
       }
     }
     __syncwarp();
+  }
+  // ---- phase 3: rank ------------------------------------------------------------------------------------------
+  if (n == 64) __threadfence();                 // this thread's atomicAdds are visible before the block counts itself
+  __syncthreads();
+  if (wid == 0) {
+    if (n != 64) {
+      rank35_warp(S.satd[0][lane], lane < 3 ? S.satd[0][32 + lane] : 0xFFFFFFFFu, 3, cand_out + (size_t)item.pu * 8, lane);
+    } else {
+      uint32_t done = 0;
+      if (lane == 0) { __threadfence(); done = atomicAdd(reinterpret_cast<uint32_t *>(cand_out + (size_t)item.pu * 8), 1u); }
+      done = __shfl_sync(0xffffffffu, done, 0);
+      if (done == 3) {                          // the other three quadrants are complete: rank the totals
+        __threadfence();
+        const uint32_t *sp = satd_out + (size_t)item.pu * 35;
+        rank35_warp(__ldcg(sp + lane), lane < 3 ? __ldcg(sp + 32 + lane) : 0xFFFFFFFFu, 3, cand_out + (size_t)item.pu * 8, lane);
+      }
+    }
   }
 }
 
 // One 8x8 CU: the 2Nx2N 8x8 PU and the four 4x4 PUs of its NxN trial (TEncCu.cpp:819-826).  A slab is one 8x8
 // area for two modes; in the NxN slabs every 4x4 quadrant is predicted from its own PU's references and
-// transformed with diag(H4 x4).
-__device__ __forceinline__ void item_small(RmdWarp &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
-                                           const RmdItem item, uint32_t a8, uint32_t a4, int lane, uint32_t *__restrict__ satd_out) {
+// transformed with diag(H4 x4).  The 36 slabs are dealt round-robin to the block's warps.
+__device__ __forceinline__ void block_small(RmdBlockS &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
+                                            const RmdItem item, uint32_t a8, uint32_t a4, uint32_t *__restrict__ satd_out,
+                                            uint8_t *__restrict__ cand_out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int px = pu.x, py = pu.y;
   const int g = lane >> 2, t = lane & 3;
-  if (lane < 16) {
+  // lines: 8x8 at L[0..33), its filtered copy at [34..67) (make_modek's convention), 4x4 PU k at [68 + 20k ..)
+  int16_t *L = S.line[0];
+  if (wid == 0 && lane < 16) {
     const int r = lane >> 1, cw = lane & 1;
     *reinterpret_cast<uint32_t *>(&S.org[r * ORG_P + 4 * cw]) =
         __ldg(reinterpret_cast<const uint32_t *>(Y + (size_t)(py + r) * pitch + px + 4 * cw));
   }
-  // lines: 8x8 at line[0][0..33), its filtered copy at [34..67) (make_modek's convention), 4x4 PU k at [68 + 20k ..)
-  int16_t *L = S.line[0];
-  build_line_warp(S, Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, 8, L, lane);
-  filter_line_warp(L, L + 34, 8, lane);
-  { const int dc = line_dc_warp(L, 8, lane); if (lane == 0) S.dcs[0] = (int16_t)dc; }
-  for (int k = 0; k < 4; k++) {
-    build_line_warp(S, Y, pitch, geo.W, geo.H, geo.ctu_w, px + (k & 1) * 4, py + (k >> 1) * 4, 4, L + 68 + 20 * k, lane);
-    const int dc = line_dc_warp(L + 68 + 20 * k, 4, lane);
-    if (lane == 0) S.dcs[1 + k] = (int16_t)dc;
+  {
+    int16_t *l4 = L + 68 + 20 * wid;            // warp k: the line of 4x4 PU k, then a quarter of the 8x8 line
+    build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px + (wid & 1) * 4, py + (wid >> 1) * 4, 4, l4, 0, 17, lane);
+    build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, 8, L, wid * 9, min(33, wid * 9 + 9), lane);
+    __syncwarp();
+    const int dc = line_dc_warp(l4, 4, lane);
+    if (lane == 0) S.dcs[1 + wid] = (int16_t)dc;
   }
-  __syncwarp();
+  __syncthreads();
+  if (wid == 0) {
+    filter_line_warp(L, L + 34, 8, lane);
+    const int dc = line_dc_warp(L, 8, lane);
+    if (lane == 0) S.dcs[0] = (int16_t)dc;
+  }
+  __syncthreads();
   const size_t p = item.pu;
-  for (int r = 0; r < 18; r++) {
+  for (int q = wid; q < 36; q += RMD_BW) {
+    const int r = q >> 1;
+    const bool small = q & 1;
+    uint32_t bf[2] = {0u, 0u};
 #pragma unroll
-    for (int small = 0; small < 2; small++) {
-      uint32_t bf[2] = {0u, 0u};
+    for (int e = 0; e < 2; e++) {
+      const int mode = 2 * r + e;
+      if (mode >= 35) continue;                 // warp-uniform
+      const bool hor = mode >= 2 && mode < 18;
+      const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
+      const int sub = (uy >> 2) * 2 + (ux >> 2);
+      const ModeK k = small ? make_modek(L + 68 + 20 * sub, 4, mode, S.dcs[1 + sub]) : make_modek(L, 8, mode, S.dcs[0]);
+      const int X = small ? ux & 3 : ux, Yc = small ? uy & 3 : uy;
+      bf[e] = resid_pair(&S.org[uy * ORG_P + ux], ORG_P, hor, predict_pair_k(k, X, Yc));
+    }
+    const uint32_t a = small ? a4 : a8;
+    float c1[4], c2[4];
+    mma_f16_16816(c1, a, 0u, 0u, a, bf[0], bf[1]);
+    mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
+    float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
+    if (!small) {
+      const bool upper = lane & 16;
+      float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int mode = 2 * r + e;
-        if (mode >= 35) continue;               // warp-uniform
-        const bool hor = mode >= 2 && mode < 18;
-        const int ux = hor ? g : 2 * t, uy = hor ? 2 * t : g;
-        const int sub = (uy >> 2) * 2 + (ux >> 2);
-        const ModeK k = small ? make_modek(L + 68 + 20 * sub, 4, mode, S.dcs[1 + sub]) : make_modek(L, 8, mode, S.dcs[0]);
-        const int X = small ? ux & 3 : ux, Yc = small ? uy & 3 : uy;
-        bf[e] = resid_pair(&S.org[uy * ORG_P + ux], ORG_P, hor, predict_pair_k(k, X, Yc));
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int mode = 2 * r + (upper ? 1 : 0);
+      if ((lane & 15) == 0 && mode < 35) {
+        const uint32_t sv = ((uint32_t)v + 2) >> 2;
+        satd_out[p * 35 + mode] = sv; S.satd[0][mode] = sv;
       }
-      const uint32_t a = small ? a4 : a8;
-      float c1[4], c2[4];
-      mma_f16_16816(c1, a, 0u, 0u, a, bf[0], bf[1]);
-      mma_f16_16816(c2, a, 0u, 0u, a, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-      float sA = fabsf(c2[0]) + fabsf(c2[1]), sB = fabsf(c2[2]) + fabsf(c2[3]);
-      if (!small) {
-        const bool upper = lane & 16;
-        float v = (upper ? sB : sA) + __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 16);
+    } else {
+      // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int mode = 2 * r + (upper ? 1 : 0);
-        if ((lane & 15) == 0 && mode < 35) satd_out[p * 35 + mode] = ((uint32_t)v + 2) >> 2;
-      } else {
-        // 4x4 blocks: lanes sharing (g>>2, t>>1) hold one block of each unit: reduce over lane bits 0, 2, 3
+      for (int o = 1; o <= 8; o <<= 1) {
+        if (o == 2) continue;
+        sA += __shfl_xor_sync(0xffffffffu, sA, o);
+        sB += __shfl_xor_sync(0xffffffffu, sB, o);
+      }
+      if ((lane & 13) == 0) {                   // lanes 0, 2, 16, 18
 #pragma unroll
-        for (int o = 1; o <= 8; o <<= 1) {
-          if (o == 2) continue;
-          sA += __shfl_xor_sync(0xffffffffu, sA, o);
-          sB += __shfl_xor_sync(0xffffffffu, sB, o);
-        }
-        if ((lane & 13) == 0) {                 // lanes 0, 2, 16, 18
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int mode = 2 * r + e;
-            if (mode >= 35) continue;
-            // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
-            const bool hor = mode >= 2 && mode < 18;
-            const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
-            satd_out[(p + 1 + sub) * 35 + mode] = ((uint32_t)(e ? sB : sA) + 1) >> 1;   // TComRdCost.cpp:1636-1640
-          }
+        for (int e = 0; e < 2; e++) {
+          const int mode = 2 * r + e;
+          if (mode >= 35) continue;
+          // the result is transposed: its row block (g>>2) follows the slab's n index, its column block (t>>1) the k index
+          const bool hor = mode >= 2 && mode < 18;
+          const int sub = hor ? (t >> 1) * 2 + (g >> 2) : (g >> 2) * 2 + (t >> 1);
+          const uint32_t sv = ((uint32_t)(e ? sB : sA) + 1) >> 1;   // TComRdCost.cpp:1636-1640
+          satd_out[(p + 1 + sub) * 35 + mode] = sv; S.satd[1 + sub][mode] = sv;
         }
       }
     }
   }
+  __syncthreads();
+  for (int k = wid; k < 5; k += RMD_BW)
+    rank35_warp(S.satd[k][lane], lane < 3 ? S.satd[k][32 + lane] : 0xFFFFFFFFu, 8, cand_out + (p + k) * 8, lane);
 }
 
-__global__ void __launch_bounds__(RMD_WARPS * 32, 4)
+__global__ void __launch_bounds__(RMD_BW * 32, 8)
 k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcdl_pu *__restrict__ pus,
-            const RmdItem *__restrict__ items, int *__restrict__ ctrl, uint32_t *__restrict__ satd_out) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  RmdWarp *smw = reinterpret_cast<RmdWarp *>(smraw);
+            const RmdItem *__restrict__ items, int *__restrict__ ctrl, uint32_t *__restrict__ satd_out, uint8_t *__restrict__ cand_out) {
+  __shared__ __align__(16) RmdBlockS S;
   const int lane = threadIdx.x & 31;
-  RmdWarp &S = smw[threadIdx.x >> 5];
   const int g = lane >> 2, t = lane & 3;
   // A fragments (m16n8k16 row-major A): only the diagonal 8x8 blocks are non-zero
   uint32_t a8, a4;
@@ -711,51 +815,17 @@ k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcd
     a4 = on ? (((__popc((g & 3) & (c0 & 3)) & 1) ? neg : one) | (((__popc((g & 3) & (c1 & 3)) & 1) ? neg : one) << 16)) : 0u;
   }
   const int nitems = ctrl[1];
-  int it = 0;
-  if (lane == 0) it = atomicAdd(&ctrl[0], 1);
-  it = __shfl_sync(0xffffffffu, it, 0);
+  int it = blockIdx.x;                          // first round is static: k_rmd_plan started the counter at gridDim.x
   while (it < nitems) {
     int nxt = 0;
-    if (lane == 0) nxt = atomicAdd(&ctrl[0], 1);    // claim the next item now: its latency hides behind this one
+    if (threadIdx.x == 0) nxt = atomicAdd(&ctrl[0], 1);   // claim the next item now: its latency hides behind this one
     const RmdItem item = items[it];
     const hevcdl_pu pu = pus[item.pu];
-    if (item.kind == 1) item_small(S, Y, pitch, geo, pu, item, a8, a4, lane, satd_out);
-    else item_large(S, Y, pitch, geo, pu, item, a8, lane, satd_out);
-    __syncwarp();
-    it = __shfl_sync(0xffffffffu, nxt, 0);
-  }
-}
-
-// SATD-ranked candidates of every PU: cand[8], the first 3 (size >= 16) or 8 valid, the rest 255.  Rank by
-// (satd, mode): the strict '<' insertion from the worst slot of xUpdateCandList (TEncSearch.cpp:5562-5585)
-// keeps the earlier (lower) mode ahead on equal cost.
-__global__ void __launch_bounds__(256)
-k_rmd_rank(const int *__restrict__ ctu_off, int nctu, const hevcdl_pu *__restrict__ pus, const uint32_t *__restrict__ satd,
-           uint8_t *__restrict__ cand) {
-  const int lane = threadIdx.x & 31;
-  const int npu = ctu_off[nctu];
-  for (int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < npu; p += gridDim.x * 8) {
-    const uint32_t s0 = satd[(size_t)p * 35 + lane];
-    const uint32_t s1 = lane < 3 ? satd[(size_t)p * 35 + 32 + lane] : 0xFFFFFFFFu;
-    int r0 = 0, r1 = 0;
-#pragma unroll
-    for (int j = 0; j < 35; j++) {
-      const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, s0, j) : __shfl_sync(0xffffffffu, s1, j - 32);
-      r0 += (cj < s0) || (cj == s0 && j < lane);
-      r1 += (cj < s1) || (cj == s1 && j < 32 + lane);
-    }
-    const int keep = num_rd_modes(pus[p].size);
-    uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const uint32_t m0 = __ballot_sync(0xffffffffu, r0 == k), m1 = __ballot_sync(0xffffffffu, lane < 3 && r1 == k);
-      if (k < keep) {
-        const uint32_t mode = m0 ? (uint32_t)(__ffs(m0) - 1) : (uint32_t)(32 + __ffs(m1) - 1);
-        if (k < 4) lo = (lo & ~(0xFFu << (8 * k))) | (mode << (8 * k));
-        else hi = (hi & ~(0xFFu << (8 * (k - 4)))) | (mode << (8 * (k - 4)));
-      }
-    }
-    if (lane == 0) *reinterpret_cast<uint2 *>(cand + (size_t)p * 8) = make_uint2(lo, hi);
+    if (item.kind == 1) block_small(S, Y, pitch, geo, pu, item, a8, a4, satd_out, cand_out);
+    else block_large(S, Y, pitch, geo, pu, item, a8, satd_out, cand_out);
+    if (threadIdx.x == 0) S.next_item = nxt;
+    __syncthreads();                            // also: every warp is done with the item's shared memory
+    it = S.next_item;
   }
 }
 
