@@ -56,6 +56,16 @@ __device__ __forceinline__ void filter_line_warp(const int16_t *line, int16_t *f
 
 // filtered references are used iff min(|m-10|,|m-26|) > thr[size]; never for DC
 // (HM TComPattern.cpp:545-570, table TComPrediction.cpp:50-58)
+// the same rule as a 35-bit mask per PU size (bit m set: mode m predicts from the filtered line)
+__host__ __device__ constexpr unsigned long long mode_filter_mask(int n) {
+  unsigned long long m = 0;
+  const int thr = n == 8 ? 7 : (n == 16 ? 1 : 0);
+  for (int mode = 0; mode < 35; mode++) {
+    const int d10 = mode > 10 ? mode - 10 : 10 - mode, d26 = mode > 26 ? mode - 26 : 26 - mode;
+    if (mode != 1 && n != 4 && n != 64 && (d10 < d26 ? d10 : d26) > thr) m |= 1ull << mode;
+  }
+  return m;
+}
 __device__ __forceinline__ bool mode_uses_filter(int mode, int n) {
   if (mode == 1 || n == 4 || n == 64) return false;
   const int thr = n == 8 ? 7 : (n == 16 ? 1 : 0);
@@ -353,7 +363,7 @@ struct RmdItem {
 constexpr int MAX_ITEMS_CTU = 64;
 constexpr int RMD_BW = 4;                       // warps per block of k_rmd_items
 constexpr int ORG_P = 40;                       // row pitch of the staged block: 10 words -> conflict-free 16-bit reads
-constexpr int RED_P = 33;
+constexpr int RED_P = 36;                       // 16-byte aligned rows, conflict-free column writes and float4 row reads
 constexpr int PTAB_P = 132;
 
 // ctrl[0] = work counter of k_rmd_items (starts at its grid size: the first item of a block is blockIdx.x),
@@ -454,6 +464,8 @@ struct RmdBlockS {
   uint32_t satd[5][36];           // finished SATDs of the item's PU(s), for the ranking
   int16_t dcs[8];
   int next_item;
+  int grp_ctr;                    // next reduction group of the current item (block_large)
+  int pad_[2];
   RmdWarpS w[RMD_BW];
 };
 
@@ -522,20 +534,17 @@ __device__ __forceinline__ int line_dc_warp(const int16_t *line, int n, int lane
 // SATD-ranked candidates of one PU: cand[8], the first 3 (size >= 16) or 8 valid, the rest 255.  Rank by
 // (satd, mode): the strict '<' insertion from the worst slot of xUpdateCandList (TEncSearch.cpp:5562-5585)
 // keeps the earlier (lower) mode ahead on equal cost.  s0: SATD of mode `lane`; s1: of mode 32 + lane (lane < 3).
-__device__ __noinline__ void rank35_warp(uint32_t s0, uint32_t s1, int keep, uint8_t *__restrict__ cand8, int lane) {
-  int r0 = 0, r1 = 0;
-#pragma unroll 5
-  for (int j = 0; j < 35; j++) {
-    const uint32_t cj = j < 32 ? __shfl_sync(0xffffffffu, s0, j & 31) : __shfl_sync(0xffffffffu, s1, j & 31);
-    r0 += (cj < s0) || (cj == s0 && j < lane);
-    r1 += (cj < s1) || (cj == s1 && j < 32 + lane);
-  }
+__device__ __forceinline__ void rank35_warp(uint32_t s0, uint32_t s1, int keep, uint8_t *__restrict__ cand8, int lane) {
+  // key = satd << 6 | mode (satd < 2^24: at most 64 blocks of (64*64*255 + 2) >> 2); repeated warp-wide minimum
+  uint32_t k0 = (s0 << 6) | (uint32_t)lane, k1 = lane < 3 ? ((s1 << 6) | (uint32_t)(32 + lane)) : 0xFFFFFFFFu;
   uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const uint32_t m0 = __ballot_sync(0xffffffffu, r0 == k), m1 = __ballot_sync(0xffffffffu, lane < 3 && r1 == k);
-    if (k < keep) {
-      const uint32_t mode = m0 ? (uint32_t)(__ffs(m0) - 1) : (uint32_t)(32 + __ffs(m1) - 1);
+    if (k < keep) {                             // warp-uniform
+      const uint32_t m = __reduce_min_sync(0xffffffffu, min(k0, k1));
+      if (k0 == m) k0 = 0xFFFFFFFFu;
+      if (k1 == m) k1 = 0xFFFFFFFFu;
+      const uint32_t mode = m & 63u;
       if (k < 4) lo = (lo & ~(0xFFu << (8 * k))) | (mode << (8 * k));
       else hi = (hi & ~(0xFFu << (8 * (k - 4)))) | (mode << (8 * (k - 4)));
     }
@@ -545,22 +554,26 @@ __device__ __noinline__ void rank35_warp(uint32_t s0, uint32_t s1, int keep, uin
 
 // PUs >= 16: the staged region is the 16x16 PU, the 32x32 PU, or one 32x32 quadrant of a 64x64 PU.  Rolled loops
 // on purpose: the hot loop is a few hundred instructions, so the warps of an SM share the instruction cache.
+template <int RS>
 __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restrict__ Y, int pitch, const FrameGeom &geo, const hevcdl_pu pu,
                                             const RmdItem item, uint32_t a8, uint32_t *__restrict__ satd_out, uint8_t *__restrict__ cand_out) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   RmdWarpS &Wp = S.w[wid];
   const int n = pu.size, px = pu.x, py = pu.y, lg = ilog2(n);
-  const int rs = n == 16 ? 16 : 32;             // region side
-  const int lgnb = rs == 32 ? 2 : 1;            // log2(8x8 blocks per region row)
-  const int spm = rs == 32 ? 8 : 2;             // slabs per mode; a reduction group is up to 8 slabs = 16 blocks
-  const int mpg = rs == 32 ? 1 : 4;             // modes per reduction group
+  constexpr int rs = RS;                        // region side: 16 (16x16 PU) or 32
+  constexpr int lgnb = rs == 32 ? 2 : 1;        // log2(8x8 blocks per region row)
+  constexpr int spm = rs == 32 ? 8 : 2;         // slabs per mode; a reduction group is up to 8 slabs = 16 blocks
+  constexpr int ngroups = rs == 32 ? 35 : 11;   // 32: one mode per group; 16: eight groups of 4 modes, then 32, 33, 34 alone
+  const unsigned long long fmask = n == 16 ? mode_filter_mask(16) : (n == 32 ? mode_filter_mask(32) : 0ull);
   const int rx0 = n == 64 ? (item.quad & 1) * 32 : 0, ry0 = n == 64 ? (item.quad >> 1) * 32 : 0;
   const int g = lane >> 2, t = lane & 3;
   const bool has_flt = n == 16 || n == 32;
   // ---- phase 1: stage the region and its transpose; every warp fills a quarter of the reference line ----------
+  if (tid == 0) S.grp_ctr = 0;
   {
-    const int wpr = rs >> 2, lgw = rs == 32 ? 3 : 2;
+    constexpr int wpr = rs >> 2, lgw = rs == 32 ? 3 : 2;
     const uint8_t *src = Y + (size_t)(py + ry0) * pitch + px + rx0;
+#pragma unroll
     for (int i = tid; i < rs * wpr; i += RMD_BW * 32) {
       const int r = i >> lgw, cw = i & (wpr - 1);
       const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * pitch + 4 * cw));
@@ -599,12 +612,17 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
   }
   __syncthreads();
 
-  // ---- phase 2: warp wid evaluates modes wid, wid + 4, ... ---------------------------------------------------
-  for (int mfirst = wid; mfirst < 35; mfirst += RMD_BW * mpg) {
-    for (int mi = 0; mi < mpg; mi++) {
-      const int mode = mfirst + RMD_BW * mi;
-      if (mode >= 35) break;                    // warp-uniform
-      const bool flt = mode_uses_filter(mode, n), hor = mode >= 2 && mode < 18;
+  // ---- phase 2: the warps pull reduction groups (1 or 4 modes) from a block-wide counter ------------------------
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&S.grp_ctr, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= ngroups) break;
+    const int mfirst = rs == 32 ? q : (q < 8 ? 4 * q : 24 + q);
+    const int nm = rs == 32 ? 1 : (q < 8 ? 4 : 1);
+    for (int mi = 0; mi < nm; mi++) {
+      const int mode = mfirst + mi;
+      const bool flt = (fmask >> mode) & 1ull, hor = mode >= 2 && mode < 18;
       const int16_t *c = S.line[flt ? 1 : 0] + 2 * n;
       const int angle = c_mode_angle[mode], sg = hor ? -1 : 1;
       const uint8_t *o = (hor ? S.orgT : S.org) + g * ORG_P + 2 * t;
@@ -669,10 +687,10 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
     __syncwarp();
     // block totals: lane l sums half of row (l & 15), the two halves meet through one shuffle
     {
-      const float *row = &Wp.red[lane & 15][(lane >> 4) * 16];
+      const float4 *row = reinterpret_cast<const float4 *>(&Wp.red[lane & 15][(lane >> 4) * 16]);
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; k++) acc += row[k];
+      for (int k = 0; k < 4; k++) { const float4 r4 = row[k]; acc += (r4.x + r4.y) + (r4.z + r4.w); }
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
       uint32_t v = ((uint32_t)acc + 2) >> 2;    // per-block rounding (TComRdCost.cpp:1739-1749)
       v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -685,8 +703,8 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
           else { satd_out[(size_t)item.pu * 35 + mfirst] = v; S.satd[0][mfirst] = v; }
         }
       } else {
-        const int mode = mfirst + RMD_BW * (lane >> 2);   // lanes 4m..4m+3 hold the four blocks of the group's m-th mode
-        if (lane < 16 && (lane & 3) == 0 && mode < 35) { satd_out[(size_t)item.pu * 35 + mode] = v; S.satd[0][mode] = v; }
+        const int mode = mfirst + (lane >> 2);  // lanes 4m..4m+3 hold the four blocks of the group's m-th mode
+        if ((lane >> 2) < nm && (lane & 3) == 0) { satd_out[(size_t)item.pu * 35 + mode] = v; S.satd[0][mode] = v; }
       }
     }
     __syncwarp();
@@ -822,7 +840,8 @@ k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcd
     const RmdItem item = items[it];
     const hevcdl_pu pu = pus[item.pu];
     if (item.kind == 1) block_small(S, Y, pitch, geo, pu, item, a8, a4, satd_out, cand_out);
-    else block_large(S, Y, pitch, geo, pu, item, a8, satd_out, cand_out);
+    else if (pu.size == 16) block_large<16>(S, Y, pitch, geo, pu, item, a8, satd_out, cand_out);
+    else block_large<32>(S, Y, pitch, geo, pu, item, a8, satd_out, cand_out);
     if (threadIdx.x == 0) S.next_item = nxt;
     __syncthreads();                            // also: every warp is done with the item's shared memory
     it = S.next_item;
