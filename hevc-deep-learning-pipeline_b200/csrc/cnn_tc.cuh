@@ -64,6 +64,21 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   return v[0];
 }
 
+// Sum of v[e] over the 32 lanes for e in [0,16): every lane l returns the total of element l & 15.
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int j = 0; j < n / 2; j++) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   uint32_t *r = reinterpret_cast<uint32_t *>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -128,20 +143,35 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
   const uint32_t idesc = idesc_bf16(128, 128);
   uint32_t npair = 0;   // running count of tile pairs (same sequence in every role)
 
+  // raw samples of the next CTU, fetched one CTU ahead so the HBM/L2 latency hides behind the epilogue
+  uint32_t pf_y[4] = {0, 0, 0, 0}, pf_u[4] = {0, 0, 0, 0}, pf_v[4] = {0, 0, 0, 0};
+  auto prefetch_ctu = [&](int c) {
+    const int cx = c % geo.ctu_w, cy = c / geo.ctu_w;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int it = tid + 256 * k, y = it >> 4, x4 = (it & 15) * 4;
+      const int gy = cy * 64 + y, gx = cx * 64 + x4;
+      pf_y[k] = 0; pf_u[k] = 0; pf_v[k] = 0;
+      if (gy < geo.H && gx < geo.W) {             // W is a multiple of 8: 4 pixels are in or out together
+        pf_y[k] = __ldg(reinterpret_cast<const uint32_t *>(Y + (size_t)gy * pitch + gx));
+        pf_u[k] = __ldg(reinterpret_cast<const uint16_t *>(U + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
+        pf_v[k] = __ldg(reinterpret_cast<const uint16_t *>(V + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
+      }
+    }
+  };
+  if (warp < 8 && (int)blockIdx.x < geo.nctu) prefetch_ctu(blockIdx.x);
+
   for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x) {
     const int ctu_x = ctu % geo.ctu_w, ctu_y = ctu / geo.ctu_w;
     // ---- staging: (R,G) and (B,0) planes of the CTU and of its four zero-padded quadrants ----
     if (warp < 8) {
-      for (int it = tid; it < 1024; it += 256) {
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const int it = tid + 256 * kk;
         const int y = it >> 4, x4 = (it & 15) * 4;
         const int gy = ctu_y * 64 + y, gx = ctu_x * 64 + x4;
-        uint32_t yv = 0, uv = 0, vv = 0;
-        const bool in = gy < geo.H && gx < geo.W;   // W is a multiple of 8: 4 pixels are in or out together
-        if (in) {
-          yv = *reinterpret_cast<const uint32_t *>(Y + (size_t)gy * pitch + gx);
-          uv = *reinterpret_cast<const uint16_t *>(U + (size_t)(gy >> 1) * cpitch + (gx >> 1));
-          vv = *reinterpret_cast<const uint16_t *>(V + (size_t)(gy >> 1) * cpitch + (gx >> 1));
-        }
+        const uint32_t yv = pf_y[kk], uv = pf_u[kk], vv = pf_v[kk];
+        const bool in = gy < geo.H && gx < geo.W;
         uint32_t rg[4], b0[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -165,6 +195,7 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
       fence_async_smem();
     }
     __syncthreads();
+    if (warp < 8 && ctu + (int)gridDim.x < geo.nctu) prefetch_ctu(ctu + gridDim.x);
 
     if (warp == 8) {
       // ---- MMA issue: 4 tile pairs (conv64 quarters 0-1, 2-3; conv1 quadrants 0-1, 2-3) ----------
@@ -205,6 +236,8 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
       // ---- epilogue: warp = (lane quarter, channel half) ---------------------------------------
       const int lq = warp & 3, h = warp >> 2;
       const int m = lq * 32 + lane, g = m >> 3, ii = m & 7;
+      const float g64r = __ldg(fp + F_G64 + 8 * h + (lane & 7)), b64r = __ldg(fp + F_B64 + 8 * h + (lane & 7));
+      const float g1r = __ldg(fp + F_G1 + 8 * h + (lane & 7)), b1r = __ldg(fp + F_B1 + 8 * h + (lane & 7));
       float s[8], q[8], pool64[4][8];
 #pragma unroll
       for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
@@ -242,29 +275,23 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
           }
           const bool reduce_now = t >= 3;
           if (reduce_now) {
-            // per-channel totals over the sample: lanes (butterfly), then the 4 warps of this half
+            // per-channel totals over the sample: transposing reduction inside the warp (lane l & 15 ends with value
+            // l: sums of channels 0..7, then sums of squares), the 4 warps of this channel half through shared memory
+            float pv[16];
 #pragma unroll
-            for (int c = 0; c < 8; c++)
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
-                q[c] += __shfl_xor_sync(0xffffffffu, q[c], o);
-              }
-            if (lane == 0) {
-#pragma unroll
-              for (int c = 0; c < 8; c++) { red[(rb * 8 + warp) * 16 + c] = s[c]; red[(rb * 8 + warp) * 16 + 8 + c] = q[c]; }
-            }
+            for (int c = 0; c < 8; c++) { pv[c] = s[c]; pv[8 + c] = q[c]; }
+            const float wt = warp_transpose_sum16(pv, lane);
+            if (lane < 16) red[(rb * 8 + warp) * 16 + lane] = wt;
             EPI_BAR_SYNC();
-            const float rcnt = t == 3 ? 1.f / 4096.f : 1.f / 1024.f;   // sample sizes are powers of two: exact
-            const int gofs = t == 3 ? F_G64 : F_G1, bofs = t == 3 ? F_B64 : F_B1;
+            float tot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) tot += red[(rb * 8 + h * 4 + k) * 16 + (lane & 15)];
+            const float totq = __shfl_down_sync(0xffffffffu, tot, 8);       // lanes 0..7: sum of squares of channel `lane`
+            float sc1, sh1;                                                  // scale/shift of channel lane & 7 (valid in lanes 0..7)
+            bn_scale_shift(tot, totq, t == 3 ? 1.f / 4096.f : 1.f / 1024.f, 1e-5f * 255.f * 255.f, t == 3 ? g64r : g1r, t == 3 ? b64r : b1r, sc1, sh1);
             float sc[8], sh[8];
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-              float ts = 0.f, tq = 0.f;
-#pragma unroll
-              for (int k = 0; k < 4; k++) { ts += red[(rb * 8 + h * 4 + k) * 16 + c]; tq += red[(rb * 8 + h * 4 + k) * 16 + 8 + c]; }
-              bn_scale_shift(ts, tq, rcnt, 1e-5f * 255.f * 255.f, __ldg(fp + gofs + 8 * h + c), __ldg(fp + bofs + 8 * h + c), sc[c], sh[c]);
-            }
+            for (int c = 0; c < 8; c++) { sc[c] = __shfl_sync(0xffffffffu, sc1, c); sh[c] = __shfl_sync(0xffffffffu, sh1, c); }
             rb ^= 1;
             uint8_t *cbase = cat + (size_t)ctu * CAT_BYTES;
             if (t == 3) {
@@ -389,6 +416,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   } else {
     const int lq = warp & 3, h = warp >> 2;
     const int m = lq * 32 + lane, yy = m >> 3, xi = m & 7;
+    const float g2r = __ldg(fp + F_G2 + 32 * h + lane), b2r = __ldg(fp + F_B2 + 32 * h + lane);
     uint32_t it = 0, rb = 0;
     for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
 #pragma unroll 1
@@ -429,15 +457,17 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
         }
         EPI_BAR_SYNC();
         const int chunk = 4 * h + 2 * (b0 ? 1 : 0) + (b3 ? 1 : 0);   // 8 channels [8*chunk, 8*chunk+8)
+        // lane l finishes channel 32h + l (totals of the 4 warps of this half), then hands scale/shift to the lanes that need it
+        float a = 0.f, bq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { a += red[(rb * 8 + h * 4 + k) * 64 + lane]; bq += red[(rb * 8 + h * 4 + k) * 64 + 32 + lane]; }
+        float sc1, sh1;
+        bn_scale_shift(a, bq, 1.f / 256.f, 1e-5f, g2r, b2r, sc1, sh1);
         float y0[8], y1[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          const int cl = (chunk & 3) * 8 + c;   // channel index inside this half's 32
-          float a = 0.f, bq = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; k++) { a += red[(rb * 8 + h * 4 + k) * 64 + cl]; bq += red[(rb * 8 + h * 4 + k) * 64 + 32 + cl]; }
-          float sc, sh;
-          bn_scale_shift(a, bq, 1.f / 256.f, 1e-5f, __ldg(fp + F_G2 + 8 * chunk + c), __ldg(fp + F_B2 + 8 * chunk + c), sc, sh);
+          const int srcl = (chunk & 3) * 8 + c;   // channel index inside this half's 32
+          const float sc = __shfl_sync(0xffffffffu, sc1, srcl), sh = __shfl_sync(0xffffffffu, sh1, srcl);
           y0[c] = fmaxf(fmaf(w0[c], sc, sh), 0.f);
           y1[c] = fmaxf(fmaf(w1[c], sc, sh), 0.f);
         }
@@ -586,14 +616,18 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 }
 
 // ================================================================================================
-// K4: fc1 + fc2 (tensor cores), fc3 + argmax + label rules; one CTA = 128 samples = 32 CTUs
+// K4: fc1 + fc2 (tensor cores), fc3 + argmax + label rules; one CTA = FC_NT samples = FC_NT/4 CTUs.
+// fc1 streams its 1 MB of bf16 weights through every CTA, so the sample tile is kept small (more CTAs in flight,
+// 4x less MMA and epilogue time per CTA) rather than large.
 // ================================================================================================
-constexpr int K4_STAGE = 32768 + 16384, K4_NSTAGE = 4;
+constexpr int FC_NT = 32;
+constexpr int K4_STAGE = 32768 + FC_NT * 128, K4_NSTAGE = 4;     // fc1 weights [256 x 64] + features [FC_NT x 64], bf16
 constexpr int K4_BAR = K4_NSTAGE * K4_STAGE, K4_SMEM = K4_BAR + 128;
 // after the fc1 K loop the stage memory is reused:
-constexpr int K4_FC2W = 0, K4_H1 = 65536, K4_H2 = 131072 /* fp32 [128][65] */, K4_F3W = K4_H2 + 128 * 65 * 4 /* [16][64] fp32 */,
-              K4_LG = K4_F3W + 4096 /* fp32 [128][16] */;
-static_assert(K4_LG + 128 * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in the stage memory");
+constexpr int K4_FC2W = 0, K4_H1 = 65536 /* bf16 fc2 operand [FC_NT/8][32][8][8] */, K4_H2 = K4_H1 + FC_NT * 512 /* fp32 [FC_NT][65] */,
+              K4_F3W = K4_H2 + FC_NT * 65 * 4 /* [16][64] fp32 */, K4_LG = K4_F3W + 4096 /* fp32 [FC_NT][16] */;
+static_assert(K4_LG + FC_NT * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in the stage memory");
+static_assert(K4_H2 % 16 == 0 && K4_F3W % 16 == 0, "alignment");
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix,
@@ -615,12 +649,12 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     mbar_init(bar_done, 1); mbar_init(bar_w2, 1); mbar_init(bar_done2, 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  if (warp == 8) tmem_alloc(&tmem_slot, 128);   // fc1: 2 x FC_NT columns, fc2: FC_NT columns
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = tmem_slot;
-  const uint32_t idesc = idesc_bf16(128, 128);
+  const uint32_t idesc = idesc_bf16(128, FC_NT);
   const uint32_t sb = smem_u32(sm);
 
   if (warp == 8) {
@@ -629,7 +663,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
         const int st = kc & 3;
         mbar_expect_tx(&bar_full[st], K4_STAGE);
         bulk_g2s(sm + st * K4_STAGE, blob + OFF_FC1 + (size_t)kc * 32768, 32768, &bar_full[st]);
-        bulk_g2s(sm + st * K4_STAGE + 32768, feats + ((size_t)kc * (npad >> 3) + nt * 16) * 1024, 16384, &bar_full[st]);
+        bulk_g2s(sm + st * K4_STAGE + 32768, feats + ((size_t)kc * (npad >> 3) + nt * (FC_NT / 8)) * 1024, FC_NT * 128, &bar_full[st]);
       };
       for (int kc = 0; kc < K4_NSTAGE; kc++) load(kc);
 #pragma unroll 1
@@ -642,7 +676,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
         for (int t = 0; t < 4; t++) {
           const uint32_t acc = (kc | t) ? 1u : 0u;
           mma_bf16_ss(tbase, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, acc);
-          mma_bf16_ss(tbase + 128, da + (uint64_t)(1024 + t * 16), db + (uint64_t)(t * 16), idesc, acc);
+          mma_bf16_ss(tbase + FC_NT, da + (uint64_t)(1024 + t * 16), db + (uint64_t)(t * 16), idesc, acc);
         }
         mma_commit(&bar_free[st]);
         if (kc >= 1 && kc - 1 + K4_NSTAGE < 32) {   // refill the stage consumed one iteration ago
@@ -657,7 +691,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     }
     __syncwarp();
   } else {
-    // fc1 epilogue: thread = output o, 128 sample columns -> relu -> bf16 -> fc2 B operand [n][k=o]
+    // fc1 epilogue: thread = output o, FC_NT sample columns -> relu -> bf16 -> fc2 B operand [n][k=o]
     const int lq = warp & 3, mh = warp >> 2;
     const int o = mh * 128 + lq * 32 + lane;
     const float bias = __ldg(fp + F_F1B + o);
@@ -665,9 +699,9 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     fence_after_sync();
     for (int f = tid; f < 16 * 64; f += 256) reinterpret_cast<float *>(sm + K4_F3W)[f] = __ldg(fp + F_F3W + f);
 #pragma unroll 1
-    for (int cb = 0; cb < 128; cb += 32) {
+    for (int cb = 0; cb < FC_NT; cb += 32) {
       float v[32];
-      tmem_ld32(tmem_addr(tbase, lq * 32, mh * 128 + cb), v);
+      tmem_ld32(tmem_addr(tbase, lq * 32, mh * FC_NT + cb), v);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j++) {
@@ -686,25 +720,25 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
       mbar_wait(bar_w2, 0);
       const uint64_t da = smem_desc(sb + K4_FC2W, 128, 4096), db = smem_desc(sb + K4_H1, 128, 4096);
 #pragma unroll
-      for (int t = 0; t < 16; t++) mma_bf16_ss(tbase + 256, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t ? 1u : 0u);
+      for (int t = 0; t < 16; t++) mma_bf16_ss(tbase + 2 * FC_NT, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t ? 1u : 0u);
       mma_commit(bar_done2);
     }
     __syncwarp();
   } else {
-    const int lq = warp & 3, nh = warp >> 2;   // lanes = fc2 outputs (0..63 real), nh = sample half
+    const int lq = warp & 3;   // lanes = fc2 outputs (0..63 real): warps 0 and 1 read them back
     mbar_wait(bar_done2, 0);
     fence_after_sync();
-    if (lq < 2) {
+    if (warp < 2) {
       const int o = lq * 32 + lane;
       const float bias = __ldg(fp + F_F2B + o);
       float *h2 = reinterpret_cast<float *>(sm + K4_H2);
 #pragma unroll 1
-      for (int cb = 0; cb < 64; cb += 32) {
+      for (int cb = 0; cb < FC_NT; cb += 32) {
         float v[32];
-        tmem_ld32(tmem_addr(tbase, lq * 32, 256 + nh * 64 + cb), v);
+        tmem_ld32(tmem_addr(tbase, lq * 32, 2 * FC_NT + cb), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j++) h2[(nh * 64 + cb + j) * 65 + o] = fmaxf(v[j] + bias, 0.f);
+        for (int j = 0; j < 32; j++) h2[(cb + j) * 65 + o] = fmaxf(v[j] + bias, 0.f);
       }
     }
     fence_before_sync();
@@ -712,7 +746,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
   __syncthreads();
   // fc3 (use_model.py:40,57): one thread per sample
   float *lg = reinterpret_cast<float *>(sm + K4_LG);
-  if (tid < 128) {
+  if (tid < FC_NT) {
     const float *h2 = reinterpret_cast<const float *>(sm + K4_H2) + tid * 65;
     const float *w3 = reinterpret_cast<const float *>(sm + K4_F3W);
     float acc[16];
@@ -723,7 +757,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
 #pragma unroll
       for (int o = 0; o < 16; o++) acc[o] = fmaf(w3[o * 64 + i], x, acc[o]);
     }
-    const int n = nt * 128 + tid;
+    const int n = nt * FC_NT + tid;
 #pragma unroll
     for (int o = 0; o < 16; o++) lg[tid * 16 + o] = acc[o];
     if (n < 4 * geo.nctu && logits_out)
@@ -731,8 +765,8 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
       for (int o = 0; o < 16; o += 4) *reinterpret_cast<float4 *>(logits_out + (size_t)n * 16 + o) = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
   }
   __syncthreads();
-  if (tid < 32) {
-    const int ctu = nt * 32 + tid;
+  if (tid < FC_NT / 4) {
+    const int ctu = nt * (FC_NT / 4) + tid;
     if (ctu < geo.nctu) {
       uint8_t lab[16];
       logits_to_labels(lg + tid * 64, lab, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H, boundary_fix);
@@ -745,7 +779,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tbase, 512);
+  if (warp == 8) tmem_dealloc(tbase, 128);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -795,7 +829,7 @@ inline int tc_launch(const TcParams &p, const uint8_t *Y, const uint8_t *U, cons
   k_tc_l1<<<grid, TC_THREADS, K1_SMEM, st>>>(Y, U, V, g, pitch, cpitch, p.blob, p.cat);
   k_tc_conv2<<<grid, TC_THREADS, K2_SMEM, st>>>(g, p.blob, p.cat, p.a2);
   k_tc_conv3<<<grid, TC_THREADS, K3_SMEM, st>>>(g, p.blob, p.a2, p.feats, p.npad);
-  k_tc_fc<<<p.npad / 128, TC_THREADS, K4_SMEM, st>>>(g, p.blob, p.feats, p.npad, boundary_fix, labels, logits, ctu_cnt);
+  k_tc_fc<<<p.npad / FC_NT, TC_THREADS, K4_SMEM, st>>>(g, p.blob, p.feats, p.npad, boundary_fix, labels, logits, ctu_cnt);
   return 4;
 }
 
