@@ -158,6 +158,8 @@ k_cnn_fp32(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const u
            FrameGeom geo, int pitch, int cpitch, Fp32Params P, int boundary_fix, uint8_t *__restrict__ labels,
            float *__restrict__ logits_out, uint32_t *__restrict__ ctu_cnt) {
   extern __shared__ float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   float *regAC = smem;                 // img, then conv2 out
   float *regB = smem + SM_AC;          // conv1/conv64 out, then conv3 out
   float *fc1o = regB + SM_B, *fc2o = fc1o + 4 * 256, *lgt = fc2o + 4 * 64;

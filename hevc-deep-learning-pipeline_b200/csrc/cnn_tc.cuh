@@ -123,6 +123,7 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
   float *red = reinterpret_cast<float *>(sm + K1_RED);              // [2][8 warps][16]
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
@@ -159,6 +160,7 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
       }
     }
   };
+  pdl_wait();                                   // prologue done; from here on global memory of the frame is touched
   if (warp < 8 && (int)blockIdx.x < geo.nctu) prefetch_ctu(blockIdx.x);
 
   for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x) {
@@ -352,6 +354,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   float *red = reinterpret_cast<float *>(sm + K2_RED);              // [2][8 warps][64]
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 8); }
@@ -370,6 +373,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
     if (elect_one()) {
       mbar_expect_tx(bar_w, SZ_W2);
       for (int i = 0; i < 9; i++) bulk_g2s(sm + K2_W + i * 4096, blob + OFF_W2 + i * 4096, 4096, bar_w);
+      pdl_wait();                               // the weights are on their way; cat is the predecessor's output
       if ((int)blockIdx.x < geo.nctu) {
         mbar_expect_tx(&bar_cfull[0], CAT_BYTES);
         bulk_g2s(sm + K2_CAT, cat + (size_t)blockIdx.x * CAT_BYTES, CAT_BYTES, &bar_cfull[0]);
@@ -503,6 +507,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   float *red = reinterpret_cast<float *>(sm + K3_RED);              // [2][2 halves][8][128]
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     for (int i = 0; i < 2; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 8); }
@@ -521,6 +526,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
     if (elect_one()) {
       mbar_expect_tx(bar_w, SZ_W3);
       for (int i = 0; i < 36; i++) bulk_g2s(sm + K3_W + i * 4096, blob + OFF_W3 + i * 4096, 4096, bar_w);
+      pdl_wait();                               // a2 is the predecessor's output
       if ((int)blockIdx.x < geo.nctu)
         for (int j = 0; j < 4; j++) {
           mbar_expect_tx(&bar_afull[j], 2 * A2_PLANE);
@@ -620,14 +626,23 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 // fc1 streams its 1 MB of bf16 weights through every CTA, so the sample tile is kept small (more CTAs in flight,
 // 4x less MMA and epilogue time per CTA) rather than large.
 // ================================================================================================
-constexpr int FC_NT = 32;
-constexpr int K4_STAGE = 32768 + FC_NT * 128, K4_NSTAGE = 4;     // fc1 weights [256 x 64] + features [FC_NT x 64], bf16
-constexpr int K4_BAR = K4_NSTAGE * K4_STAGE, K4_SMEM = K4_BAR + 128;
+#ifndef HEVCDL_FC_NT
+#define HEVCDL_FC_NT 32
+#endif
+#ifndef HEVCDL_FC_NSTAGE
+#define HEVCDL_FC_NSTAGE 4
+#endif
+constexpr int FC_NT = HEVCDL_FC_NT;
+constexpr int K4_STAGE = 32768 + FC_NT * 128, K4_NSTAGE = HEVCDL_FC_NSTAGE;     // fc1 weights [256 x 64] + features [FC_NT x 64], bf16
+constexpr int K4_BAR = K4_NSTAGE * K4_STAGE;
+constexpr int K4_FC2W = (K4_BAR + 128 + 1023) / 1024 * 1024;     // fc2 weights, loaded in the prologue
+constexpr int K4_F3W = K4_FC2W + SZ_FC2;                           // fc3 weights transposed, fp32 [64][16]
+constexpr int K4_SMEM = K4_F3W + 4096;
+static_assert(K4_SMEM <= 227 * 1024, "K4 shared memory");
 // after the fc1 K loop the stage memory is reused:
-constexpr int K4_FC2W = 0, K4_H1 = 65536 /* bf16 fc2 operand [FC_NT/8][32][8][8] */, K4_H2 = K4_H1 + FC_NT * 512 /* fp32 [FC_NT][65] */,
-              K4_F3W = K4_H2 + FC_NT * 65 * 4 /* [16][64] fp32 */, K4_LG = K4_F3W + 4096 /* fp32 [FC_NT][16] */;
+constexpr int K4_H1 = 0 /* bf16 fc2 operand [FC_NT/8][32][8][8] */, K4_H2 = K4_H1 + FC_NT * 512 /* fp32 [FC_NT][65] */,
+              K4_LG = K4_H2 + (FC_NT * 65 * 4 + 15) / 16 * 16 /* fp32 [FC_NT][16] */;
 static_assert(K4_LG + FC_NT * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in the stage memory");
-static_assert(K4_H2 % 16 == 0 && K4_F3W % 16 == 0, "alignment");
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix,
@@ -635,17 +650,26 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
-  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K4_BAR);   // [4]
-  uint64_t *bar_free = bar_full + 4;                                // [4]
-  uint64_t *bar_done = bar_full + 8;                                // fc1 accumulators complete
-  uint64_t *bar_w2 = bar_full + 9;                                  // fc2 weights landed
-  uint64_t *bar_done2 = bar_full + 10;
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K4_BAR);   // [K4_NSTAGE]
+  uint64_t *bar_free = bar_full + 6;                                // [K4_NSTAGE]
+  uint64_t *bar_done = bar_full + 12;                                // fc1 accumulators complete
+  uint64_t *bar_w2 = bar_full + 13;                                 // fc2 weights landed
+  uint64_t *bar_done2 = bar_full + 14;
+  static_assert(K4_NSTAGE <= 6, "barrier slots");
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nt = blockIdx.x;   // sample tile
+  pdl_launch_dependents();
+#ifdef HEVCDL_FC_TRACE
+  long long tr[8];
+#define FC_TR(i) tr[i] = clock64()
+#else
+#define FC_TR(i)
+#endif
+  FC_TR(0);
 
   if (tid == 0) {
-    for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_free[i], 1); }
+    for (int i = 0; i < K4_NSTAGE; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_free[i], 1); }
     mbar_init(bar_done, 1); mbar_init(bar_w2, 1); mbar_init(bar_done2, 1);
     mbar_init_fence();
   }
@@ -659,17 +683,25 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
 
   if (warp == 8) {
     if (elect_one()) {
-      auto load = [&](int kc) {
-        const int st = kc & 3;
+      auto load_w = [&](int kc) {                // constant operand: fc1 weights of K chunk kc
+        const int st = kc % K4_NSTAGE;
         mbar_expect_tx(&bar_full[st], K4_STAGE);
         bulk_g2s(sm + st * K4_STAGE, blob + OFF_FC1 + (size_t)kc * 32768, 32768, &bar_full[st]);
+      };
+      auto load_f = [&](int kc) {                // the predecessor's output: features of this sample tile
+        const int st = kc % K4_NSTAGE;
         bulk_g2s(sm + st * K4_STAGE + 32768, feats + ((size_t)kc * (npad >> 3) + nt * (FC_NT / 8)) * 1024, FC_NT * 128, &bar_full[st]);
       };
-      for (int kc = 0; kc < K4_NSTAGE; kc++) load(kc);
+      auto load = [&](int kc) { load_w(kc); load_f(kc); };
+      mbar_expect_tx(bar_w2, SZ_FC2);
+      for (int i = 0; i < 16; i++) bulk_g2s(sm + K4_FC2W + i * 4096, blob + OFF_FC2 + i * 4096, 4096, bar_w2);
+      for (int kc = 0; kc < K4_NSTAGE; kc++) load_w(kc);
+      pdl_wait();
+      for (int kc = 0; kc < K4_NSTAGE; kc++) load_f(kc);
 #pragma unroll 1
       for (int kc = 0; kc < 32; kc++) {
-        const int st = kc & 3;
-        mbar_wait(&bar_full[st], (kc >> 2) & 1);
+        const int st = kc % K4_NSTAGE;
+        mbar_wait(&bar_full[st], (kc / K4_NSTAGE) & 1);
         fence_after_sync();
         const uint64_t da = smem_desc(sb + st * K4_STAGE, 128, 1024), db = smem_desc(sb + st * K4_STAGE + 32768, 128, 1024);
 #pragma unroll
@@ -680,14 +712,11 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
         }
         mma_commit(&bar_free[st]);
         if (kc >= 1 && kc - 1 + K4_NSTAGE < 32) {   // refill the stage consumed one iteration ago
-          mbar_wait(&bar_free[(kc - 1) & 3], ((kc - 1) >> 2) & 1);
+          mbar_wait(&bar_free[(kc - 1) % K4_NSTAGE], ((kc - 1) / K4_NSTAGE) & 1);
           load(kc - 1 + K4_NSTAGE);
         }
       }
       mma_commit(bar_done);
-      mbar_wait(bar_done, 0);   // all stage memory is free now: bring in the fc2 weights
-      mbar_expect_tx(bar_w2, SZ_FC2);
-      for (int i = 0; i < 16; i++) bulk_g2s(sm + K4_FC2W + i * 4096, blob + OFF_FC2 + i * 4096, 4096, bar_w2);
     }
     __syncwarp();
   } else {
@@ -695,16 +724,19 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     const int lq = warp & 3, mh = warp >> 2;
     const int o = mh * 128 + lq * 32 + lane;
     const float bias = __ldg(fp + F_F1B + o);
+    for (int f = tid; f < 16 * 64; f += 256)    // fc3 weights [16][64] -> [64][16]: conflict-free reads in the fc3 step
+      reinterpret_cast<float *>(sm + K4_F3W)[(f & 63) * 16 + (f >> 6)] = __ldg(fp + F_F3W + f);
+    FC_TR(1);
     mbar_wait(bar_done, 0);
     fence_after_sync();
-    for (int f = tid; f < 16 * 64; f += 256) reinterpret_cast<float *>(sm + K4_F3W)[f] = __ldg(fp + F_F3W + f);
+    FC_TR(2);
 #pragma unroll 1
     for (int cb = 0; cb < FC_NT; cb += 32) {
       float v[32];
       tmem_ld32(tmem_addr(tbase, lq * 32, mh * FC_NT + cb), v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
+      for (int j = 0; j < (FC_NT < 32 ? FC_NT : 32); j++) {
         const int n = cb + j;
         const __nv_bfloat16 hv = __float2bfloat16(fmaxf(v[j] + bias, 0.f));
         *reinterpret_cast<__nv_bfloat16 *>(sm + K4_H1 + (n >> 3) * 4096 + (o >> 3) * 128 + (n & 7) * 16 + (o & 7) * 2) = hv;
@@ -712,6 +744,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     }
     fence_async_smem();
     fence_before_sync();
+    FC_TR(3);
   }
   __syncthreads();
   fence_after_sync();
@@ -728,6 +761,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     const int lq = warp & 3;   // lanes = fc2 outputs (0..63 real): warps 0 and 1 read them back
     mbar_wait(bar_done2, 0);
     fence_after_sync();
+    FC_TR(4);
     if (warp < 2) {
       const int o = lq * 32 + lane;
       const float bias = __ldg(fp + F_F2B + o);
@@ -738,33 +772,32 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
         tmem_ld32(tmem_addr(tbase, lq * 32, 2 * FC_NT + cb), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j++) h2[(cb + j) * 65 + o] = fmaxf(v[j] + bias, 0.f);
+        for (int j = 0; j < (FC_NT < 32 ? FC_NT : 32); j++) h2[(cb + j) * 65 + o] = fmaxf(v[j] + bias, 0.f);
       }
     }
     fence_before_sync();
   }
   __syncthreads();
+  FC_TR(5);
   // fc3 (use_model.py:40,57): one thread per sample
   float *lg = reinterpret_cast<float *>(sm + K4_LG);
-  if (tid < FC_NT) {
-    const float *h2 = reinterpret_cast<const float *>(sm + K4_H2) + tid * 65;
-    const float *w3 = reinterpret_cast<const float *>(sm + K4_F3W);
-    float acc[16];
-#pragma unroll
-    for (int o = 0; o < 16; o++) acc[o] = __ldg(fp + F_F3B + o);
+  if (tid < FC_NT * 8) {                        // 8 threads per sample, two logits each
+    const int smp = tid >> 3, o2 = (tid & 7) * 2;
+    const float *h2 = reinterpret_cast<const float *>(sm + K4_H2) + smp * 65;
+    const float *w3 = reinterpret_cast<const float *>(sm + K4_F3W) + o2;
+    float a0 = __ldg(fp + F_F3B + o2), a1 = __ldg(fp + F_F3B + o2 + 1);
+#pragma unroll 8
     for (int i = 0; i < 64; i++) {
       const float x = h2[i];
-#pragma unroll
-      for (int o = 0; o < 16; o++) acc[o] = fmaf(w3[o * 64 + i], x, acc[o]);
+      const float2 w = *reinterpret_cast<const float2 *>(w3 + i * 16);
+      a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1);
     }
-    const int n = nt * FC_NT + tid;
-#pragma unroll
-    for (int o = 0; o < 16; o++) lg[tid * 16 + o] = acc[o];
-    if (n < 4 * geo.nctu && logits_out)
-#pragma unroll
-      for (int o = 0; o < 16; o += 4) *reinterpret_cast<float4 *>(logits_out + (size_t)n * 16 + o) = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+    const int n = nt * FC_NT + smp;
+    *reinterpret_cast<float2 *>(lg + smp * 16 + o2) = make_float2(a0, a1);
+    if (n < 4 * geo.nctu && logits_out) *reinterpret_cast<float2 *>(logits_out + (size_t)n * 16 + o2) = make_float2(a0, a1);
   }
   __syncthreads();
+  FC_TR(6);
   if (tid < FC_NT / 4) {
     const int ctu = nt * (FC_NT / 4) + tid;
     if (ctu < geo.nctu) {
@@ -779,6 +812,12 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
   }
   fence_before_sync();
   __syncthreads();
+  FC_TR(7);
+#ifdef HEVCDL_FC_TRACE
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("fc trace blk %d: setup %lld loop %lld fc1epi %lld fc2 %lld fc2epi %lld fc3 %lld labels %lld total %lld clk\n", (int)blockIdx.x,
+           tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[7] - tr[0]);
+#endif
   if (warp == 8) tmem_dealloc(tbase, 128);
 }
 
@@ -822,14 +861,26 @@ inline int tc_configure(std::string &err) {
   return HEVCDL_OK;
 }
 
-// Queue the four CNN kernels of one frame.  Returns the number of kernels launched.
+template <typename... KArgs, typename... Args>
+inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Queue the four CNN kernels of one frame (programmatic dependent launch: each kernel's prologue overlaps its
+// predecessor's tail).  Returns the number of kernels launched.
 inline int tc_launch(const TcParams &p, const uint8_t *Y, const uint8_t *U, const uint8_t *V, FrameGeom g, int pitch, int cpitch,
                      int boundary_fix, uint8_t *labels, float *logits, uint32_t *ctu_cnt, int num_sms, cudaStream_t st) {
   const int grid = g.nctu < num_sms ? g.nctu : num_sms;
-  k_tc_l1<<<grid, TC_THREADS, K1_SMEM, st>>>(Y, U, V, g, pitch, cpitch, p.blob, p.cat);
-  k_tc_conv2<<<grid, TC_THREADS, K2_SMEM, st>>>(g, p.blob, p.cat, p.a2);
-  k_tc_conv3<<<grid, TC_THREADS, K3_SMEM, st>>>(g, p.blob, p.a2, p.feats, p.npad);
-  k_tc_fc<<<p.npad / FC_NT, TC_THREADS, K4_SMEM, st>>>(g, p.blob, p.feats, p.npad, boundary_fix, labels, logits, ctu_cnt);
+  tc_launch_pdl(k_tc_l1, grid, K1_SMEM, st, Y, U, V, g, pitch, cpitch, p.blob, p.cat);
+  tc_launch_pdl(k_tc_conv2, grid, K2_SMEM, st, g, p.blob, (const uint8_t *)p.cat, p.a2);
+  tc_launch_pdl(k_tc_conv3, grid, K3_SMEM, st, g, p.blob, (const uint8_t *)p.a2, p.feats, p.npad);
+  tc_launch_pdl(k_tc_fc, p.npad / FC_NT, K4_SMEM, st, g, p.blob, (const uint8_t *)p.feats, p.npad, boundary_fix, labels, logits, ctu_cnt);
   return 4;
 }
 

@@ -30,6 +30,13 @@ struct Fp32Params {
   const float *f3wT, *f3b;               // [64][16]
 };
 
+// Programmatic dependent launch (PDL): every kernel of the frame pipeline lets its successor start early
+// (pdl_launch_dependents at entry) and runs its own prologue -- barrier init, TMEM allocation, weight loads --
+// before pdl_wait(), which returns once the predecessor grid has completed and its writes are visible.  Without
+// the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct FrameGeom {
   int W, H;        // luma size
   int ctu_w, ctu_h, nctu;

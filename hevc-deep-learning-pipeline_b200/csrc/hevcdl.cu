@@ -18,6 +18,18 @@ using namespace hevcdl;
 
 namespace {
 
+// Kernel launch with the programmatic-dependent-launch attribute (common.cuh: pdl_wait / pdl_launch_dependents).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 enum SlotState { SLOT_FREE = 0, SLOT_QUEUED = 1, SLOT_DONE = 2 };
 
 struct Slot {
@@ -200,16 +212,15 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot &s, bool timed) {
                           s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr, ctx->numSMs, ctx->stream);
   } else {
     const int grid = g.nctu < 4 * ctx->numSMs ? g.nctu : 4 * ctx->numSMs;
-    k_cnn_fp32<<<grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream>>>(s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch,
-                                                                    ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits,
-                                                                    ctx->cfg.rmd ? s.dCtuCnt : nullptr);
+    launch_pdl(k_cnn_fp32, grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream, s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch, ctx->fp,
+               ctx->cfg.boundary_fix, s.dLabels, s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr);
     launches++;
   }
   if (timed) cudaEventRecord(s.evT1, ctx->stream);
   if (ctx->cfg.rmd) {
-    k_rmd_plan<<<(g.nctu + 7) / 8, 256, 0, ctx->stream>>>(s.dLabels, s.dCtuCnt, gd, ctx->rmdBlocks, s.dCtuOff, s.dPus, s.dItems, s.dSatd,
-                                                          s.dCand, s.dCtrl);
-    k_rmd_items<<<ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream>>>(s.dY, gd, ctx->pitch, s.dPus, s.dItems, s.dCtrl, s.dSatd, s.dCand);
+    launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, ctx->stream, s.dLabels, s.dCtuCnt, gd, ctx->rmdBlocks, s.dCtuOff, s.dPus, s.dItems,
+               s.dSatd, s.dCand, s.dCtrl);
+    launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream, s.dY, gd, ctx->pitch, s.dPus, s.dItems, s.dCtrl, s.dSatd, s.dCand);
     launches += 2;
   }
   if (timed) cudaEventRecord(s.evT2, ctx->stream);

@@ -373,6 +373,8 @@ k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_
            int *__restrict__ ctu_off, hevcdl_pu *__restrict__ pus, RmdItem *__restrict__ items, uint32_t *__restrict__ satd,
            uint8_t *__restrict__ cand, int *__restrict__ ctrl) {
   const int lane = threadIdx.x & 31, ctu = blockIdx.x * 8 + (threadIdx.x >> 5);
+  pdl_launch_dependents();
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = items_grid;
   if (ctu >= geo.nctu) return;
   // counts of the preceding CTUs (PUs, big items, small items) and the frame's total of big items
@@ -832,6 +834,8 @@ k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcd
     const bool on = (g >> 2) == (t >> 1);
     a4 = on ? (((__popc((g & 3) & (c0 & 3)) & 1) ? neg : one) | (((__popc((g & 3) & (c1 & 3)) & 1) ? neg : one) << 16)) : 0u;
   }
+  pdl_launch_dependents();
+  pdl_wait();
   const int nitems = ctrl[1];
   int it = blockIdx.x;                          // first round is static: k_rmd_plan started the counter at gridDim.x
   while (it < nitems) {

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libhevcdl.so")
+LIB_PATH = os.environ.get("HEVCDL_LIB") or os.path.join(_HERE, "csrc", "libhevcdl.so")   # HEVCDL_LIB: tuning builds only
 DEFAULT_WEIGHTS = os.path.join(os.path.dirname(_HERE), "weights", "hevc_encoder_model.hdlw")
 
 PREC_FP32, PREC_BF16_TC = 0, 1
