@@ -1,7 +1,9 @@
 // hevcdl.cu -- C-ABI implementation (include/hevcdl.h) over the sm_100a kernels.
-// Host side: frame slots, pinned staging, one compute stream + one D2H stream, CUDA events.
+// Host side: frame slots, pinned staging, three streams (copies in, kernels, copies out) chained by CUDA events,
+// so the H2D copy of frame i+1 and the D2H copies of frame i-1 overlap the kernels of frame i.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -56,7 +58,7 @@ struct Slot {
   uint8_t *hCand = nullptr;
   size_t hPuCap = 0;
   bool pusFetched = false;
-  cudaEvent_t evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
+  cudaEvent_t evIn = nullptr, evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
 };
 
 }  // namespace
@@ -66,7 +68,8 @@ struct hevcdl_ctx {
   FrameGeom geo{};
   int pitch = 0, cpitch = 0;           // device plane pitches (bytes)
   size_t puCap = 0;
-  cudaStream_t stream = nullptr, d2h = nullptr;
+  cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;   // kernels / copies in / labels out
+  cudaStream_t d2hPu = nullptr;        // PU lists out, on demand (its own stream: must not queue behind later frames' label copies)
   std::vector<Slot> slots;
   float *dWeights = nullptr;           // raw HDLW blob
   float *dPacked = nullptr;            // fp32-path packed weights
@@ -180,6 +183,7 @@ int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
   CK(cudaMallocHost(&s.hLabels, (size_t)g.nctu * 16));
   CK(cudaMallocHost(&s.hLogits, (size_t)g.nctu * 64 * sizeof(float)));
   CK(cudaMallocHost(&s.hCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
+  CK(cudaEventCreateWithFlags(&s.evIn, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.evLabels, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.evRmd, cudaEventDisableTiming));
   CK(cudaEventCreate(&s.evT0)); CK(cudaEventCreate(&s.evT1)); CK(cudaEventCreate(&s.evT2));
@@ -245,10 +249,13 @@ int submit_impl(hevcdl_ctx *ctx, int frame, const T *y, int sy, const T *u, cons
     else cudaGetLastError();
     src_y = reinterpret_cast<const uint8_t *>(y);
   }
-  if (direct) {
-    CK(cudaMemcpy2DAsync(s->dY, P, src_y, sy, W, H, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(s->dU, CP, u, sc, W / 2, H / 2, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(s->dV, CP, v, sc, W / 2, H / 2, cudaMemcpyHostToDevice, ctx->stream));
+  if (direct && sy == P && sc == CP && (const uint8_t *)u == src_y + (size_t)P * H && (const uint8_t *)v == (const uint8_t *)u + (size_t)CP * (H / 2)) {
+    // one contiguous pinned I420 frame whose strides equal the device pitches: a single copy
+    CK(cudaMemcpyAsync(s->dY, src_y, (size_t)P * H + 2 * (size_t)CP * (H / 2), cudaMemcpyHostToDevice, ctx->h2d));
+  } else if (direct) {
+    CK(cudaMemcpy2DAsync(s->dY, P, src_y, sy, W, H, cudaMemcpyHostToDevice, ctx->h2d));
+    CK(cudaMemcpy2DAsync(s->dU, CP, u, sc, W / 2, H / 2, cudaMemcpyHostToDevice, ctx->h2d));
+    CK(cudaMemcpy2DAsync(s->dV, CP, v, sc, W / 2, H / 2, cudaMemcpyHostToDevice, ctx->h2d));
   } else {
     for (int r = 0; r < H; r++) {
       const T *row = y + (size_t)r * sy;
@@ -260,17 +267,20 @@ int submit_impl(hevcdl_ctx *ctx, int frame, const T *y, int sy, const T *u, cons
       if (sizeof(T) == 1) { memcpy(hu + (size_t)r * CP, ru, W / 2); memcpy(hv + (size_t)r * CP, rv, W / 2); }
       else for (int x = 0; x < W / 2; x++) { hu[(size_t)r * CP + x] = (uint8_t)ru[x]; hv[(size_t)r * CP + x] = (uint8_t)rv[x]; }
     }
-    CK(cudaMemcpyAsync(s->dY, s->hPlanes, (size_t)P * H + 2 * (size_t)CP * (H / 2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s->dY, s->hPlanes, (size_t)P * H + 2 * (size_t)CP * (H / 2), cudaMemcpyHostToDevice, ctx->h2d));
   }
+  CK(cudaEventRecord(s->evIn, ctx->h2d));
+  CK(cudaStreamWaitEvent(ctx->stream, s->evIn, 0));
   s->frame = frame; s->state = SLOT_QUEUED; s->pusFetched = false;
   ctx->stats.kernel_launches += launch_pipeline(ctx, *s, true);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(s->evRmd, ctx->stream));                 // every kernel of the frame is done
+  CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
+  CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->d2h));
+  CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
   if (ctx->cfg.rmd)
-    CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaEventRecord(s->evLabels, ctx->stream));
-  CK(cudaEventRecord(s->evRmd, ctx->stream));
+    CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h));
+  CK(cudaEventRecord(s->evLabels, ctx->d2h));
   return HEVCDL_OK;
 }
 
@@ -293,13 +303,13 @@ int fetch_pus(hevcdl_ctx *ctx, Slot *s) {
   const size_t n = (size_t)s->hCtuOff[ctx->geo.nctu];
   int rc = ensure_host_pu_cap(ctx, *s, n ? n : 1);
   if (rc) return rc;
-  CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
+  CK(cudaStreamWaitEvent(ctx->d2hPu, s->evRmd, 0));
   if (n) {
-    CK(cudaMemcpyAsync(s->hPus, s->dPus, n * sizeof(hevcdl_pu), cudaMemcpyDeviceToHost, ctx->d2h));
-    CK(cudaMemcpyAsync(s->hSatd, s->dSatd, n * 35 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->d2h));
-    CK(cudaMemcpyAsync(s->hCand, s->dCand, n * 8, cudaMemcpyDeviceToHost, ctx->d2h));
+    CK(cudaMemcpyAsync(s->hPus, s->dPus, n * sizeof(hevcdl_pu), cudaMemcpyDeviceToHost, ctx->d2hPu));
+    CK(cudaMemcpyAsync(s->hSatd, s->dSatd, n * 35 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->d2hPu));
+    CK(cudaMemcpyAsync(s->hCand, s->dCand, n * 8, cudaMemcpyDeviceToHost, ctx->d2hPu));
   }
-  CK(cudaStreamSynchronize(ctx->d2h));
+  CK(cudaStreamSynchronize(ctx->d2hPu));
   s->pusFetched = true;
   return HEVCDL_OK;
 }
@@ -366,6 +376,8 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   };
   if (cu(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
   if (cu(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
+  if (cu(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
+  if (cu(cudaStreamCreateWithFlags(&ctx->d2hPu, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
   if ((rc = load_weights(ctx))) return fail(rc);
   ctx->cfg.weights_path = nullptr;
   if (cu(cudaFuncSetAttribute(k_cnn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_BYTES), "smem attr") ||
@@ -390,13 +402,16 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
 void hevcdl_destroy(hevcdl_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+  if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+  if (ctx->d2hPu) cudaStreamSynchronize(ctx->d2hPu);
   for (auto &s : ctx->slots) {
     cudaFree(s.dY); cudaFree(s.dLabels); cudaFree(s.dLogits); cudaFree(s.dCtuOff);
     cudaFree(s.dPus); cudaFree(s.dSatd); cudaFree(s.dCand); cudaFree(s.dCtuCnt); cudaFree(s.dCtrl); cudaFree(s.dItems);
     cudaFreeHost(s.hPlanes); cudaFreeHost(s.hLabels); cudaFreeHost(s.hLogits); cudaFreeHost(s.hCtuOff);
     cudaFreeHost(s.hPus); cudaFreeHost(s.hSatd); cudaFreeHost(s.hCand);
+    if (s.evIn) cudaEventDestroy(s.evIn);
     if (s.evLabels) cudaEventDestroy(s.evLabels);
     if (s.evRmd) cudaEventDestroy(s.evRmd);
     if (s.evT0) cudaEventDestroy(s.evT0);
@@ -407,6 +422,8 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
   tc_release(&ctx->tc);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+  if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+  if (ctx->d2hPu) cudaStreamDestroy(ctx->d2hPu);
   cudaGetLastError();
   delete ctx;
 }
@@ -482,6 +499,25 @@ int hevcdl_ctu_pu_range(hevcdl_ctx *ctx, int frame, int addr, int *first, int *c
   if (rc) return rc;
   *first = s->hCtuOff[addr];
   *count = s->hCtuOff[addr + 1] - s->hCtuOff[addr];
+  return HEVCDL_OK;
+}
+
+int hevcdl_frame_view_get(hevcdl_ctx *ctx, int frame, int want_pus, hevcdl_frame_view *out) {
+  if (!ctx || !out) return HEVCDL_E_INVAL;
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  memset(out, 0, sizeof *out);
+  out->labels = s->hLabels; out->logits = s->hLogits; out->nctu = ctx->geo.nctu;
+  if (ctx->cfg.rmd) {
+    out->ctu_off = s->hCtuOff;
+    if (want_pus) {
+      if ((rc = fetch_pus(ctx, s))) return rc;
+      out->npu = s->hCtuOff[ctx->geo.nctu];
+      out->pus = s->hPus; out->satd = s->hSatd; out->cand = s->hCand;
+    }
+  }
   return HEVCDL_OK;
 }
 
@@ -591,6 +627,40 @@ int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int i
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (launches) *launches = nl / 2;
   ctx->stats.kernel_launches += nl;
+  return HEVCDL_OK;
+}
+
+int hevcdl_bench_e2e(hevcdl_ctx *ctx, int first_id, int iters, int depth, int nbuf, const uint8_t *const *y,
+                     const uint8_t *const *u, const uint8_t *const *v, int stride_y, int stride_c, double *seconds,
+                     uint64_t *d2h_bytes, uint64_t *checksum) {
+  if (!ctx || iters <= 0 || depth <= 0 || nbuf <= 0 || !y || !u || !v || !seconds) return HEVCDL_E_INVAL;
+  if (depth > (int)ctx->slots.size()) depth = (int)ctx->slots.size();
+  uint64_t bytes = 0, chk = 0;
+  const int nctu = ctx->geo.nctu;
+  auto consume = [&](int frame) -> int {
+    hevcdl_frame_view fv;
+    int rc = hevcdl_frame_view_get(ctx, frame, ctx->cfg.rmd, &fv);
+    if (rc) return rc;
+    bytes += (uint64_t)nctu * 16 + (uint64_t)nctu * 64 * sizeof(float);
+    chk += fv.labels[(size_t)nctu * 16 - 1];
+    if (fv.ctu_off) bytes += ((uint64_t)nctu + 1) * sizeof(int32_t);
+    if (fv.npu > 0) {
+      bytes += (uint64_t)fv.npu * (sizeof(hevcdl_pu) + 35 * sizeof(uint32_t) + 8);
+      chk += fv.cand[(size_t)fv.npu * 8 - 8] + fv.satd[(size_t)fv.npu * 35 - 1];
+    }
+    return hevcdl_release_frame(ctx, frame);
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  int done = 0;
+  for (int i = 0; i < iters; i++) {
+    int rc = hevcdl_submit_frame_u8(ctx, first_id + i, y[i % nbuf], stride_y, u[i % nbuf], v[i % nbuf], stride_c);
+    if (rc) return rc;
+    if (i + 1 - done >= depth) { rc = consume(first_id + done); if (rc) return rc; done++; }
+  }
+  for (; done < iters; done++) { int rc = consume(first_id + done); if (rc) return rc; }
+  *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (d2h_bytes) *d2h_bytes = bytes;
+  if (checksum) *checksum = chk;
   return HEVCDL_OK;
 }
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_debug_copy", "hevcdl_get_stats",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_get_stats",
     "hevcdl_stream",
 ]
 
@@ -35,6 +35,11 @@ class Cfg(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("ctus", C.c_uint64), ("pus", C.c_uint64), ("ms_cnn", C.c_double),
                 ("ms_rmd", C.c_double), ("kernel_launches", C.c_uint64)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("labels", C.c_void_p), ("logits", C.c_void_p), ("ctu_off", C.c_void_p), ("pus", C.c_void_p),
+                ("satd", C.c_void_p), ("cand", C.c_void_p), ("nctu", C.c_int32), ("npu", C.c_int32)]
 
 
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("part", "u1"), ("ctu", "<u2")])
@@ -71,9 +76,12 @@ def load_library():
     L.hevcdl_frame_pu_count.argtypes = [vp, ip, C.POINTER(ip)]
     L.hevcdl_frame_pus.argtypes = [vp, ip, vp, vp, vp]
     L.hevcdl_ctu_pu_range.argtypes = [vp, ip, ip, C.POINTER(ip), C.POINTER(ip)]
+    L.hevcdl_frame_view_get.argtypes = [vp, ip, ip, C.POINTER(FrameView)]
     L.hevcdl_release_frame.argtypes = [vp, ip]
     L.hevcdl_rmd_exact.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp]
     L.hevcdl_bench_resident.argtypes = [vp, vp, ip, ip, C.POINTER(C.c_float), C.POINTER(ip)]
+    L.hevcdl_bench_e2e.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_uint64)]
     L.hevcdl_debug_copy.argtypes = [vp, ip, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hevcdl_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hevcdl_stream.argtypes = [vp]
@@ -153,6 +161,23 @@ class DepthPredictor:
         self._ck(self.lib.hevcdl_frame_pus(self.h, frame, _ptr(pus), _ptr(satd), _ptr(cand)), "frame_pus")
         return pus, satd, cand
 
+    def view(self, frame, want_pus=True):
+        """Zero-copy results of one frame: numpy arrays over the context's pinned host buffers, valid until
+        release(frame).  Returns dict(labels [nctu,16], logits [nctu,4,16], ctu_off, pus, satd [npu,35], cand [npu,8])."""
+        v = FrameView()
+        self._ck(self.lib.hevcdl_frame_view_get(self.h, frame, int(want_pus and self.rmd), C.byref(v)), "frame_view_get")
+
+        def arr(ptr, ctype, n, shape, dtype=None):
+            if not ptr or n == 0:
+                return np.empty(shape, dtype or np.dtype(ctype))
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+            return (a.view(dtype) if dtype is not None else a).reshape(shape)
+        n, m = v.nctu, v.npu
+        return {"labels": arr(v.labels, C.c_uint8, n * 16, (n, 16)), "logits": arr(v.logits, C.c_float, n * 64, (n, 4, 16)),
+                "ctu_off": arr(v.ctu_off, C.c_int32, n + 1 if v.ctu_off else 0, (n + 1 if v.ctu_off else 0,)),
+                "pus": arr(v.pus, C.c_uint8, m * 8, (m,), PU_DTYPE), "satd": arr(v.satd, C.c_uint32, m * 35, (m, 35)),
+                "cand": arr(v.cand, C.c_uint8, m * 8, (m, 8))}
+
     def ctu_pu_range(self, frame, addr):
         a, b = C.c_int(), C.c_int()
         self._ck(self.lib.hevcdl_ctu_pu_range(self.h, frame, addr, C.byref(a), C.byref(b)), "ctu_pu_range")
@@ -204,6 +229,17 @@ class DepthPredictor:
         nl = C.c_int()
         self._ck(self.lib.hevcdl_bench_resident(self.h, _ptr(fr), len(fr), iters, ms, C.byref(nl)), "bench_resident")
         return list(ms), nl.value
+
+    def bench_e2e(self, first_id, iters, depth, frames):
+        """frames: list of (Y, U, V) uint8 host planes (same strides).  Returns (seconds, d2h_bytes, checksum)."""
+        n = len(frames)
+        ys = (C.c_void_p * n)(*[f[0].ctypes.data for f in frames])
+        us = (C.c_void_p * n)(*[f[1].ctypes.data for f in frames])
+        vs = (C.c_void_p * n)(*[f[2].ctypes.data for f in frames])
+        sec, nb, chk = C.c_double(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.hevcdl_bench_e2e(self.h, first_id, iters, depth, n, ys, us, vs, frames[0][0].strides[0],
+                                           frames[0][1].strides[0], C.byref(sec), C.byref(nb), C.byref(chk)), "bench_e2e")
+        return sec.value, nb.value, chk.value
 
     def debug_copy(self, which):
         """Tensor-core path intermediates of the last frame (0 cat, 1 a2, 2 features) as raw bf16 bits."""

@@ -102,6 +102,22 @@ int hevcdl_frame_pu_count(hevcdl_ctx *ctx, int frame, int *npu);
 int hevcdl_frame_pus(hevcdl_ctx *ctx, int frame, hevcdl_pu *pus, uint32_t *satd, uint8_t *cand);
 int hevcdl_ctu_pu_range(hevcdl_ctx *ctx, int frame, int ctu_rs_addr, int *first, int *count);
 
+/* Zero-copy access to everything the device produced for one frame: pointers into the context's pinned host
+ * buffers (the same bytes the copying getters above return), valid until hevcdl_release_frame(frame).  Blocks
+ * until the frame is done; with want_pus != 0 also until the PU lists have arrived (rmd=1 contexts only,
+ * otherwise pus/satd/cand are NULL and npu = 0).  This is what the sidecar's consumer would read instead of
+ * parsing ./pred/<frame>/ctu<addr>.txt one file at a time (HM TEncCu.cpp:244-253). */
+typedef struct {
+  const uint8_t *labels;   /* [nctu*16] */
+  const float *logits;     /* [nctu*4*16] */
+  const int32_t *ctu_off;  /* [nctu+1] first PU of each CTU (NULL when rmd=0) */
+  const hevcdl_pu *pus;    /* [npu] */
+  const uint32_t *satd;    /* [npu*35] */
+  const uint8_t *cand;     /* [npu*8] */
+  int32_t nctu, npu;
+} hevcdl_frame_view;
+int hevcdl_frame_view_get(hevcdl_ctx *ctx, int frame, int want_pus, hevcdl_frame_view *out);
+
 int hevcdl_release_frame(hevcdl_ctx *ctx, int frame);
 
 /* Exact RMD for explicit inputs, the same device code as K6 fed what the reference feeds its
@@ -124,6 +140,15 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
  * launched per pass. */
 int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int iters, float ms[3],
                           int *launches);
+
+/* Measurement, end to end: `iters` frames through the public calls above -- hevcdl_submit_frame_u8 from the HOST
+ * planes y/u/v[i % nbuf] (pinned or pageable, caller-owned), hevcdl_frame_view_get(want_pus) on the oldest frame
+ * once `depth` frames are in flight, hevcdl_release_frame -- timed with the host's steady clock from the first
+ * submit to the last view.  Frame ids first_id .. first_id+iters-1.  seconds: wall time; d2h_bytes: bytes of the
+ * views read; checksum: a value folded from every view so the reads cannot be elided. */
+int hevcdl_bench_e2e(hevcdl_ctx *ctx, int first_id, int iters, int depth, int nbuf, const uint8_t *const *y,
+                     const uint8_t *const *u, const uint8_t *const *v, int stride_y, int stride_c, double *seconds,
+                     uint64_t *d2h_bytes, uint64_t *checksum);
 
 /* Test hook (tensor-core path only): copy one L2-resident intermediate of the most recent frame to
  * the host -- which = 0: conv1/conv64 output planes ("cat"), 1: conv2 output planes, 2: conv3

@@ -179,6 +179,24 @@ def test_boundary_fix_makes_partial_ctus_tile(built, host, pkg):
     ref.close(); fix.close()
 
 
+def test_frame_view_is_the_same_bytes_as_the_copying_getters(built, host, pkg):
+    Y, U, V = pkg.synth.synth_frame(416, 240, 6)
+    dp = _mk(host, 416, 240, 1, rmd=True, slots=2)
+    dp.submit(3, Y, U, V)
+    v = dp.view(3)
+    lab, lg = dp.labels(3, want_logits=True)
+    pus, satd, cand = dp.pus(3)
+    assert (v["labels"] == lab).all() and (v["logits"] == lg).all()
+    assert len(v["pus"]) == len(pus) > 0 and (v["pus"] == pus).all() and (v["satd"] == satd).all() and (v["cand"] == cand).all()
+    assert v["ctu_off"][-1] == len(pus) and (np.diff(v["ctu_off"]) >= 0).all()
+    dp.release(3)
+    dp2 = _mk(host, 416, 240, 0, rmd=False)
+    dp2.submit(0, Y, U, V)
+    v2 = dp2.view(0)
+    assert v2["labels"].shape == (28, 16) and len(v2["pus"]) == 0
+    dp2.release(0); dp.close(); dp2.close()
+
+
 def test_slots_busy_and_release(built, host, pkg):
     Y, U, V = pkg.synth.synth_frame(128, 64, 0)
     dp = _mk(host, 128, 64, 0, rmd=False, slots=2)
