@@ -21,8 +21,9 @@
 //   HEVCDL_DEVICE     CUDA ordinal (default 0)
 //   HEVCDL_PRECISION  fp32 (default: tightest parity with the torch sidecar) | bf16 (tcgen05 tensor cores)
 //   HEVCDL_BOUNDARY_FIX 1 = raise labels of picture-edge CTUs so partial CTUs tile (default 0 = reference)
-//   HEVCDL_RMD        1 = also run the batched 35-mode SATD pass (results are fetched by hevcdl_frame_pus; the
-//                     stock estIntraPredLumaQT does not consume them) (default 0)
+//   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
+//                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
+//                     decisions follow the +-1 % BD-rate clause, not the bit-exact one) (default 0: HM's own pass)
 // There is no fallback: any library failure aborts the encoder with the library's error text.
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,7 @@
 #include "TLibEncoder/TEncTop.h"
 
 #include "hevcdl.h"
+#include "rmd_hook.h"
 
 namespace {
 
@@ -39,6 +41,11 @@ struct HevcdlSession {
   hevcdl_ctx *ctx = nullptr;
   int width = 0, height = 0;
   int frame = -1;               // frame currently resident on the device (-1: none)
+  bool gpu_rmd = false;         // HEVCDL_RMD=1: first-pass SATDs come from the device
+  hevcdl_frame_view view;       // results of `frame` (pinned host memory owned by the library)
+  bool have_view = false;
+  int ctu_first = 0, ctu_count = 0, cursor = 0;   // PU range of the CTU being compressed + last hit
+  unsigned long long hook_hits = 0, hook_misses = 0;
 
   static void die(const char *what, int rc, hevcdl_ctx *c) {
     fprintf(stderr, "hevcdl: %s failed: %s (%s)\n", what, hevcdl_status_str(rc), hevcdl_last_error(c));
@@ -55,6 +62,7 @@ struct HevcdlSession {
     cfg.slots = 2;
     cfg.precision = ((e = getenv("HEVCDL_PRECISION")) && !strcmp(e, "bf16")) ? HEVCDL_PREC_BF16_TC : HEVCDL_PREC_FP32;
     cfg.rmd = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
+    gpu_rmd = cfg.rmd != 0;
     cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
     cfg.weights_path = (e = getenv("HEVCDL_WEIGHTS")) ? e : HEVCDL_DEFAULT_WEIGHTS;
     const int rc = hevcdl_create(&cfg, &ctx);
@@ -73,6 +81,36 @@ struct HevcdlSession {
                                              org->getAddr(COMPONENT_Cb), org->getAddr(COMPONENT_Cr), org->getStride(COMPONENT_Cb));
     if (rc) die("hevcdl_submit_frame_pel16", rc, ctx);
     frame = id;
+    have_view = false;
+  }
+
+  // PU range of one CTU in the frame's device results (fetched once per frame, zero-copy)
+  void begin_ctu(int addr) {
+    if (!gpu_rmd) return;
+    if (!have_view) {
+      const int rc = hevcdl_frame_view_get(ctx, frame, 1, &view);
+      if (rc) die("hevcdl_frame_view_get", rc, ctx);
+      have_view = true;
+    }
+    ctu_first = view.ctu_off[addr];
+    ctu_count = view.ctu_off[addr + 1] - ctu_first;
+    cursor = 0;
+  }
+
+  // SATD of (PU at picture position x,y of the given size, mode); PUs are queried in the order the device listed them
+  bool lookup(unsigned x, unsigned y, unsigned size, unsigned mode, unsigned *sad) {
+    for (int k = 0; k < ctu_count; k++) {
+      const int i = (cursor + k) % ctu_count;
+      const hevcdl_pu &p = view.pus[ctu_first + i];
+      if (p.x == x && p.y == y && p.size == size) {
+        cursor = i;
+        *sad += view.satd[(size_t)(ctu_first + i) * 35 + mode];
+        hook_hits++;
+        return true;
+      }
+    }
+    hook_misses++;
+    return false;                 // not on the device's list (cannot happen for consistent labels): HM computes it
   }
 
   ~HevcdlSession() {
@@ -80,9 +118,10 @@ struct HevcdlSession {
       if (getenv("HEVCDL_VERBOSE")) {
         hevcdl_stats_t st;
         if (!hevcdl_get_stats(ctx, &st))
-          fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches\n",
+          fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches, "
+                          "first-pass SATDs served %llu / missed %llu\n",
                   (unsigned long long)st.frames, (unsigned long long)st.ctus, st.ms_cnn, st.ms_rmd,
-                  (unsigned long long)st.kernel_launches);
+                  (unsigned long long)st.kernel_launches, hook_hits, hook_misses);
       }
       hevcdl_destroy(ctx);
     }
@@ -112,6 +151,7 @@ Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
   UInt label[16];                                   // same lifetime as the reference's stack array (TEncCu.cpp:247)
   for ( Int i = 0; i < 16; i++ ) label[i] = depth8[i];
   m_ppcBestCU[0]->set_pred( label );
+  g_session.begin_ctu( (int)ctuRsAddr );
 
   DEBUG_STRING_NEW(sDebug)
   xCompressCU( m_ppcBestCU[0], m_ppcTempCU[0], 0 DEBUG_STRING_PASS_INTO(sDebug) );
@@ -123,4 +163,11 @@ Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
     xCtuCollectARLStats( pCtu );
   }
 #endif
+}
+
+// First-pass SATD hook (rmd_hook.h): called from the reference's estIntraPredLumaQT mode loop.
+bool hevcdl_hm_rmd_satd( TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode, unsigned* sad )
+{
+  if ( !g_session.gpu_rmd || !g_session.have_view ) return false;
+  return g_session.lookup( pcCU->getCUPelX() + x0InCu, pcCU->getCUPelY() + y0InCu, width, mode, sad );
 }

@@ -70,3 +70,28 @@ def test_dropin_tensor_core_precision_runs(tmp_path, built, pkg):
     assert r["rc"] == 0 and "kernel launches" in r["stderr"], r["stderr"][-400:]
     ok, out = hm_util.decode_ok(str(tmp_path))
     assert ok, out[-400:]
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_dropin_first_pass_satd_served_by_the_device(tmp_path, built, host, pkg):
+    """HEVCDL_RMD=1: every (PU, mode) SATD the reference's first pass asks for is found in the device's list --
+    35 per PU the encoder visits, none missed -- and the stream still decodes (mode decisions then follow the
+    original-reference SATDs: BD-rate clause, tools/bdrate_sweep.py)."""
+    import re
+    w, h = 192, 128
+    frames = [pkg.synth.synth_frame(w, h, 20 + i) for i in range(2)]
+    hm_util.write_yuv(str(tmp_path / "in.yuv"), frames)
+    dp = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=True)
+    npu = 0
+    for f, (Y, U, V) in enumerate(frames):
+        dp.submit(f, Y, U, V)
+        npu += len(dp.view(f)["pus"])
+        dp.release(f)
+    dp.close()
+    r = hm_util.encode("hevcdl", str(tmp_path), "in.yuv", w, h, 2, 32, env={"HEVCDL_RMD": "1", "HEVCDL_VERBOSE": "1"})
+    assert r["rc"] == 0, r["stderr"][-400:]
+    m = re.search(r"first-pass SATDs served (\d+) / missed (\d+)", r["stderr"])
+    assert m and int(m.group(2)) == 0 and int(m.group(1)) == 35 * npu, (r["stderr"][-300:], npu)
+    ok, out = hm_util.decode_ok(str(tmp_path))
+    assert ok, out[-400:]

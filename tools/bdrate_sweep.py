@@ -6,7 +6,8 @@ SURVEY.md fact 6):
   anchor  oracle/_ref/TAppEncoder_anchor  stock HM-16.20 decision (pruning off)
   hm_dl   oracle/_ref/TAppEncoder_ref     the UNMODIFIED reference fed ./pred files holding fp32 labels
   dropin  hm_plugin/_build/TAppEncoder_hevcdl   reference sources + this repo's compressCtu, labels from the B200
-                                          (HEVCDL_PRECISION = fp32 and bf16)
+                                          (HEVCDL_PRECISION = fp32 and bf16; *_gpu_rmd: HEVCDL_RMD=1, the first-pass
+                                          SATDs of estIntraPredLumaQT also come from the B200, original-pixel references)
 Writes a JSON report (rates, PSNRs, encoder seconds, BD numbers) to the path given by --out.
 usage: python tools/bdrate_sweep.py [--width 1920 --height 1024 --frames 1 --out gpurun_out/bdrate.json]
 """
@@ -54,7 +55,9 @@ def main():
         for f, lab in enumerate(labels):
             hm_util.write_pred(os.path.join(td, "pred"), f, lab)
         kinds = [("anchor", "anchor", None), ("hm_dl", "ref", None), ("dropin_fp32", "hevcdl", {"HEVCDL_PRECISION": "fp32"}),
-                 ("dropin_bf16", "hevcdl", {"HEVCDL_PRECISION": "bf16"})]
+                 ("dropin_bf16", "hevcdl", {"HEVCDL_PRECISION": "bf16"}),
+                 ("dropin_gpu_rmd", "hevcdl", {"HEVCDL_PRECISION": "fp32", "HEVCDL_RMD": "1"}),
+                 ("dropin_bf16_gpu_rmd", "hevcdl", {"HEVCDL_PRECISION": "bf16", "HEVCDL_RMD": "1"})]
         for name, kind, env in kinds:
             rows = []
             for qp in qps:
@@ -76,7 +79,10 @@ def main():
                 "time_ratio": float(np.mean([x["seconds"] for x in rep["runs"][anchor]]) / max(1e-9, np.mean([x["seconds"] for x in rep["runs"][test]])))}
     rep["bd"] = {"hm_dl_vs_anchor": cmp("hm_dl", "anchor"), "dropin_fp32_vs_anchor": cmp("dropin_fp32", "anchor"),
                  "dropin_bf16_vs_anchor": cmp("dropin_bf16", "anchor"), "dropin_bf16_vs_hm_dl": cmp("dropin_bf16", "hm_dl"),
-                 "dropin_fp32_vs_hm_dl": cmp("dropin_fp32", "hm_dl")}
+                 "dropin_fp32_vs_hm_dl": cmp("dropin_fp32", "hm_dl"),
+                 "dropin_gpu_rmd_vs_hm_dl": cmp("dropin_gpu_rmd", "hm_dl"), "dropin_gpu_rmd_vs_anchor": cmp("dropin_gpu_rmd", "anchor"),
+                 "dropin_bf16_gpu_rmd_vs_hm_dl": cmp("dropin_bf16_gpu_rmd", "hm_dl"),
+                 "dropin_bf16_gpu_rmd_vs_anchor": cmp("dropin_bf16_gpu_rmd", "anchor")}
     rep["dropin_fp32_bitstreams_identical_to_hm_dl"] = all(x["sha1"] == y["sha1"] for x, y in zip(rep["runs"]["dropin_fp32"], rep["runs"]["hm_dl"]))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(rep, open(a.out, "w"), indent=1)
