@@ -143,7 +143,7 @@ def run_b200(args, rank, world, local_rank):
     prec = host.PREC_BF16_TC if args.precision == "bf16" else host.PREC_FP32
     pool_n = args.pool
     pool = make_pool(pkg.synth, w, h, pool_n, rank)
-    dp = host.DepthPredictor(w, h, device=local_rank, slots=pool_n, precision=prec, rmd=True)
+    dp = host.DepthPredictor(w, h, device=local_rank, slots=pool_n, precision=prec, rmd=True, batch=args.batch)
     nctu = dp.nctu
     frame_bytes = w * h * 3 // 2
 
@@ -188,7 +188,7 @@ def run_b200(args, rank, world, local_rank):
         a[:w * h] = Y.ravel(); a[w * h:w * h * 5 // 4] = U.ravel(); a[w * h * 5 // 4:] = V.ravel()
         pinned.append((buf, a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2),
                        a[w * h * 5 // 4:].reshape(h // 2, w // 2)))
-    depth = min(3, pool_n)
+    depth = min(2 + args.batch, pool_n)
     d2h_bytes = [0]
 
     chk = [0]
@@ -247,7 +247,7 @@ def run_b200(args, rank, world, local_rank):
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec else "f32", "data": "synthetic",
         "config": {"workload": "1 frame %dx%d all-intra QP32 per step (%d CTUs), CNN labels + 35-mode SATD (RMD) on 1 B200 per rank" % (w, h, nctu),
-                   "precision": args.precision, "frames_sharded": "frame f -> rank f mod N, no data-path collective",
+                   "precision": args.precision, "frames_per_cnn_launch": args.batch, "frames_sharded": "frame f -> rank f mod N, no data-path collective",
                    "l2": "inputs rotate over %d resident frames per rank (%.0f MB planes + outputs > 126 MB L2)" % (pool_n, pool_n * frame_bytes / 1e6),
                    "pus_per_frame": npu_total / pool_n},
         "clocks": clocks,
@@ -300,6 +300,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--pool", type=int, default=48)
+    ap.add_argument("--batch", type=int, default=2, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
     ap.add_argument("--ref-ctus", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -48,6 +48,7 @@ struct TcParams {
 
 constexpr int TC_THREADS = 288;    // warps 0-7: staging + epilogue, warp 8: loads + MMA issue
 #define EPI_BAR_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+#define EPI2_BAR_SYNC() asm volatile("bar.sync 1, 512;" ::: "memory")   // kernels with 16 epilogue warps
 
 // Sum of v[e] over the 32 lanes, for all e in [0,32): lane l returns the total of element l.
 __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
@@ -77,6 +78,30 @@ __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) 
     }
   }
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// Sum of v[e] over the 32 lanes for e in [0,8): every lane l returns the total of element l & 7.
+__device__ __forceinline__ float warp_transpose_sum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int off = 4, n = 8; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int j = 0; j < n / 2; j++) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  float r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 8);
+  return r + __shfl_xor_sync(0xffffffffu, r, 16);
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
@@ -111,9 +136,11 @@ constexpr int P1_PITCH = 36, P1_BYTES = 36 * 36 * 4;
 constexpr int K1_W = 0, K1_P64 = K1_W + SZ_L1W, K1_P1 = K1_P64 + 2 * P64_BYTES, K1_RED = K1_P1 + 8 * P1_BYTES,
               K1_BAR = K1_RED + 2 * 8 * 16 * 4, K1_SMEM = K1_BAR + 64;
 
+// 8 epilogue warps (warp = TMEM lane quarter + 4 * channel half) + 1 TMA/MMA warp.  A 16-epilogue-warp variant (4
+// channels per thread) was measured slower (40.9 vs 37 us per 1080p frame): twice the TMEM load instructions and
+// duplicated reduction work outweigh the extra latency hiding.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint8_t *__restrict__ V, FrameGeom geo, int pitch,
-        int cpitch, const uint8_t *__restrict__ blob, uint8_t *__restrict__ cat) {
+k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t *__restrict__ blob, uint8_t *__restrict__ cat) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
@@ -146,7 +173,10 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
 
   // raw samples of the next CTU, fetched one CTU ahead so the HBM/L2 latency hides behind the epilogue
   uint32_t pf_y[4] = {0, 0, 0, 0}, pf_u[4] = {0, 0, 0, 0}, pf_v[4] = {0, 0, 0, 0};
-  auto prefetch_ctu = [&](int c) {
+  const int total = geo.nctu * fb.n;            // CTUs of all frames of this launch
+  auto prefetch_ctu = [&](int cg) {
+    const int f = cg / geo.nctu, c = cg - f * geo.nctu;
+    const uint8_t *__restrict__ Y = fb.Y[f], *__restrict__ U = fb.U[f], *__restrict__ V = fb.V[f];
     const int cx = c % geo.ctu_w, cy = c / geo.ctu_w;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -161,10 +191,12 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
     }
   };
   pdl_wait();                                   // prologue done; from here on global memory of the frame is touched
-  if (warp < 8 && (int)blockIdx.x < geo.nctu) prefetch_ctu(blockIdx.x);
+  const long long trace_t0 = clock64(); (void)trace_t0;
+  if (warp < 8 && (int)blockIdx.x < total) prefetch_ctu(blockIdx.x);
 
-  for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x) {
-    const int ctu_x = ctu % geo.ctu_w, ctu_y = ctu / geo.ctu_w;
+  for (int ctu = blockIdx.x; ctu < total; ctu += gridDim.x) {
+    const int ctu_l = ctu % geo.nctu;           // CTU address inside its frame
+    const int ctu_x = ctu_l % geo.ctu_w, ctu_y = ctu_l / geo.ctu_w;
     // ---- staging: (R,G) and (B,0) planes of the CTU and of its four zero-padded quadrants ----
     if (warp < 8) {
 #pragma unroll
@@ -197,17 +229,17 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
       fence_async_smem();
     }
     __syncthreads();
-    if (warp < 8 && ctu + (int)gridDim.x < geo.nctu) prefetch_ctu(ctu + gridDim.x);
+    if (warp < 8 && ctu + (int)gridDim.x < total) prefetch_ctu(ctu + gridDim.x);
 
     if (warp == 8) {
       // ---- MMA issue: 4 tile pairs (conv64 quarters 0-1, 2-3; conv1 quadrants 0-1, 2-3) ----------
       if (elect_one()) {
-        mbar_wait(bar_w, 0);
+        MBAR_WAIT(bar_w, 0, 0);
         const uint32_t sb = smem_u32(sm);
 #pragma unroll 1
         for (int pi = 0; pi < 4; pi++) {
           const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
-          mbar_wait(&bar_empty[p], (use & 1) ^ 1);
+          MBAR_WAIT(&bar_empty[p], (use & 1) ^ 1, 1);
           fence_after_sync();
           const bool c1 = pi >= 2;
           uint32_t a0, a1, plane_stride, row_stride;
@@ -247,7 +279,7 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
 #pragma unroll 1
       for (int pi = 0; pi < 4; pi++) {
         const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
-        mbar_wait(&bar_full[p], use & 1);
+        MBAR_WAIT(&bar_full[p], use & 1, 2);
         fence_after_sync();
 #pragma unroll
         for (int e = 0; e < 2; e++) {
@@ -261,6 +293,9 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[p]);
           }
+#ifdef HEVCDL_ABLATE_EPI
+          if (v[0][0] != 12345.f) continue;
+#endif
 #pragma unroll
           for (int c = 0; c < 8; c++)
 #pragma unroll
@@ -332,6 +367,7 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
   }
   fence_before_sync();
   __syncthreads();
+  TRACE_TOTAL(16, trace_t0);
   if (warp == 8) tmem_dealloc(tbase, 512);
 }
 
@@ -341,9 +377,14 @@ k_tc_l1(const uint8_t *__restrict__ Y, const uint8_t *__restrict__ U, const uint
 constexpr int K2_W = 0, K2_CAT = K2_W + SZ_W2, K2_RED = K2_CAT + 2 * CAT_BYTES, K2_BAR = K2_RED + 2 * 8 * 64 * 4,
               K2_SMEM = K2_BAR + 128;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// 16 epilogue warps (warp = TMEM lane quarter + 4 * 16-channel group) + 1 TMA/MMA warp: the epilogue is
+// CUDA-core work over 64 K accumulator values per CTU and was issue-bound with 8 warps (2 per scheduler).
+constexpr int K2_THREADS = 17 * 32, K2_MMA_WARP = 16;
+
+__global__ void __launch_bounds__(K2_THREADS, 1)
 k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ cat, uint8_t *__restrict__ a2) {
   using namespace tc;
+  const long long trace_t0 = clock64(); (void)trace_t0;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K2_BAR);   // [4] per sample
@@ -351,25 +392,25 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   uint64_t *bar_cfull = bar_full + 8;                               // [2] cat buffer landed
   uint64_t *bar_cfree = bar_full + 10;                              // [2] cat buffer no longer read
   uint64_t *bar_w = bar_full + 12;
-  float *red = reinterpret_cast<float *>(sm + K2_RED);              // [2][8 warps][64]
+  float *red = reinterpret_cast<float *>(sm + K2_RED);              // [2][16 warps][16 sums + 16 sums of squares]
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
 
   if (tid == 0) {
-    for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 8); }
+    for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 16); }
     for (int i = 0; i < 2; i++) { mbar_init(&bar_cfull[i], 1); mbar_init(&bar_cfree[i], 1); }
     mbar_init(bar_w, 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  if (warp == K2_MMA_WARP) tmem_alloc(&tmem_slot, 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = tmem_slot;
   const uint32_t idesc = idesc_bf16(128, 64);
 
-  if (warp == 8) {
+  if (warp == K2_MMA_WARP) {
     if (elect_one()) {
       mbar_expect_tx(bar_w, SZ_W2);
       for (int i = 0; i < 9; i++) bulk_g2s(sm + K2_W + i * 4096, blob + OFF_W2 + i * 4096, 4096, bar_w);
@@ -385,107 +426,120 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
         const uint32_t b = it & 1;
         const int next = ctu + gridDim.x;
         if (next < geo.nctu) {   // prefetch the next CTU's planes into the other buffer
-          if (it >= 1) mbar_wait(&bar_cfree[b ^ 1], ((it - 1) >> 1) & 1);
+          if (it >= 1) MBAR_WAIT(&bar_cfree[b ^ 1], ((it - 1) >> 1) & 1, 4);
           mbar_expect_tx(&bar_cfull[b ^ 1], CAT_BYTES);
           bulk_g2s(sm + K2_CAT + (b ^ 1) * CAT_BYTES, cat + (size_t)next * CAT_BYTES, CAT_BYTES, &bar_cfull[b ^ 1]);
         }
-        mbar_wait(&bar_cfull[b], (it >> 1) & 1);
+        MBAR_WAIT(&bar_cfull[b], (it >> 1) & 1, 5);
         const uint32_t cbuf = sb + K2_CAT + b * CAT_BYTES;
         const uint64_t db = smem_desc(sb + K2_W, 128, 256);
         const uint64_t d64 = smem_desc(cbuf + 8 * CAT_PLANE, CAT_PLANE, 288);   // shared conv64 planes
+        // Two samples at a time = four independent accumulators in flight: an MMA that accumulates into the same TMEM
+        // tile as its predecessor costs ~138 cycles whatever its size (tools/tc_probe.cu), so a lone chain of 64-column
+        // MMAs runs the tensor pipe at a third of its rate.  The other two samples' tiles belong to the epilogue meanwhile.
 #pragma unroll 1
-        for (int smp = 0; smp < 4; smp++) {
-          mbar_wait(&bar_empty[smp], (it & 1) ^ 1);
+        for (int sp = 0; sp < 4; sp += 2) {
+          MBAR_WAIT(&bar_empty[sp], (it & 1) ^ 1, 6);
+          MBAR_WAIT(&bar_empty[sp + 1], (it & 1) ^ 1, 6);
           fence_after_sync();
-          const uint64_t d1 = smem_desc(cbuf + smp * 2 * CAT_PLANE, CAT_PLANE, 288);
-          const uint32_t t0 = tbase + (2 * smp) * 64, t1 = t0 + 64;
+          const uint64_t d1a = smem_desc(cbuf + sp * 2 * CAT_PLANE, CAT_PLANE, 288);
+          const uint64_t d1b = smem_desc(cbuf + (sp + 1) * 2 * CAT_PLANE, CAT_PLANE, 288);
+          const uint32_t t0 = tbase + (2 * sp) * 64;     // tiles: sample sp left/right, sample sp+1 left/right
 #pragma unroll
           for (int tap = 0; tap < 9; tap++) {
             const uint64_t aofs = (uint64_t)((tap / 3) * 18 + (tap % 3));   // 16-byte units
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-              const uint64_t da = (j ? d64 : d1) + aofs;
+              const uint64_t daa = (j ? d64 : d1a) + aofs, dab = (j ? d64 : d1b) + aofs;
               const uint64_t bofs = (uint64_t)(((tap * 2 + j) * 2048) >> 4);
               const uint32_t acc = (tap | j) ? 1u : 0u;
-              mma_bf16_ss(t0, da, db + bofs, idesc, acc);
-              mma_bf16_ss(t1, da + 8, db + bofs, idesc, acc);     // right half: +8 pixels
+              mma_bf16_ss(t0, daa, db + bofs, idesc, acc);
+              mma_bf16_ss(t0 + 64, daa + 8, db + bofs, idesc, acc);     // right half: +8 pixels
+              mma_bf16_ss(t0 + 128, dab, db + bofs, idesc, acc);
+              mma_bf16_ss(t0 + 192, dab + 8, db + bofs, idesc, acc);
             }
           }
-          mma_commit(&bar_full[smp]);
+          mma_commit(&bar_full[sp]);
+          mma_commit(&bar_full[sp + 1]);
         }
         mma_commit(&bar_cfree[b]);
       }
     }
     __syncwarp();
   } else {
-    const int lq = warp & 3, h = warp >> 2;
+    const int lq = warp & 3, cq = warp >> 2;      // TMEM lane quarter, group of 16 output channels
     const int m = lq * 32 + lane, yy = m >> 3, xi = m & 7;
-    const float g2r = __ldg(fp + F_G2 + 32 * h + lane), b2r = __ldg(fp + F_B2 + 32 * h + lane);
+    const float g2r = __ldg(fp + F_G2 + 16 * cq + (lane & 15)), b2r = __ldg(fp + F_B2 + 16 * cq + (lane & 15));
     uint32_t it = 0, rb = 0;
     for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
 #pragma unroll 1
       for (int smp = 0; smp < 4; smp++) {
-        mbar_wait(&bar_full[smp], it & 1);
+        MBAR_WAIT(&bar_full[smp], it & 1, 7);
         fence_after_sync();
-        float v0[32], v1[32];
-        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * smp) * 64 + 32 * h), v0);
-        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * smp + 1) * 64 + 32 * h), v1);
+        float v0[16], v1[16];
+        tmem_ld16(tmem_addr(tbase, lq * 32, (2 * smp) * 64 + 16 * cq), v0);
+        tmem_ld16(tmem_addr(tbase, lq * 32, (2 * smp + 1) * 64 + 16 * cq), v1);
         tmem_ld_wait();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[smp]);
-        float s[32], q[32];
+#ifdef HEVCDL_ABLATE_EPI
+        if (__all_sync(0xffffffffu, v0[0] != 12345.f)) continue;
+#endif
+        float s[16], q[16];
 #pragma unroll
-        for (int c = 0; c < 32; c++) { s[c] = v0[c] + v1[c]; q[c] = fmaf(v0[c], v0[c], v1[c] * v1[c]); }
-        const float ts = warp_transpose_sum32(s, lane), tq = warp_transpose_sum32(q, lane);
-        red[(rb * 8 + warp) * 64 + lane] = ts;
-        red[(rb * 8 + warp) * 64 + 32 + lane] = tq;
+        for (int c = 0; c < 16; c++) { s[c] = v0[c] + v1[c]; q[c] = fmaf(v0[c], v0[c], v1[c] * v1[c]); }
+        const float ts = warp_transpose_sum16(s, lane), tq = warp_transpose_sum16(q, lane);   // lane l & 15: channel 16cq + (l & 15)
+        if (lane < 16) { red[(rb * 16 + warp) * 32 + lane] = ts; red[(rb * 16 + warp) * 32 + 16 + lane] = tq; }
         // 2x2 max-pool: exchange halves with the x neighbour (lane^1) then the y neighbour (lane^8);
-        // this thread ends with 8 channels of one window for each of the two tiles
+        // this thread ends with 4 channels of one window for each of the two tiles
         const bool b0 = lane & 1, b3 = lane & 8;
-        float p0[16], p1[16];
+        float p0[8], p1[8];
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-          const float keep0 = b0 ? v0[16 + c] : v0[c], send0 = b0 ? v0[c] : v0[16 + c];
-          const float keep1 = b0 ? v1[16 + c] : v1[c], send1 = b0 ? v1[c] : v1[16 + c];
+        for (int c = 0; c < 8; c++) {
+          const float keep0 = b0 ? v0[8 + c] : v0[c], send0 = b0 ? v0[c] : v0[8 + c];
+          const float keep1 = b0 ? v1[8 + c] : v1[c], send1 = b0 ? v1[c] : v1[8 + c];
           p0[c] = fmaxf(keep0, __shfl_xor_sync(0xffffffffu, send0, 1));
           p1[c] = fmaxf(keep1, __shfl_xor_sync(0xffffffffu, send1, 1));
         }
-        float w0[8], w1[8];
+        float w0[4], w1[4];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          const float keep0 = b3 ? p0[8 + c] : p0[c], send0 = b3 ? p0[c] : p0[8 + c];
-          const float keep1 = b3 ? p1[8 + c] : p1[c], send1 = b3 ? p1[c] : p1[8 + c];
+        for (int c = 0; c < 4; c++) {
+          const float keep0 = b3 ? p0[4 + c] : p0[c], send0 = b3 ? p0[c] : p0[4 + c];
+          const float keep1 = b3 ? p1[4 + c] : p1[c], send1 = b3 ? p1[c] : p1[4 + c];
           w0[c] = fmaxf(keep0, __shfl_xor_sync(0xffffffffu, send0, 8));
           w1[c] = fmaxf(keep1, __shfl_xor_sync(0xffffffffu, send1, 8));
         }
-        EPI_BAR_SYNC();
-        const int chunk = 4 * h + 2 * (b0 ? 1 : 0) + (b3 ? 1 : 0);   // 8 channels [8*chunk, 8*chunk+8)
-        // lane l finishes channel 32h + l (totals of the 4 warps of this half), then hands scale/shift to the lanes that need it
+        EPI2_BAR_SYNC();
+        // lane l finishes channel 16cq + (l & 15) (totals of the 4 warps of this channel group), then hands scale/shift
+        // to the lanes that need it
         float a = 0.f, bq = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { a += red[(rb * 8 + h * 4 + k) * 64 + lane]; bq += red[(rb * 8 + h * 4 + k) * 64 + 32 + lane]; }
+        for (int k = 0; k < 4; k++) { a += red[(rb * 16 + cq * 4 + k) * 32 + (lane & 15)]; bq += red[(rb * 16 + cq * 4 + k) * 32 + 16 + (lane & 15)]; }
         float sc1, sh1;
         bn_scale_shift(a, bq, 1.f / 256.f, 1e-5f, g2r, b2r, sc1, sh1);
-        float y0[8], y1[8];
+        const int sub = 8 * (b0 ? 1 : 0) + 4 * (b3 ? 1 : 0);   // this thread's 4 channels inside the group of 16
+        float y0[4], y1[4];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          const int srcl = (chunk & 3) * 8 + c;   // channel index inside this half's 32
-          const float sc = __shfl_sync(0xffffffffu, sc1, srcl), sh = __shfl_sync(0xffffffffu, sh1, srcl);
+        for (int c = 0; c < 4; c++) {
+          const float sc = __shfl_sync(0xffffffffu, sc1, sub + c), sh = __shfl_sync(0xffffffffu, sh1, sub + c);
           y0[c] = fmaxf(fmaf(w0[c], sc, sh), 0.f);
           y1[c] = fmaxf(fmaf(w1[c], sc, sh), 0.f);
         }
         rb ^= 1;
-        // window (py, px): py = y/2, px = xi/2 (+4 for the right-half tile); plane row 4*(py+1)+smp, col px+1
-        uint8_t *d = a2 + (size_t)ctu * A2_BYTES + chunk * A2_PLANE + ((4 * ((yy >> 1) + 1) + smp) * 10 + (xi >> 1) + 1) * 16;
-        *reinterpret_cast<uint4 *>(d) = pack8_bf16(y0);
-        *reinterpret_cast<uint4 *>(d + 4 * 16) = pack8_bf16(y1);
+        // window (py, px): py = y/2, px = xi/2 (+4 for the right-half tile); plane row 4*(py+1)+smp, col px+1; the plane
+        // holds channels [8*chunk, 8*chunk+8) per 16-byte pixel unit, this thread owns half of it
+        const int chunk = 2 * cq + (b0 ? 1 : 0);
+        uint8_t *d = a2 + (size_t)ctu * A2_BYTES + chunk * A2_PLANE + ((4 * ((yy >> 1) + 1) + smp) * 10 + (xi >> 1) + 1) * 16 + (b3 ? 8 : 0);
+        *reinterpret_cast<uint2 *>(d) = make_uint2(tc::pack_bf16(y0[0], y0[1]), tc::pack_bf16(y0[2], y0[3]));
+        *reinterpret_cast<uint2 *>(d + 4 * 16) = make_uint2(tc::pack_bf16(y1[0], y1[1]), tc::pack_bf16(y1[2], y1[3]));
       }
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tbase, 512);
+  TRACE_TOTAL(17, trace_t0);
+  if (warp == K2_MMA_WARP) tmem_dealloc(tbase, 512);
 }
 
 // ================================================================================================
@@ -497,6 +551,7 @@ constexpr int K3_W = 0, K3_A2 = K3_W + SZ_W3, K3_RED = K3_A2 + A2_BYTES, K3_BAR 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ a2, uint8_t *__restrict__ feats, int npad) {
   using namespace tc;
+  const long long trace_t0 = clock64(); (void)trace_t0;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K3_BAR);   // [2] accumulator ready
@@ -538,12 +593,12 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
       uint32_t it = 0;
       for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
         const uint32_t t = it & 1;
-        mbar_wait(&bar_empty[t], ((it >> 1) & 1) ^ 1);
+        MBAR_WAIT(&bar_empty[t], ((it >> 1) & 1) ^ 1, 9);
         fence_after_sync();
         const uint32_t dacc = tbase + t * 256;
 #pragma unroll 1
         for (int j = 0; j < 4; j++) {
-          mbar_wait(&bar_afull[j], it & 1);
+          MBAR_WAIT(&bar_afull[j], it & 1, 10);
           const uint64_t dact = smem_desc(sb + K3_A2 + j * 2 * A2_PLANE, A2_PLANE, 160);
 #pragma unroll
           for (int tap = 0; tap < 9; tap++) {
@@ -556,7 +611,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
         const int next = ctu + gridDim.x;
         if (next < geo.nctu)
           for (int j = 0; j < 4; j++) {   // refill each plane pair as soon as its MMAs have drained
-            mbar_wait(&bar_afree[j], it & 1);
+            MBAR_WAIT(&bar_afree[j], it & 1, 11);
             mbar_expect_tx(&bar_afull[j], 2 * A2_PLANE);
             bulk_g2s(sm + K3_A2 + j * 2 * A2_PLANE, a2 + (size_t)next * A2_BYTES + j * 2 * A2_PLANE, 2 * A2_PLANE, &bar_afull[j]);
           }
@@ -570,7 +625,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
     const float gam = __ldg(fp + F_G3 + c), bet = __ldg(fp + F_B3 + c);
     for (int ctu = blockIdx.x; ctu < geo.nctu; ctu += gridDim.x, it++) {
       const uint32_t t = it & 1;
-      mbar_wait(&bar_full[t], (it >> 1) & 1);
+      MBAR_WAIT(&bar_full[t], (it >> 1) & 1, 12);
       fence_after_sync();
       float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
       float pooled[2][4][4];   // [py local][sample][px]
@@ -594,6 +649,9 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[t]);
+#ifdef HEVCDL_ABLATE_EPI
+      if (__all_sync(0xffffffffu, s[0] != 12345.f)) continue;
+#endif
       float *rr = red + ((rb * 2 + hy) * 8) * 128;
 #pragma unroll
       for (int smp = 0; smp < 4; smp++) { rr[smp * 128 + c] = s[smp]; rr[(4 + smp) * 128 + c] = q[smp]; }
@@ -618,6 +676,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   }
   fence_before_sync();
   __syncthreads();
+  TRACE_TOTAL(18, trace_t0);
   if (warp == 8) tmem_dealloc(tbase, 512);
 }
 
@@ -633,20 +692,21 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 #define HEVCDL_FC_NSTAGE 4
 #endif
 constexpr int FC_NT = HEVCDL_FC_NT;
+constexpr int FC_KPH = FC_NT <= 32 ? 4 : (FC_NT <= 64 ? 2 : 1);   // K-phases = independent accumulators per output tile
 constexpr int K4_STAGE = 32768 + FC_NT * 128, K4_NSTAGE = HEVCDL_FC_NSTAGE;     // fc1 weights [256 x 64] + features [FC_NT x 64], bf16
 constexpr int K4_BAR = K4_NSTAGE * K4_STAGE;
 constexpr int K4_FC2W = (K4_BAR + 128 + 1023) / 1024 * 1024;     // fc2 weights, loaded in the prologue
 constexpr int K4_F3W = K4_FC2W + SZ_FC2;                           // fc3 weights transposed, fp32 [64][16]
 constexpr int K4_SMEM = K4_F3W + 4096;
 static_assert(K4_SMEM <= 227 * 1024, "K4 shared memory");
+static_assert(3 * FC_KPH * FC_NT <= 512, "K4 tensor memory: 2*KPH fc1 + KPH fc2 accumulators");
 // after the fc1 K loop the stage memory is reused:
 constexpr int K4_H1 = 0 /* bf16 fc2 operand [FC_NT/8][32][8][8] */, K4_H2 = K4_H1 + FC_NT * 512 /* fp32 [FC_NT][65] */,
               K4_LG = K4_H2 + (FC_NT * 65 * 4 + 15) / 16 * 16 /* fp32 [FC_NT][16] */;
 static_assert(K4_LG + FC_NT * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in the stage memory");
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix,
-        uint8_t *__restrict__ labels, float *__restrict__ logits_out, uint32_t *__restrict__ ctu_cnt) {
+k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
@@ -673,7 +733,7 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     mbar_init(bar_done, 1); mbar_init(bar_w2, 1); mbar_init(bar_done2, 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 128);   // fc1: 2 x FC_NT columns, fc2: FC_NT columns
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);   // fc1: 8 x FC_NT columns, fc2: 4 x FC_NT columns
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -706,9 +766,11 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
         const uint64_t da = smem_desc(sb + st * K4_STAGE, 128, 1024), db = smem_desc(sb + st * K4_STAGE + 32768, 128, 1024);
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-          const uint32_t acc = (kc | t) ? 1u : 0u;
-          mma_bf16_ss(tbase, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, acc);
-          mma_bf16_ss(tbase + FC_NT, da + (uint64_t)(1024 + t * 16), db + (uint64_t)(t * 16), idesc, acc);
+          // eight independent accumulators (4 K-phases x 2 output tiles): a dependent MMA costs ~138 cycles whatever
+          // its size (tools/tc_probe.cu), these are 16-cycle MMAs; the epilogue adds the four K-phases
+          const uint32_t accp = (kc || t >= FC_KPH) ? 1u : 0u;
+          mma_bf16_ss(tbase + (2 * (t % FC_KPH)) * FC_NT, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, accp);
+          mma_bf16_ss(tbase + (2 * (t % FC_KPH) + 1) * FC_NT, da + (uint64_t)(1024 + t * 16), db + (uint64_t)(t * 16), idesc, accp);
         }
         mma_commit(&bar_free[st]);
         if (kc >= 1 && kc - 1 + K4_NSTAGE < 32) {   // refill the stage consumed one iteration ago
@@ -732,8 +794,15 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     FC_TR(2);
 #pragma unroll 1
     for (int cb = 0; cb < FC_NT; cb += 32) {
-      float v[32];
+      float v[32], w[32];
       tmem_ld32(tmem_addr(tbase, lq * 32, mh * FC_NT + cb), v);
+#pragma unroll
+      for (int t = 1; t < FC_KPH; t++) {        // the other K-phases
+        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * t + mh) * FC_NT + cb), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] += w[j];
+      }
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < (FC_NT < 32 ? FC_NT : 32); j++) {
@@ -753,7 +822,8 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
       mbar_wait(bar_w2, 0);
       const uint64_t da = smem_desc(sb + K4_FC2W, 128, 4096), db = smem_desc(sb + K4_H1, 128, 4096);
 #pragma unroll
-      for (int t = 0; t < 16; t++) mma_bf16_ss(tbase + 2 * FC_NT, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t ? 1u : 0u);
+      for (int t = 0; t < 16; t++)
+        mma_bf16_ss(tbase + (2 * FC_KPH + (t % FC_KPH)) * FC_NT, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t >= FC_KPH ? 1u : 0u);
       mma_commit(bar_done2);
     }
     __syncwarp();
@@ -768,8 +838,15 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
       float *h2 = reinterpret_cast<float *>(sm + K4_H2);
 #pragma unroll 1
       for (int cb = 0; cb < FC_NT; cb += 32) {
-        float v[32];
-        tmem_ld32(tmem_addr(tbase, lq * 32, 2 * FC_NT + cb), v);
+        float v[32], w[32];
+        tmem_ld32(tmem_addr(tbase, lq * 32, 2 * FC_KPH * FC_NT + cb), v);
+#pragma unroll
+        for (int t = 1; t < FC_KPH; t++) {
+          tmem_ld32(tmem_addr(tbase, lq * 32, (2 * FC_KPH + t) * FC_NT + cb), w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] += w[j];
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < (FC_NT < 32 ? FC_NT : 32); j++) h2[(cb + j) * 65 + o] = fmaxf(v[j] + bias, 0.f);
@@ -781,26 +858,35 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
   FC_TR(5);
   // fc3 (use_model.py:40,57): one thread per sample
   float *lg = reinterpret_cast<float *>(sm + K4_LG);
-  if (tid < FC_NT * 8) {                        // 8 threads per sample, two logits each
-    const int smp = tid >> 3, o2 = (tid & 7) * 2;
-    const float *h2 = reinterpret_cast<const float *>(sm + K4_H2) + smp * 65;
-    const float *w3 = reinterpret_cast<const float *>(sm + K4_F3W) + o2;
-    float a0 = __ldg(fp + F_F3B + o2), a1 = __ldg(fp + F_F3B + o2 + 1);
+  if (tid < 256) {                              // 8 threads per sample, two logits each
+#pragma unroll 1
+    for (int idx = tid; idx < FC_NT * 8; idx += 256) {
+      const int smp = idx >> 3, o2 = (idx & 7) * 2;
+      const float *h2 = reinterpret_cast<const float *>(sm + K4_H2) + smp * 65;
+      const float *w3 = reinterpret_cast<const float *>(sm + K4_F3W) + o2;
+      float a0 = __ldg(fp + F_F3B + o2), a1 = __ldg(fp + F_F3B + o2 + 1);
 #pragma unroll 8
-    for (int i = 0; i < 64; i++) {
-      const float x = h2[i];
-      const float2 w = *reinterpret_cast<const float2 *>(w3 + i * 16);
-      a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1);
+      for (int i = 0; i < 64; i++) {
+        const float x = h2[i];
+        const float2 w = *reinterpret_cast<const float2 *>(w3 + i * 16);
+        a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1);
+      }
+      const int n = nt * FC_NT + smp;            // global sample = 4 * global CTU + quadrant
+      *reinterpret_cast<float2 *>(lg + smp * 16 + o2) = make_float2(a0, a1);
+      if (n < 4 * geo.nctu * fb.n) {
+        const int f = (n >> 2) / geo.nctu, nl = n - f * 4 * geo.nctu;
+        if (fb.logits[f]) *reinterpret_cast<float2 *>(fb.logits[f] + (size_t)nl * 16 + o2) = make_float2(a0, a1);
+      }
     }
-    const int n = nt * FC_NT + smp;
-    *reinterpret_cast<float2 *>(lg + smp * 16 + o2) = make_float2(a0, a1);
-    if (n < 4 * geo.nctu && logits_out) *reinterpret_cast<float2 *>(logits_out + (size_t)n * 16 + o2) = make_float2(a0, a1);
   }
   __syncthreads();
   FC_TR(6);
   if (tid < FC_NT / 4) {
-    const int ctu = nt * (FC_NT / 4) + tid;
-    if (ctu < geo.nctu) {
+    const int ctu_g = nt * (FC_NT / 4) + tid;
+    if (ctu_g < geo.nctu * fb.n) {
+      const int f = ctu_g / geo.nctu, ctu = ctu_g - f * geo.nctu;
+      uint8_t *__restrict__ labels = fb.labels[f];
+      uint32_t *__restrict__ ctu_cnt = fb.ctu_cnt[f];
       uint8_t lab[16];
       logits_to_labels(lg + tid * 64, lab, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H, boundary_fix);
       uint4 pk;
@@ -818,11 +904,11 @@ k_tc_fc(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__restri
     printf("fc trace blk %d: setup %lld loop %lld fc1epi %lld fc2 %lld fc2epi %lld fc3 %lld labels %lld total %lld clk\n", (int)blockIdx.x,
            tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[7] - tr[0]);
 #endif
-  if (warp == 8) tmem_dealloc(tbase, 128);
+  if (warp == 8) tmem_dealloc(tbase, 512);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-inline int tc_prepare(const char *hdlt_path, int nctu, TcParams *p, std::string &err) {
+inline int tc_prepare(const char *hdlt_path, int nctu /* CTUs of one launch: frames per batch x CTUs per frame */, TcParams *p, std::string &err) {
   FILE *f = fopen(hdlt_path, "rb");
   if (!f) { err = std::string("cannot open tensor-core weight blob: ") + hdlt_path; return HEVCDL_E_WEIGHTS; }
   std::vector<uint8_t> buf(SZ_HDLT);
@@ -862,9 +948,9 @@ inline int tc_configure(std::string &err) {
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int smem, cudaStream_t st, Args... args) {
+inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int threads, int smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -874,13 +960,16 @@ inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int smem, c
 
 // Queue the four CNN kernels of one frame (programmatic dependent launch: each kernel's prologue overlaps its
 // predecessor's tail).  Returns the number of kernels launched.
-inline int tc_launch(const TcParams &p, const uint8_t *Y, const uint8_t *U, const uint8_t *V, FrameGeom g, int pitch, int cpitch,
-                     int boundary_fix, uint8_t *labels, float *logits, uint32_t *ctu_cnt, int num_sms, cudaStream_t st) {
-  const int grid = g.nctu < num_sms ? g.nctu : num_sms;
-  tc_launch_pdl(k_tc_l1, grid, K1_SMEM, st, Y, U, V, g, pitch, cpitch, p.blob, p.cat);
-  tc_launch_pdl(k_tc_conv2, grid, K2_SMEM, st, g, p.blob, (const uint8_t *)p.cat, p.a2);
-  tc_launch_pdl(k_tc_conv3, grid, K3_SMEM, st, g, p.blob, (const uint8_t *)p.a2, p.feats, p.npad);
-  tc_launch_pdl(k_tc_fc, p.npad / FC_NT, K4_SMEM, st, g, p.blob, (const uint8_t *)p.feats, p.npad, boundary_fix, labels, logits, ctu_cnt);
+inline int tc_launch(const TcParams &p, const FrameBatch &fb, FrameGeom g, int pitch, int cpitch, int boundary_fix, int num_sms,
+                     cudaStream_t st) {
+  FrameGeom gt = g;                              // K2/K3 only loop over CTUs: give them the launch's total
+  gt.nctu = g.nctu * fb.n;
+  const int grid = gt.nctu < num_sms ? gt.nctu : num_sms;
+  const int npad = ((4 * gt.nctu + 127) / 128) * 128;   // <= p.npad (sized for the largest batch); the feats layout follows the launch
+  tc_launch_pdl(k_tc_l1, grid, TC_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat);
+  tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2);
+  tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad);
+  tc_launch_pdl(k_tc_fc, npad / FC_NT, TC_THREADS, K4_SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
   return 4;
 }
 

@@ -52,6 +52,18 @@ __host__ __device__ __forceinline__ void yuv2rgb(int y, int cb, int cr, int &r, 
   b = clip255((c + 132201 * d + 32768) >> 16);
 }
 
+// Frames of one CNN launch.  All-intra frames are independent, so several frames of the same geometry can share a
+// launch: 510 CTUs of one 1080p frame leave 148 persistent CTAs with 3 or 4 CTUs each (86 % balance) and the fc
+// kernel with 64 CTAs; two frames give 6.9 -> 7 (98 %) and 128 CTAs.  Global CTU index g = frame * nctu + ctu.
+constexpr int MAX_BATCH = 4;
+struct FrameBatch {
+  const uint8_t *Y[MAX_BATCH], *U[MAX_BATCH], *V[MAX_BATCH];
+  uint8_t *labels[MAX_BATCH];
+  float *logits[MAX_BATCH];
+  uint32_t *ctu_cnt[MAX_BATCH];   // may be null (rmd = 0)
+  int n;
+};
+
 // Logits of the 4 quadrant forwards -> 16 labels (use_model.py:101-119), optional boundary fix.
 // lg: [4][16].  Runs in one thread.
 __device__ __forceinline__ void logits_to_labels(const float *lg, uint8_t *label, int ctu_x, int ctu_y,

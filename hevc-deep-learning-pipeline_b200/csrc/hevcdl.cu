@@ -32,7 +32,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-enum SlotState { SLOT_FREE = 0, SLOT_QUEUED = 1, SLOT_DONE = 2 };
+enum SlotState { SLOT_FREE = 0, SLOT_PENDING = 1 /* copied in, kernels not launched yet */, SLOT_QUEUED = 2, SLOT_DONE = 3 };
 
 struct Slot {
   int frame = -1;
@@ -58,6 +58,7 @@ struct Slot {
   uint8_t *hCand = nullptr;
   size_t hPuCap = 0;
   bool pusFetched = false;
+  bool timed = false;                  // head of a launch batch: its evT0..evT2 bracket the batch's stages
   cudaEvent_t evIn = nullptr, evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
 };
 
@@ -76,6 +77,8 @@ struct hevcdl_ctx {
   Fp32Params fp{};
   TcParams tc{};
   int numSMs = 0;
+  int batch = 1;                       // frames per CNN launch (cfg.batch)
+  std::vector<Slot *> pending;         // submitted frames waiting for their batch to fill
   int rmdBlocks = 0;                   // persistent grid of k_rmd_items: resident blocks per SM x SMs
   std::string err;
   hevcdl_stats_t stats{};
@@ -157,7 +160,7 @@ int load_weights(hevcdl_ctx *ctx) {
     std::string tp = ctx->cfg.weights_path;
     const size_t dot = tp.rfind('.');
     tp = (dot == std::string::npos ? tp : tp.substr(0, dot)) + ".hdlt";
-    return tc_prepare(tp.c_str(), ctx->geo.nctu, &ctx->tc, ctx->err);
+    return tc_prepare(tp.c_str(), ctx->geo.nctu * ctx->batch, &ctx->tc, ctx->err);
   }
   return HEVCDL_OK;
 }
@@ -205,30 +208,69 @@ int ensure_host_pu_cap(hevcdl_ctx *ctx, Slot &s, size_t n) {
   return HEVCDL_OK;
 }
 
-// Queue the device pipeline of one slot on ctx->stream.  Returns kernels launched.
-int launch_pipeline(hevcdl_ctx *ctx, Slot &s, bool timed) {
+// Queue the device pipeline of n <= cfg.batch slots on ctx->stream: one CNN launch for all of them (tensor-core path),
+// then the RMD kernels per frame.  Returns kernels launched.
+int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
   const FrameGeom g = ctx->geo;
-  FrameGeom gd = g;
   int launches = 0;
-  if (timed) cudaEventRecord(s.evT0, ctx->stream);
+  Slot &head = *sl[0];
+  if (timed) cudaEventRecord(head.evT0, ctx->stream);
   if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
-    launches += tc_launch(ctx->tc, s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, s.dLabels,
-                          s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr, ctx->numSMs, ctx->stream);
+    FrameBatch fb{};
+    fb.n = n;
+    for (int i = 0; i < n; i++) {
+      Slot &s = *sl[i];
+      fb.Y[i] = s.dY; fb.U[i] = s.dU; fb.V[i] = s.dV;
+      fb.labels[i] = s.dLabels; fb.logits[i] = s.dLogits; fb.ctu_cnt[i] = ctx->cfg.rmd ? s.dCtuCnt : nullptr;
+    }
+    launches += tc_launch(ctx->tc, fb, g, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, ctx->numSMs, ctx->stream);
   } else {
     const int grid = g.nctu < 4 * ctx->numSMs ? g.nctu : 4 * ctx->numSMs;
-    launch_pdl(k_cnn_fp32, grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream, s.dY, s.dU, s.dV, gd, ctx->pitch, ctx->cpitch, ctx->fp,
-               ctx->cfg.boundary_fix, s.dLabels, s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr);
-    launches++;
+    for (int i = 0; i < n; i++) {
+      Slot &s = *sl[i];
+      launch_pdl(k_cnn_fp32, grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream, (const uint8_t *)s.dY, (const uint8_t *)s.dU, (const uint8_t *)s.dV, g,
+                 ctx->pitch, ctx->cpitch, ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr);
+      launches++;
+    }
   }
-  if (timed) cudaEventRecord(s.evT1, ctx->stream);
-  if (ctx->cfg.rmd) {
-    launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, ctx->stream, s.dLabels, s.dCtuCnt, gd, ctx->rmdBlocks, s.dCtuOff, s.dPus, s.dItems,
-               s.dSatd, s.dCand, s.dCtrl);
-    launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream, s.dY, gd, ctx->pitch, s.dPus, s.dItems, s.dCtrl, s.dSatd, s.dCand);
-    launches += 2;
+  if (timed) cudaEventRecord(head.evT1, ctx->stream);
+  for (int i = 0; i < n; i++) {
+    Slot &s = *sl[i];
+    if (ctx->cfg.rmd) {
+      launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, ctx->stream, (const uint8_t *)s.dLabels, (const uint32_t *)s.dCtuCnt, g, ctx->rmdBlocks, s.dCtuOff,
+                 s.dPus, s.dItems, s.dSatd, s.dCand, s.dCtrl);
+      launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream, (const uint8_t *)s.dY, g, ctx->pitch, (const hevcdl_pu *)s.dPus,
+                 (const RmdItem *)s.dItems, s.dCtrl, s.dSatd, s.dCand);
+      launches += 2;
+    }
+    cudaEventRecord(s.evRmd, ctx->stream);                      // every kernel of this frame is done
   }
-  if (timed) cudaEventRecord(s.evT2, ctx->stream);
+  if (timed) cudaEventRecord(head.evT2, ctx->stream);
   return launches;
+}
+
+// Launch the kernels of the frames submitted so far (a full batch, or fewer when somebody asks for a pending frame)
+// and queue their label copies behind them.
+int flush_pending(hevcdl_ctx *ctx) {
+  const int n = (int)ctx->pending.size();
+  if (n == 0) return HEVCDL_OK;
+  const FrameGeom &g = ctx->geo;
+  for (Slot *s : ctx->pending) CK(cudaStreamWaitEvent(ctx->stream, s->evIn, 0));
+  ctx->stats.kernel_launches += launch_pipeline(ctx, ctx->pending.data(), n, true);
+  CK(cudaGetLastError());
+  for (int i = 0; i < n; i++) {
+    Slot *s = ctx->pending[i];
+    s->state = SLOT_QUEUED;
+    s->timed = i == 0;
+    CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
+    CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->d2h));
+    CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
+    if (ctx->cfg.rmd)
+      CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h));
+    CK(cudaEventRecord(s->evLabels, ctx->d2h));
+  }
+  ctx->pending.clear();
+  return HEVCDL_OK;
 }
 
 template <class T>
@@ -270,26 +312,26 @@ int submit_impl(hevcdl_ctx *ctx, int frame, const T *y, int sy, const T *u, cons
     CK(cudaMemcpyAsync(s->dY, s->hPlanes, (size_t)P * H + 2 * (size_t)CP * (H / 2), cudaMemcpyHostToDevice, ctx->h2d));
   }
   CK(cudaEventRecord(s->evIn, ctx->h2d));
-  CK(cudaStreamWaitEvent(ctx->stream, s->evIn, 0));
-  s->frame = frame; s->state = SLOT_QUEUED; s->pusFetched = false;
-  ctx->stats.kernel_launches += launch_pipeline(ctx, *s, true);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(s->evRmd, ctx->stream));                 // every kernel of the frame is done
-  CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
-  CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->d2h));
-  CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
-  if (ctx->cfg.rmd)
-    CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h));
-  CK(cudaEventRecord(s->evLabels, ctx->d2h));
+  s->frame = frame; s->state = SLOT_PENDING; s->pusFetched = false; s->timed = false;
+  ctx->pending.push_back(s);
+  if ((int)ctx->pending.size() >= ctx->batch) return flush_pending(ctx);
   return HEVCDL_OK;
 }
 
 int finish_slot(hevcdl_ctx *ctx, Slot *s) {
+  if (s->state == SLOT_PENDING) {               // its batch never filled: launch what is there
+    int rc = flush_pending(ctx);
+    if (rc) return rc;
+  }
   if (s->state == SLOT_QUEUED) {
     CK(cudaEventSynchronize(s->evLabels));
-    float a = 0, b = 0;
-    if (cudaEventElapsedTime(&a, s->evT0, s->evT1) == cudaSuccess) ctx->stats.ms_cnn += a;
-    if (cudaEventElapsedTime(&b, s->evT1, s->evT2) == cudaSuccess) ctx->stats.ms_rmd += b;
+    if (s->timed) {                             // stage times of the whole launch batch, once
+      float a = 0, b = 0;
+      if (cudaEventSynchronize(s->evT2) == cudaSuccess) {
+        if (cudaEventElapsedTime(&a, s->evT0, s->evT1) == cudaSuccess) ctx->stats.ms_cnn += a;
+        if (cudaEventElapsedTime(&b, s->evT1, s->evT2) == cudaSuccess) ctx->stats.ms_rmd += b;
+      }
+    }
     s->state = SLOT_DONE;
     ctx->stats.frames++; ctx->stats.ctus += ctx->geo.nctu;
     if (ctx->cfg.rmd) ctx->stats.pus += s->hCtuOff[ctx->geo.nctu];
@@ -359,6 +401,9 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   hevcdl_ctx *ctx = new hevcdl_ctx();
   ctx->cfg = *cfg;
   ctx->cfg.slots = cfg->slots < 1 ? 1 : cfg->slots;
+  ctx->batch = cfg->batch < 1 ? 1 : (cfg->batch > MAX_BATCH ? MAX_BATCH : cfg->batch);
+  if (ctx->batch > ctx->cfg.slots) ctx->batch = ctx->cfg.slots;
+  if (cfg->precision != HEVCDL_PREC_BF16_TC) ctx->batch = 1;   // the fp32 parity path launches per frame
   std::string wp = cfg->weights_path;
   auto fail = [&](int rc) { g_create_err = ctx->err; hevcdl_destroy(ctx); return rc; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(HEVCDL_E_CUDA); }
@@ -402,6 +447,21 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
 void hevcdl_destroy(hevcdl_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+#ifdef HEVCDL_TRACE
+  {
+    cudaDeviceSynchronize();
+    unsigned long long tr[64];
+    if (cudaMemcpyFromSymbol(tr, tc::g_trace, sizeof tr) == cudaSuccess) {
+      fprintf(stderr, "hevcdl trace (block 0 cycles, summed over all launches; epilogue sites are summed over the epilogue warps):\n"
+                      " K1: total %llu | mma: w %llu empty %llu | epi: full %llu\n"
+                      " K2: total %llu | mma: cfree %llu cfull %llu empty %llu | epi: full %llu\n"
+                      " K3: total %llu | mma: empty %llu afull %llu afree %llu | epi: full %llu\n",
+              tr[16], tr[0], tr[1], tr[2], tr[17], tr[4], tr[5], tr[6], tr[7], tr[18], tr[9], tr[10], tr[11], tr[12]);
+      memset(tr, 0, sizeof tr);
+      cudaMemcpyToSymbol(tc::g_trace, tr, sizeof tr);
+    }
+  }
+#endif
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
@@ -525,7 +585,7 @@ int hevcdl_release_frame(hevcdl_ctx *ctx, int frame) {
   if (!ctx) return HEVCDL_E_INVAL;
   Slot *s = find_slot(ctx, frame);
   if (!s) return HEVCDL_E_NOFRAME;
-  if (s->state == SLOT_QUEUED) {
+  if (s->state == SLOT_QUEUED || s->state == SLOT_PENDING) {
     int rc = finish_slot(ctx, s);
     if (rc) return rc;
   }
@@ -607,16 +667,24 @@ int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int i
   int nl = 0;
   // pass 1: whole pipeline, one pair of events around all iterations
   CK(cudaEventRecord(e0, ctx->stream));
-  for (int it = 0; it < iters; it++) nl += launch_pipeline(ctx, *sl[it % nframes], false);
+  std::vector<Slot *> grp(ctx->batch);
+  auto group = [&](int it) {                     // the next <= batch distinct slots of the rotation
+    int n = 0;
+    for (; n < ctx->batch && it + n < iters && n < nframes; n++) grp[n] = sl[(it + n) % nframes];
+    return n;
+  };
+  for (int it = 0; it < iters;) { const int n = group(it); nl += launch_pipeline(ctx, grp.data(), n, false); it += n; }
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaEventSynchronize(e1));
   CK(cudaGetLastError());
   CK(cudaEventElapsedTime(&ms[0], e0, e1));
   // pass 2: same work with per-stage events (stage split; not used for the headline)
   double cnn = 0, rmd = 0;
-  for (int it = 0; it < iters; it++) {
-    Slot &s = *sl[it % nframes];
-    nl += launch_pipeline(ctx, s, true);
+  for (int it = 0; it < iters;) {
+    const int n = group(it);
+    it += n;
+    Slot &s = *grp[0];
+    nl += launch_pipeline(ctx, grp.data(), n, true);
     CK(cudaEventSynchronize(s.evT2));
     float a = 0, b = 0;
     CK(cudaEventElapsedTime(&a, s.evT0, s.evT1));
@@ -668,6 +736,7 @@ int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size
   if (!ctx || which < 0 || which > 2) return HEVCDL_E_INVAL;
   if (ctx->cfg.precision != HEVCDL_PREC_BF16_TC) { ctx->err = "intermediates exist only on the tensor-core path"; return HEVCDL_E_INVAL; }
   cudaSetDevice(ctx->cfg.device);
+  if (ctx->batch != 1) { ctx->err = "debug_copy needs a batch=1 context"; return HEVCDL_E_INVAL; }
   const size_t sz[3] = {(size_t)ctx->geo.nctu * CAT_BYTES, (size_t)ctx->geo.nctu * A2_BYTES, (size_t)ctx->tc.npad * 4096};
   const uint8_t *src[3] = {ctx->tc.cat, ctx->tc.a2, ctx->tc.feats};
   if (size) *size = sz[which];

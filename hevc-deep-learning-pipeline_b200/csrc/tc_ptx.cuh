@@ -38,7 +38,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
+// (tuning builds: -DHEVCDL_ABLATE_MMA drops the MMAs, -DHEVCDL_ABLATE_EPI the epilogue math -- timing experiments only)
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+#ifdef HEVCDL_ABLATE_MMA
+  return;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
@@ -118,6 +122,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+
+// Tuning builds only (-DHEVCDL_TRACE): cycles block 0 spends in each mbarrier wait site, dumped by hevcdl_destroy.
+#ifdef HEVCDL_TRACE
+__device__ unsigned long long g_trace[64];
+#define MBAR_WAIT(bar, par, site)                                                                            \
+  do {                                                                                                       \
+    const long long t0_ = clock64();                                                                         \
+    mbar_wait(bar, par);                                                                                     \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_trace[site], (unsigned long long)(clock64() - t0_)); \
+  } while (0)
+#define TRACE_TOTAL(site, t0)                                                                                \
+  do {                                                                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_trace[site], (unsigned long long)(clock64() - (t0))); \
+  } while (0)
+#else
+#define MBAR_WAIT(bar, par, site) mbar_wait(bar, par)
+#define TRACE_TOTAL(site, t0)
+#endif
 
 // ---- bulk async copy global -> shared (TMA engine, 1-D), completes on an mbarrier --------------
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

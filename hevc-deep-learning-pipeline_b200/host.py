@@ -29,7 +29,7 @@ EXPORTS = [
 class Cfg(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("slots", C.c_int32), ("precision", C.c_int32), ("rmd", C.c_int32), ("boundary_fix", C.c_int32),
-                ("weights_path", C.c_char_p)]
+                ("batch", C.c_int32), ("weights_path", C.c_char_p)]
 
 
 class Stats(C.Structure):
@@ -99,13 +99,13 @@ class DepthPredictor:
     encoder_intra_main.cfg:20-22), so ranks shard frames f -> rank f % world with no exchange."""
 
     def __init__(self, width, height, device=0, slots=2, precision=PREC_FP32, rmd=True, boundary_fix=False,
-                 weights=DEFAULT_WEIGHTS):
+                 weights=DEFAULT_WEIGHTS, batch=1):
         self.lib = load_library()
         self.width, self.height = int(width), int(height)
         self.ctu_w, self.ctu_h = (self.width + 63) // 64, (self.height + 63) // 64
         self.nctu = self.ctu_w * self.ctu_h
         self.rmd = bool(rmd)
-        cfg = Cfg(1, device, self.width, self.height, slots, precision, int(rmd), int(boundary_fix),
+        cfg = Cfg(2, device, self.width, self.height, slots, precision, int(rmd), int(boundary_fix), int(batch),
                   os.fsencode(weights))
         h = C.c_void_p()
         rc = self.lib.hevcdl_create(C.byref(cfg), C.byref(h))

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(built, host):
 
 
 def test_struct_layouts_match_header(host):
-    assert C.sizeof(host.Cfg) == 8 * 4 + 8
+    assert C.sizeof(host.Cfg) == 9 * 4 + 4 + 8              # 9 int32, padding, the weights pointer
     assert host.PU_DTYPE.itemsize == 8
     assert C.sizeof(host.Stats) == 48
 
@@ -37,9 +37,9 @@ def test_create_fails_loudly_without_gpu(built, host):
 def test_create_rejects_bad_cfg(built, host):
     lib = host.load_library()
     h = C.c_void_p()
-    cfg = host.Cfg(1, 0, 417, 240, 1, 0, 1, 0, b"x")       # width not a multiple of 8
+    cfg = host.Cfg(2, 0, 417, 240, 1, 0, 1, 0, 1, b"x")       # width not a multiple of 8
     assert lib.hevcdl_create(C.byref(cfg), C.byref(h)) == -1
-    cfg = host.Cfg(99, 0, 416, 240, 1, 0, 1, 0, b"x")      # wrong ABI version
+    cfg = host.Cfg(99, 0, 416, 240, 1, 0, 1, 0, 1, b"x")      # wrong ABI version
     assert lib.hevcdl_create(C.byref(cfg), C.byref(h)) == -1
     assert lib.hevcdl_status_str(-2).decode().startswith("no usable CUDA device")
 

@@ -197,6 +197,33 @@ def test_frame_view_is_the_same_bytes_as_the_copying_getters(built, host, pkg):
     dp2.release(0); dp.close(); dp2.close()
 
 
+@pytest.mark.parametrize("batch", [2, 3])
+def test_batched_launches_give_the_same_results(built, host, pkg, batch):
+    """cfg.batch > 1: several frames share one CNN launch.  Frames are independent, so every output must be bit-identical
+    to the batch=1 context -- including the odd frame whose batch never fills (launched when it is asked for)."""
+    w, h = 416, 240
+    frames = [pkg.synth.synth_frame(w, h, 30 + i) for i in range(5)]
+    ref = _mk(host, w, h, 1, rmd=True, slots=1)
+    want = []
+    for i, f in enumerate(frames):
+        ref.submit(i, *f)
+        v = ref.view(i)
+        want.append({k: v[k].copy() for k in v})
+        ref.release(i)
+    ref.close()
+    dp = _mk(host, w, h, 1, rmd=True, slots=6, batch=batch)
+    for i, f in enumerate(frames):
+        dp.submit(100 + i, *f)
+    for i in (4, 0, 2, 1, 3):                                  # any order; frame 4 (or 3, 4) sits in an unfilled batch
+        v = dp.view(100 + i)
+        for k in ("labels", "logits", "ctu_off", "pus", "satd", "cand"):
+            assert (v[k] == want[i][k]).all(), (batch, i, k)
+        dp.release(100 + i)
+    st = dp.stats()
+    assert st["frames"] == 5
+    dp.close()
+
+
 def test_slots_busy_and_release(built, host, pkg):
     Y, U, V = pkg.synth.synth_frame(128, 64, 0)
     dp = _mk(host, 128, 64, 0, rmd=False, slots=2)
@@ -238,3 +265,35 @@ def test_full_size_properties_4k(built, host, pkg):
     b = l2.reshape(33, 59, 16)[0:32, 0:58]
     assert (a == b).all()
     dp.close(); dp2.close()
+
+
+@pytest.mark.parametrize("w,h", [(3840, 2160), (7680, 4320)])
+def test_tensor_core_path_and_k6_at_full_sizes(built, host, oracle, weights, pkg, w, h):
+    """BASELINE configs[3]/[4] picture sizes (2040 / 8160 CTUs) through the tensor-core CNN and K6: labels against
+    the oracle on sampled CTU rows (incl. the partial bottom row), K6 PU lists + SATDs bit-exact against the oracle on
+    the same rows, per-CTU offsets consistent over the whole frame, and every PU ranked."""
+    Y, U, V = pkg.synth.synth_frame(w, h, 1)
+    dp = _mk(host, w, h, 1, rmd=True, slots=1)
+    dp.submit(0, Y, U, V)
+    v = dp.view(0)
+    lab, lg, off, pus, satd, cand = v["labels"], v["logits"], v["ctu_off"], v["pus"], v["satd"], v["cand"]
+    cw, ch = (w + 63) // 64, (h + 63) // 64
+    assert lab.shape == (cw * ch, 16) and off[0] == 0 and off[-1] == len(pus) and (np.diff(off) >= 0).all()
+    assert (np.repeat(np.arange(cw * ch), np.diff(off)) == pus["ctu"]).all()
+    keep = np.where(pus["size"] >= 16, 3, 8)
+    assert all((cand[i, :keep[i]] < 35).all() and (cand[i, keep[i]:] == 255).all() for i in range(0, len(pus), 97))
+    best = satd.argmin(axis=1)
+    assert (cand[:, 0] == best).all()                          # ties -> lower mode == numpy's first minimum
+    for r in (0, ch // 2, ch - 1):
+        a, b = r * cw, r * cw + min(cw, 24)
+        olab, olg, mar = oracle.frame_labels(weights, Y, U, V, a, b, want_logits=True)
+        assert np.abs(lg[a:b] - olg[a:b]).max() < 1.0
+        nbad, nsafe = unsafe_label_mismatches(lab[a:b], olab[a:b], mar[a:b], EPS[1])
+        assert nbad == 0 and nsafe > 0, (r, nbad, nsafe)
+        opu, osatd = oracle.frame_rmd(Y, lab, a, b)
+        sl = slice(off[a], off[b])
+        assert len(opu) == off[b] - off[a]
+        assert (pus["x"][sl] == opu[:, 0]).all() and (pus["y"][sl] == opu[:, 1]).all() and (pus["size"][sl] == opu[:, 2]).all()
+        assert (satd[sl] == osatd).all()
+    dp.release(0)
+    dp.close()

@@ -58,10 +58,11 @@ __global__ void __launch_bounds__(128, 1) k_probe(Args a) {
       t0 = clock64();
       for (int r = 0; r < a.reps; r += 4) {
         const uint32_t acc = r ? 1u : 0u;
-        mma_bf16_ss(tbase, da, db, idesc, acc);
-        mma_bf16_ss(tbase + a.N, da, db, idesc, acc);
-        mma_bf16_ss(tbase + 2 * a.N, da, db, idesc, acc);
-        mma_bf16_ss(tbase + 3 * a.N, da, db, idesc, acc);
+        const uint64_t oa = (uint64_t)((r >> 2) & 7) * dka, ob = (uint64_t)((r >> 2) & 7) * dkb;   // distinct operands when kstep != 0
+        mma_bf16_ss(tbase, da + oa, db + ob, idesc, acc);
+        mma_bf16_ss(tbase + a.N, da + oa, db + ob, idesc, acc);
+        mma_bf16_ss(tbase + 2 * a.N, da + oa, db + ob, idesc, acc);
+        mma_bf16_ss(tbase + 3 * a.N, da + oa, db + ob, idesc, acc);
       }
       ti = clock64();
     }
@@ -214,6 +215,34 @@ int main() {
           printf("test3 M=%3d N=%3d K=16 nacc=%d: %.1f cycles/MMA total, %.1f issue (ideal math %.0f)\n", M, N, nacc, c[0] / 512.0, c[1] / 512.0,
                  128.0 * N / 256);
         }
+  }
+
+  // ---- test 5: cycles per MMA with the operand layouts the CNN kernels actually use, distinct operands per MMA ------
+  {
+    __nv_bfloat16 *dA, *dB;
+    CK(cudaMalloc(&dA, 64 * 1024)); CK(cudaMalloc(&dB, 64 * 1024));
+    CK(cudaMemset(dA, 0, 64 * 1024)); CK(cudaMemset(dB, 0, 64 * 1024));
+    struct Cfg { const char *name; uint32_t alb, asb, aks, blb, bsb, bks; int N, nacc; };
+    const Cfg cfgs[] = {
+        {"canonical A + canonical B, N=64", 128, 256, 4096, 128, 256, 2048, 64, 4},
+        {"canonical A + canonical B, N=128", 128, 256, 4096, 128, 256, 4096, 128, 4},
+        {"canonical A + canonical B, N=32", 128, 256, 4096, 128, 256, 1024, 32, 4},
+        {"K2-like: window A (LBO 8192, SBO 288, +16B/step) + canonical B, N=64", 8192, 288, 16, 128, 256, 2048, 64, 4},
+        {"K1-like: window A (LBO 8192, SBO 544, +16B/step) + canonical B, N=128", 8192, 544, 16, 128, 256, 4096, 128, 4},
+        {"fc-like: A (LBO 128, SBO 1024, +256B/step) + B (LBO 128, SBO 1024), N=32", 128, 1024, 256, 128, 1024, 256, 32, 4},
+        {"K3-like: canonical A + window B (LBO 6400, SBO 160, +16B/step), N=256", 128, 256, 4096, 6400, 160, 16, 256, 1},
+        {"canonical A + canonical B, N=256", 128, 256, 4096, 128, 256, 0, 256, 1},
+    };
+    for (const Cfg &c : cfgs) {
+      Args a{dA, dB, 48 * 1024, 48 * 1024, 0, c.alb, c.asb, c.aks, 0, c.blb, c.bsb, c.bks, 128, c.N, c.nacc == 1 ? 8 : 1, c.nacc == 1 ? 64 : 512, c.nacc, nullptr, d_cyc};
+      k_probe<<<1, 128, 100 * 1024>>>(a);
+      CK(cudaDeviceSynchronize());
+      long long cy[2];
+      CK(cudaMemcpy(cy, d_cyc, 16, cudaMemcpyDeviceToHost));
+      const double bytes = 128 * 32.0 + c.N * 32.0;
+      printf("test5 %-78s nacc=%d: %.1f cycles/MMA (%.0f B of operands -> %.0f B/cycle; math floor %.0f)\n", c.name, c.nacc, cy[0] / 512.0, bytes,
+             bytes / (cy[0] / 512.0), 128.0 * c.N / 256);
+    }
   }
 
   // ---- test 4: tcgen05.ld throughput ------------------------------------------------------------
