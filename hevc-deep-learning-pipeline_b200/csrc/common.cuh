@@ -64,6 +64,18 @@ struct FrameBatch {
   int n;
 };
 
+// The same for the RMD kernels: one plan + one items launch serve all frames of a batch (one work-item queue).
+struct RmdBatch {
+  const uint8_t *Y[MAX_BATCH];
+  const uint8_t *labels[MAX_BATCH];
+  const uint32_t *ctu_cnt[MAX_BATCH];
+  int *ctu_off[MAX_BATCH];
+  hevcdl_pu *pus[MAX_BATCH];
+  uint32_t *satd[MAX_BATCH];
+  uint8_t *cand[MAX_BATCH];
+  int n;
+};
+
 // Logits of the 4 quadrant forwards -> 16 labels (use_model.py:101-119), optional boundary fix.
 // lg: [4][16].  Runs in one thread.
 __device__ __forceinline__ void logits_to_labels(const float *lg, uint8_t *label, int ctu_x, int ctu_y,

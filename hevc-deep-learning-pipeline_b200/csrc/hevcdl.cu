@@ -178,7 +178,7 @@ int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
   CK(cudaMalloc(&s.dCtuCnt, (size_t)g.nctu * sizeof(uint32_t)));
   CK(cudaMalloc(&s.dCtrl, 2 * sizeof(int)));
   CK(cudaMemset(s.dCtrl, 0, 2 * sizeof(int)));
-  CK(cudaMalloc(&s.dItems, (size_t)g.nctu * MAX_ITEMS_CTU * sizeof(RmdItem)));
+  CK(cudaMalloc(&s.dItems, (size_t)g.nctu * MAX_ITEMS_CTU * sizeof(RmdItem) * ctx->batch));   // the head slot of a batch holds its queue
   CK(cudaMalloc(&s.dPus, ctx->puCap * sizeof(hevcdl_pu)));
   CK(cudaMalloc(&s.dSatd, ctx->puCap * 35 * sizeof(uint32_t)));
   CK(cudaMalloc(&s.dCand, ctx->puCap * 8));
@@ -234,17 +234,19 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
     }
   }
   if (timed) cudaEventRecord(head.evT1, ctx->stream);
-  for (int i = 0; i < n; i++) {
-    Slot &s = *sl[i];
-    if (ctx->cfg.rmd) {
-      launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, ctx->stream, (const uint8_t *)s.dLabels, (const uint32_t *)s.dCtuCnt, g, ctx->rmdBlocks, s.dCtuOff,
-                 s.dPus, s.dItems, s.dSatd, s.dCand, s.dCtrl);
-      launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream, (const uint8_t *)s.dY, g, ctx->pitch, (const hevcdl_pu *)s.dPus,
-                 (const RmdItem *)s.dItems, s.dCtrl, s.dSatd, s.dCand);
-      launches += 2;
+  if (ctx->cfg.rmd) {                             // one plan + one items launch for the whole batch (queue in the head slot)
+    RmdBatch rb{};
+    rb.n = n;
+    for (int i = 0; i < n; i++) {
+      Slot &s = *sl[i];
+      rb.Y[i] = s.dY; rb.labels[i] = s.dLabels; rb.ctu_cnt[i] = s.dCtuCnt; rb.ctu_off[i] = s.dCtuOff;
+      rb.pus[i] = s.dPus; rb.satd[i] = s.dSatd; rb.cand[i] = s.dCand;
     }
-    cudaEventRecord(s.evRmd, ctx->stream);                      // every kernel of this frame is done
+    launch_pdl(k_rmd_plan, (g.nctu * n + 7) / 8, 256, 0, ctx->stream, rb, g, ctx->rmdBlocks, head.dItems, head.dCtrl);
+    launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream, rb, g, ctx->pitch, (const RmdItem *)head.dItems, head.dCtrl);
+    launches += 2;
   }
+  for (int i = 0; i < n; i++) cudaEventRecord(sl[i]->evRmd, ctx->stream);   // every kernel of these frames is done
   if (timed) cudaEventRecord(head.evT2, ctx->stream);
   return launches;
 }

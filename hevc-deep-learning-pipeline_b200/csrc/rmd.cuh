@@ -358,7 +358,7 @@ struct RmdItem {
   uint32_t pu;          // index of the PU in the frame's list (kind 1: the 2Nx2N 8x8 PU; its 4x4 PUs follow)
   uint8_t quad;         // 64x64 PUs: 32x32 quadrant handled by this item
   uint8_t kind;         // 0: PU >= 16 (table path), 1: 8x8 CU
-  uint16_t pad;
+  uint16_t frame;       // frame of the launch batch
 };
 constexpr int MAX_ITEMS_CTU = 64;
 constexpr int RMD_BW = 4;                       // warps per block of k_rmd_items
@@ -369,21 +369,23 @@ constexpr int PTAB_P = 132;
 // ctrl[0] = work counter of k_rmd_items (starts at its grid size: the first item of a block is blockIdx.x),
 // ctrl[1] = number of items of the frame
 __global__ void __launch_bounds__(256)
-k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_cnt, FrameGeom geo, int items_grid,
-           int *__restrict__ ctu_off, hevcdl_pu *__restrict__ pus, RmdItem *__restrict__ items, uint32_t *__restrict__ satd,
-           uint8_t *__restrict__ cand, int *__restrict__ ctrl) {
-  const int lane = threadIdx.x & 31, ctu = blockIdx.x * 8 + (threadIdx.x >> 5);
+k_rmd_plan(const RmdBatch rb, FrameGeom geo, int items_grid, RmdItem *__restrict__ items, int *__restrict__ ctrl) {
+  const int lane = threadIdx.x & 31, gctu = blockIdx.x * 8 + (threadIdx.x >> 5);
   pdl_launch_dependents();
   pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = items_grid;
-  if (ctu >= geo.nctu) return;
-  // counts of the preceding CTUs (PUs, big items, small items) and the frame's total of big items
+  const int total = geo.nctu * rb.n;
+  if (gctu >= total) return;
+  const int fr = gctu / geo.nctu, ctu = gctu - fr * geo.nctu;
+  // PUs of the preceding CTUs of this frame; big / small items of everything before this CTU in (frame, CTU) order,
+  // and the batch totals (big items of all frames go first in the queue)
   uint32_t pu0 = 0, big0 = 0, sm0 = 0, bigT = 0, smT = 0;
-  for (int c = lane; c < geo.nctu; c += 32) {
-    const uint32_t v = __ldg(ctu_cnt + c);
+  for (int g = lane; g < total; g += 32) {
+    const int f = g / geo.nctu, c = g - f * geo.nctu;
+    const uint32_t v = __ldg(rb.ctu_cnt[f] + c);
     const uint32_t b = (v >> 16) & 15u, s = v >> 20;
     bigT += b; smT += s;
-    if (c < ctu) { pu0 += v & 0xFFFFu; big0 += b; sm0 += s; }
+    if (g < gctu) { big0 += b; sm0 += s; if (f == fr) pu0 += v & 0xFFFFu; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -391,18 +393,21 @@ k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_
     sm0 += __shfl_xor_sync(0xffffffffu, sm0, o); bigT += __shfl_xor_sync(0xffffffffu, bigT, o);
     smT += __shfl_xor_sync(0xffffffffu, smT, o);
   }
+  int *__restrict__ ctu_off = rb.ctu_off[fr];
+  hevcdl_pu *__restrict__ pus = rb.pus[fr];
+  uint32_t *__restrict__ satd = rb.satd[fr];
+  uint8_t *__restrict__ cand = rb.cand[fr];
   if (lane == 0) {
     ctu_off[ctu] = (int)pu0;
-    if (ctu == geo.nctu - 1) {
-      ctu_off[geo.nctu] = (int)(pu0 + (__ldg(ctu_cnt + ctu) & 0xFFFFu));
-      ctrl[1] = (int)(bigT + smT);
-    }
+    if (ctu == geo.nctu - 1) ctu_off[geo.nctu] = (int)(pu0 + (__ldg(rb.ctu_cnt[fr] + ctu) & 0xFFFFu));
+    if (gctu == total - 1) ctrl[1] = (int)(bigT + smT);
   }
   uint32_t it_big = big0, it_small = bigT + sm0;
   const int W = geo.W, H = geo.H;
   const int x0 = (ctu % geo.ctu_w) * 64, y0 = (ctu / geo.ctu_w) * 64;
-  const uint4 pk = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
+  const uint4 pk = *reinterpret_cast<const uint4 *>(rb.labels[fr] + (size_t)ctu * 16);
   const uint32_t lw[4] = {pk.x, pk.y, pk.z, pk.w};
+  const uint16_t f16 = (uint16_t)fr;
   for (int round = 0; round < 2; round++) {
     const int i3 = round * 32 + lane;                                  // z-order index of an 8x8 position
     int esize = 0, ex = 0, ey = 0;
@@ -437,13 +442,13 @@ k_rmd_plan(const uint8_t *__restrict__ labels, const uint32_t *__restrict__ ctu_
       if (esize == 8) {
         for (int k = 0; k < 4; k++)
           pus[ppos + 1 + k] = hevcdl_pu{(uint16_t)(ex + (k & 1) * 4), (uint16_t)(ey + (k >> 1) * 4), 4, (uint8_t)(k + 1), (uint16_t)ctu};
-        items[spos] = RmdItem{ppos, 0, 1, 0};
+        items[spos] = RmdItem{ppos, 0, 1, f16};
       } else if (esize == 16) {
-        items[spos] = RmdItem{ppos, 0, 0, 0};
+        items[spos] = RmdItem{ppos, 0, 0, f16};
       } else if (esize == 32) {
-        items[bpos] = RmdItem{ppos, 0, 0, 0};
+        items[bpos] = RmdItem{ppos, 0, 0, f16};
       } else {
-        for (int k = 0; k < 4; k++) items[bpos + k] = RmdItem{ppos, (uint8_t)k, 0, 0};
+        for (int k = 0; k < 4; k++) items[bpos + k] = RmdItem{ppos, (uint8_t)k, 0, f16};
         for (int m = 0; m < 35; m++) satd[(size_t)ppos * 35 + m] = 0;   // quadrant items accumulate with atomicAdd
         *reinterpret_cast<uint32_t *>(cand + (size_t)ppos * 8) = 0;     // ... and count themselves here until the last one ranks
       }
@@ -820,8 +825,7 @@ __device__ __forceinline__ void block_small(RmdBlockS &S, const uint8_t *__restr
 }
 
 __global__ void __launch_bounds__(RMD_BW * 32, 8)
-k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcdl_pu *__restrict__ pus,
-            const RmdItem *__restrict__ items, int *__restrict__ ctrl, uint32_t *__restrict__ satd_out, uint8_t *__restrict__ cand_out) {
+k_rmd_items(const RmdBatch rb, FrameGeom geo, int pitch, const RmdItem *__restrict__ items, int *__restrict__ ctrl) {
   __shared__ __align__(16) RmdBlockS S;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -842,7 +846,11 @@ k_rmd_items(const uint8_t *__restrict__ Y, FrameGeom geo, int pitch, const hevcd
     int nxt = 0;
     if (threadIdx.x == 0) nxt = atomicAdd(&ctrl[0], 1);   // claim the next item now: its latency hides behind this one
     const RmdItem item = items[it];
-    const hevcdl_pu pu = pus[item.pu];
+    const int f = item.frame;
+    const uint8_t *__restrict__ Y = rb.Y[f];
+    uint32_t *__restrict__ satd_out = rb.satd[f];
+    uint8_t *__restrict__ cand_out = rb.cand[f];
+    const hevcdl_pu pu = rb.pus[f][item.pu];
     if (item.kind == 1) block_small(S, Y, pitch, geo, pu, item, a8, a4, satd_out, cand_out);
     else if (pu.size == 16) block_large<16>(S, Y, pitch, geo, pu, item, a8, satd_out, cand_out);
     else block_large<32>(S, Y, pitch, geo, pu, item, a8, satd_out, cand_out);
