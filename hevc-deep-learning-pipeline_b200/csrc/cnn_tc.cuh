@@ -296,10 +296,18 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
 #ifdef HEVCDL_ABLATE_EPI
           if (v[0][0] != 12345.f) continue;
 #endif
+          // sums and sums of squares, two channels per instruction (packed fp32 add / fma of sm_100)
 #pragma unroll
-          for (int c = 0; c < 8; c++)
+          for (int c = 0; c < 8; c += 2) {
+            float2 s2 = make_float2(s[c], s[c + 1]), q2 = make_float2(q[c], q[c + 1]);
 #pragma unroll
-            for (int pos = 0; pos < 8; pos++) { s[c] += v[pos][c]; q[c] = fmaf(v[pos][c], v[pos][c], q[c]); }
+            for (int pos = 0; pos < 8; pos++) {
+              const float2 x = make_float2(v[pos][c], v[pos][c + 1]);
+              s2 = __fadd2_rn(s2, x);
+              q2 = __ffma2_rn(x, x, q2);
+            }
+            s[c] = s2.x; s[c + 1] = s2.y; q[c] = q2.x; q[c + 1] = q2.y;
+          }
           if (t < 4) {
 #pragma unroll
             for (int c = 0; c < 8; c++) {
@@ -488,7 +496,11 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 #endif
         float s[16], q[16];
 #pragma unroll
-        for (int c = 0; c < 16; c++) { s[c] = v0[c] + v1[c]; q[c] = fmaf(v0[c], v0[c], v1[c] * v1[c]); }
+        for (int c = 0; c < 16; c += 2) {           // packed fp32: two channels per instruction
+          const float2 x0 = make_float2(v0[c], v0[c + 1]), x1 = make_float2(v1[c], v1[c + 1]);
+          const float2 s2 = __fadd2_rn(x0, x1), q2 = __ffma2_rn(x0, x0, __fmul2_rn(x1, x1));
+          s[c] = s2.x; s[c + 1] = s2.y; q[c] = q2.x; q[c + 1] = q2.y;
+        }
         const float ts = warp_transpose_sum16(s, lane), tq = warp_transpose_sum16(q, lane);   // lane l & 15: channel 16cq + (l & 15)
         if (lane < 16) { red[(rb * 16 + warp) * 32 + lane] = ts; red[(rb * 16 + warp) * 32 + 16 + lane] = tq; }
         // 2x2 max-pool: exchange halves with the x neighbour (lane^1) then the y neighbour (lane^8);
@@ -636,9 +648,16 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
         tmem_ld32(tmem_addr(tbase, lq * 32, t * 256 + 128 * hy + 64 * pr + 32), r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int sx = 0; sx < 32; sx++) {
-          s[sx >> 3] += r0[sx] + r1[sx];
-          q[sx >> 3] = fmaf(r0[sx], r0[sx], fmaf(r1[sx], r1[sx], q[sx >> 3]));
+        for (int smp = 0; smp < 4; smp++) {         // packed fp32: two pixels per instruction
+          float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int x = 0; x < 8; x += 2) {
+            const float2 a = make_float2(r0[8 * smp + x], r0[8 * smp + x + 1]), b = make_float2(r1[8 * smp + x], r1[8 * smp + x + 1]);
+            s2 = __fadd2_rn(s2, __fadd2_rn(a, b));
+            q2 = __ffma2_rn(a, a, __ffma2_rn(b, b, q2));
+          }
+          s[smp] += s2.x + s2.y;
+          q[smp] += q2.x + q2.y;
         }
 #pragma unroll
         for (int smp = 0; smp < 4; smp++)
