@@ -80,30 +80,6 @@ __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) 
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-// Sum of v[e] over the 32 lanes for e in [0,8): every lane l returns the total of element l & 7.
-__device__ __forceinline__ float warp_transpose_sum8(float (&v)[8], int lane) {
-#pragma unroll
-  for (int off = 4, n = 8; off >= 1; off >>= 1, n >>= 1) {
-    const bool up = lane & off;
-#pragma unroll
-    for (int j = 0; j < n / 2; j++) {
-      const float send = up ? v[j] : v[j + n / 2];
-      const float keep = up ? v[j + n / 2] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  float r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 8);
-  return r + __shfl_xor_sync(0xffffffffu, r, 16);
-}
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float *v) {
-  uint32_t *r = reinterpret_cast<uint32_t *>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-}
-
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
   uint32_t *r = reinterpret_cast<uint32_t *>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"

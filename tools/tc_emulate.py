@@ -178,7 +178,7 @@ def feats_layout(feats, npad):
 
 # ---- K4: fc1 + fc2 + fc3 --------------------------------------------------------------------------
 def k4_tile(feats_u16, npad, nt, blob):
-    """128 samples [nt*128, nt*128+128) -> logits [128][16]."""
+    """128 samples [nt*128, nt*128+128) -> logits [128][16] (the kernel walks the same operand layout in 32-sample tiles)."""
     D = np.zeros((256, 128))
     for kc in range(32):
         for t in range(4):
