@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 PKG = "hevc-deep-learning-pipeline_b200"
 
 FLOP_PER_CTU = 99.49e6        # CNN MACs*2 with conv64 evaluated once per CTU
+INTOP_PER_CTU = 1.72e6        # ~420 integer ops per luma pixel for the 35-mode RMD pass (NxN trials not counted)
 BYTES_PER_CTU = 6144 + 400    # 64x64 Y + 2x32x32 C in, labels + candidate lists out
 
 
@@ -259,7 +260,10 @@ def run_b200(args, rank, world, local_rank):
                      "frac": ach_tflops / pk["tensor"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                      "kernel": "CNN stage = k_tc_l1 + k_tc_conv2 + k_tc_conv3 + k_tc_fc (tcgen05)" if prec else "k_cnn_fp32", "kernel_ms": ms_cnn,
                      "hbm_achieved_gbs": BYTES_PER_CTU * nctu / (ms_cnn / 1000.0) / 1e9, "hbm_peak_gbs": pk["hbm"],
-                     "stage_ms": {"cnn": ms_cnn, "rmd": ms[2] / args.steps}},
+                     "stage_ms": {"cnn": ms_cnn, "rmd": ms[2] / args.steps},
+                     # K6 is not a contraction: algorithmic integer ops against the CUDA-core issue peak (SMs x 128 lanes x clock)
+                     "rmd_alu": {"achieved_tiops": INTOP_PER_CTU * nctu / (ms[2] / args.steps / 1000.0) / 1e12,
+                                 "peak_tiops": 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12}},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, pkg, host)
