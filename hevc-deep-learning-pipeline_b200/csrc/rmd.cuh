@@ -380,12 +380,16 @@ k_rmd_plan(const RmdBatch rb, FrameGeom geo, int items_grid, RmdItem *__restrict
   // PUs of the preceding CTUs of this frame; big / small items of everything before this CTU in (frame, CTU) order,
   // and the batch totals (big items of all frames go first in the queue)
   uint32_t pu0 = 0, big0 = 0, sm0 = 0, bigT = 0, smT = 0;
-  for (int g = lane; g < total; g += 32) {
-    const int f = g / geo.nctu, c = g - f * geo.nctu;
-    const uint32_t v = __ldg(rb.ctu_cnt[f] + c);
-    const uint32_t b = (v >> 16) & 15u, s = v >> 20;
-    bigT += b; smT += s;
-    if (g < gctu) { big0 += b; sm0 += s; if (f == fr) pu0 += v & 0xFFFFu; }
+  for (int f = 0; f < rb.n; f++) {
+    const uint32_t *__restrict__ cnt = rb.ctu_cnt[f];
+    const int before = f < fr ? geo.nctu : (f == fr ? ctu : 0);   // CTUs of frame f that precede this one
+#pragma unroll 8
+    for (int c = lane; c < geo.nctu; c += 32) {                    // independent loads: one L2 round trip per 8
+      const uint32_t v = __ldg(cnt + c);
+      const uint32_t b = (v >> 16) & 15u, s = v >> 20;
+      bigT += b; smT += s;
+      if (c < before) { big0 += b; sm0 += s; if (f == fr) pu0 += v & 0xFFFFu; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
