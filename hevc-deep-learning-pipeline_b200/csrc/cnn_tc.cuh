@@ -4,7 +4,7 @@
 //
 //   K1 k_tc_l1   : CTU staging (Y + co-sited Cb/Cr -> RGB, zero outside the picture) + conv64 and the
 //                  four per-quadrant conv1 as implicit GEMMs over 4x2-pixel "super-pixels"
-//                  (M = 128 super-pixels, N = 8 positions x 16 channels, K = 8-pixel window rows of
+//                  (M = 128 super-pixels, N = 2 channel halves x 8 positions x 8 channels, K = 8-pixel window rows of
 //                  the (R,G) / (B,0) planes), batch-stat BN + ReLU + max-pool in the epilogue -> cat
 //   K2 k_tc_conv2: conv2 (M = 8x16 pixels, N = 64 channels, K = 9 taps x 32 channels)      -> a2
 //   K3 k_tc_conv3: conv3 (M = 128 channels, N = 256 = 4 samples x 8x8 pixels, K = 9 x 64)  -> features
@@ -260,9 +260,9 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int t = pi * 2 + e;
-          float v[8][8];
-#pragma unroll
-          for (int pos = 0; pos < 8; pos++) tmem_ld8(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + pos * 16 + 8 * h), v[pos]);
+          float v[8][8];                            // [position in the 4x2 super-pixel][channel 8h + c]: 64 contiguous columns
+          tmem_ld32(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + 64 * h), &v[0][0]);
+          tmem_ld32(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + 64 * h + 32), &v[4][0]);
           tmem_ld_wait();
           if (e == 1) {   // both accumulators of the pair are in registers: hand the TMEM slots back
             fence_before_sync();

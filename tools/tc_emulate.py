@@ -94,8 +94,8 @@ def k1_ctu(rgb, blob):
                 A = operand(buf, base + p * plane_bytes + ((row0 + wr) * pitch_px + col0) * 4, 16, 2 * pitch_px * 4, 128)
                 B = operand(blob.l1w, (wofs + wr * 2 + p) * 4096, 128, 256, 128)
                 D += A @ B.T
-        # D[m = g*8+i][n = (dy*4+dx)*16 + c] -> out[c][2g+dy][4i+dx]
-        return D.reshape(16, 8, 2, 4, 16).transpose(4, 0, 2, 1, 3).reshape(16, 32, 32)
+        # D[m = g*8+i][n = h*64 + (dy*4+dx)*8 + c8] -> out[c = 8h+c8][2g+dy][4i+dx]
+        return D.reshape(16, 8, 2, 2, 4, 8).transpose(2, 5, 0, 3, 1, 4).reshape(16, 32, 32)
 
     conv64 = np.zeros((16, 64, 64))
     for qy in range(2):

@@ -70,7 +70,8 @@ def canonical(mat, sbo_bytes=None):
 
 def pack_l1(w, gamma):
     """Layer-1 B operands: 12 matrices [128 n][16 k], kb = wr*2 + plane.
-    n = (dy*4 + dx)*16 + c  (output pixel (2g+dy, 4i+dx) of the 4x2 super-pixel, channel c);
+    n = (c//8)*64 + (dy*4 + dx)*8 + c%8  (output pixel (2g+dy, 4i+dx) of the 4x2 super-pixel, channel c: the 64
+    accumulator columns an epilogue warp reads -- 8 positions x its 8 channels -- are contiguous in tensor memory);
     k = j*2 + ch2 (input pixel column j = 0..7 of the 8-px window, ch2 of the plane):
     plane 0 holds (R,G), plane 1 holds (B,0).  Window row wr = 0..5 <-> input row 2g + wr - 2."""
     sgn = np.where(gamma < 0, -1.0, 1.0).astype(np.float32)
@@ -91,8 +92,10 @@ def pack_l1(w, gamma):
                             ci = p * 2 + ch2
                             if ci > 2:
                                 continue
-                            n0 = (dy * 4 + dx) * 16
-                            m[n0:n0 + 16, j * 2 + ch2] = w[:, ci, ky, kx] * sgn
+                            pos = dy * 4 + dx
+                            for hh in range(2):
+                                n0 = hh * 64 + pos * 8
+                                m[n0:n0 + 8, j * 2 + ch2] = (w[:, ci, ky, kx] * sgn)[8 * hh:8 * hh + 8]
             mats.append(canonical(m))
     return np.concatenate(mats)
 
