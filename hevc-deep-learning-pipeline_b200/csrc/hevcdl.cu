@@ -59,7 +59,7 @@ struct Slot {
   size_t hPuCap = 0;
   bool pusFetched = false;
   bool timed = false;                  // head of a launch batch: its evT0..evT2 bracket the batch's stages
-  cudaEvent_t evIn = nullptr, evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
+  cudaEvent_t evCnn = nullptr, evIn = nullptr, evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
 };
 
 }  // namespace
@@ -70,6 +70,7 @@ struct hevcdl_ctx {
   int pitch = 0, cpitch = 0;           // device plane pitches (bytes)
   size_t puCap = 0;
   cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;   // kernels / copies in / labels out
+  cudaStream_t rmd = nullptr;          // K6 of batch k runs here, concurrently with the CNN of batch k+1 on `stream` (HEVCDL_RMD_STREAM=0: same stream)
   cudaStream_t d2hPu = nullptr;        // PU lists out, on demand (its own stream: must not queue behind later frames' label copies)
   std::vector<Slot> slots;
   float *dWeights = nullptr;           // raw HDLW blob
@@ -187,6 +188,7 @@ int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
   CK(cudaMallocHost(&s.hLogits, (size_t)g.nctu * 64 * sizeof(float)));
   CK(cudaMallocHost(&s.hCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
   CK(cudaEventCreateWithFlags(&s.evIn, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s.evCnn, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.evLabels, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.evRmd, cudaEventDisableTiming));
   CK(cudaEventCreate(&s.evT0)); CK(cudaEventCreate(&s.evT1)); CK(cudaEventCreate(&s.evT2));
@@ -214,6 +216,8 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
   const FrameGeom g = ctx->geo;
   int launches = 0;
   Slot &head = *sl[0];
+  if (ctx->rmd)
+    for (int i = 0; i < n; i++) cudaStreamWaitEvent(ctx->stream, sl[i]->evRmd, 0);   // a slot's earlier K6 (other stream) is done
   if (timed) cudaEventRecord(head.evT0, ctx->stream);
   if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
     FrameBatch fb{};
@@ -234,7 +238,14 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
     }
   }
   if (timed) cudaEventRecord(head.evT1, ctx->stream);
+  // K6 is CUDA-core work with small blocks, the CNN kernels are one big tensor-core CTA per SM: on its own stream the
+  // RMD pass of this batch shares the SMs with K1/K2 of the next batch instead of waiting in line behind them.
+  cudaStream_t rs = ctx->rmd ? ctx->rmd : ctx->stream;
   if (ctx->cfg.rmd) {                             // one plan + one items launch for the whole batch (queue in the head slot)
+    if (rs != ctx->stream) {
+      cudaEventRecord(head.evCnn, ctx->stream);
+      cudaStreamWaitEvent(rs, head.evCnn, 0);
+    }
     RmdBatch rb{};
     rb.n = n;
     for (int i = 0; i < n; i++) {
@@ -242,12 +253,14 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
       rb.Y[i] = s.dY; rb.labels[i] = s.dLabels; rb.ctu_cnt[i] = s.dCtuCnt; rb.ctu_off[i] = s.dCtuOff;
       rb.pus[i] = s.dPus; rb.satd[i] = s.dSatd; rb.cand[i] = s.dCand;
     }
-    launch_pdl(k_rmd_plan, (g.nctu * n + 7) / 8, 256, 0, ctx->stream, rb, g, ctx->rmdBlocks, head.dItems, head.dCtrl);
-    launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, ctx->stream, rb, g, ctx->pitch, (const RmdItem *)head.dItems, head.dCtrl);
+    launch_pdl(k_rmd_plan, (g.nctu * n + 7) / 8, 256, 0, rs, rb, g, ctx->rmdBlocks, head.dItems, head.dCtrl);
+    launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, rs, rb, g, ctx->pitch, (const RmdItem *)head.dItems, head.dCtrl);
     launches += 2;
+  } else {
+    rs = ctx->stream;
   }
-  for (int i = 0; i < n; i++) cudaEventRecord(sl[i]->evRmd, ctx->stream);   // every kernel of these frames is done
-  if (timed) cudaEventRecord(head.evT2, ctx->stream);
+  for (int i = 0; i < n; i++) cudaEventRecord(sl[i]->evRmd, rs);   // every kernel of these frames is done
+  if (timed) cudaEventRecord(head.evT2, rs);
   return launches;
 }
 
@@ -425,6 +438,10 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   if (cu(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
   if (cu(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
   if (cu(cudaStreamCreateWithFlags(&ctx->d2hPu, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
+  {
+    const char *e = getenv("HEVCDL_RMD_STREAM");
+    if (ctx->cfg.rmd && !(e && e[0] == '0') && cu(cudaStreamCreateWithFlags(&ctx->rmd, cudaStreamNonBlocking), "stream")) return fail(HEVCDL_E_CUDA);
+  }
   if ((rc = load_weights(ctx))) return fail(rc);
   ctx->cfg.weights_path = nullptr;
   if (cu(cudaFuncSetAttribute(k_cnn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, FP32_SMEM_BYTES), "smem attr") ||
@@ -467,6 +484,7 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
   if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+  if (ctx->rmd) cudaStreamSynchronize(ctx->rmd);
   if (ctx->d2hPu) cudaStreamSynchronize(ctx->d2hPu);
   for (auto &s : ctx->slots) {
     cudaFree(s.dY); cudaFree(s.dLabels); cudaFree(s.dLogits); cudaFree(s.dCtuOff);
@@ -474,6 +492,7 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     cudaFreeHost(s.hPlanes); cudaFreeHost(s.hLabels); cudaFreeHost(s.hLogits); cudaFreeHost(s.hCtuOff);
     cudaFreeHost(s.hPus); cudaFreeHost(s.hSatd); cudaFreeHost(s.hCand);
     if (s.evIn) cudaEventDestroy(s.evIn);
+    if (s.evCnn) cudaEventDestroy(s.evCnn);
     if (s.evLabels) cudaEventDestroy(s.evLabels);
     if (s.evRmd) cudaEventDestroy(s.evRmd);
     if (s.evT0) cudaEventDestroy(s.evT0);
@@ -486,6 +505,7 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
   if (ctx->d2hPu) cudaStreamDestroy(ctx->d2hPu);
+  if (ctx->rmd) cudaStreamDestroy(ctx->rmd);
   cudaGetLastError();
   delete ctx;
 }
@@ -675,7 +695,9 @@ int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int i
     for (; n < ctx->batch && it + n < iters && n < nframes; n++) grp[n] = sl[(it + n) % nframes];
     return n;
   };
-  for (int it = 0; it < iters;) { const int n = group(it); nl += launch_pipeline(ctx, grp.data(), n, false); it += n; }
+  Slot *last = nullptr;
+  for (int it = 0; it < iters;) { const int n = group(it); nl += launch_pipeline(ctx, grp.data(), n, false); it += n; last = grp[n - 1]; }
+  if (ctx->rmd && last) CK(cudaStreamWaitEvent(ctx->stream, last->evRmd, 0));   // the RMD stream's last launch is part of the pass
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaEventSynchronize(e1));
   CK(cudaGetLastError());
