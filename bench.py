@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "10"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -174,7 +174,6 @@ def run_b200(args, rank, world, local_rank):
     sampler.start()
     ms, launches = dp.bench_resident(frames, args.steps)
     barrier()
-    clocks = sampler.stop()
     ms_total = maxr(ms[0])
     value = world * args.steps * nctu / (ms_total / 1000.0)
     ms_cnn = ms[1] / args.steps                      # dominant kernel: one CNN launch per step
@@ -189,7 +188,7 @@ def run_b200(args, rank, world, local_rank):
         a[:w * h] = Y.ravel(); a[w * h:w * h * 5 // 4] = U.ravel(); a[w * h * 5 // 4:] = V.ravel()
         pinned.append((buf, a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2),
                        a[w * h * 5 // 4:].reshape(h // 2, w // 2)))
-    depth = min(2 + args.batch, pool_n)
+    depth = min(args.depth if args.depth > 0 else 3 * args.batch, pool_n)
     d2h_bytes = [0]
 
     chk = [0]
@@ -232,6 +231,7 @@ def run_b200(args, rank, world, local_rank):
     dt = maxr(sec) * args.steps / e2e_iters
     d2h_bytes[0] = nb * args.steps // e2e_iters
     barrier()
+    clocks = sampler.stop()                          # sampled every 10 ms over both timed regions (resident and e2e)
     e2e_py_value = world * args.steps * nctu / dt_py
     e2e_value = world * args.steps * nctu / dt
     st = dp.stats()
@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--pool", type=int, default=48)
+    ap.add_argument("--depth", type=int, default=0, help="frames in flight in the e2e measurement (0: three launch batches)")
     ap.add_argument("--batch", type=int, default=2, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
     ap.add_argument("--ref-ctus", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
