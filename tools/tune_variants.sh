@@ -1,9 +1,8 @@
 #!/bin/bash
-# Run on the GPU box: tuning builds of libhevcdl.so (tools/_var_*.so, built with -D overrides): smoke + per-kernel times.
+# Run on the GPU box: tuning builds of libhevcdl.so (tools/_var_*.so, built with -D overrides): smoke + bench value.
 mkdir -p gpurun_out
-for so in tools/_var_*.so; do
+for so in hevc-deep-learning-pipeline_b200/csrc/libhevcdl.so tools/_var_*.so; do
   echo "== $so"
   HEVCDL_LIB=$PWD/$so python __graft_entry__.py smoke 2>&1 | tail -1
-  HEVCDL_LIB=$PWD/$so timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/var_launches.csv python bench.py --steps 3 --warmup 3 --pool 4 --no-cpu-baseline > /dev/null 2>&1
-  python tools/launch_shares.py gpurun_out/var_launches.csv | grep "k_tc_fc"
+  for i in 1 2; do HEVCDL_LIB=$PWD/$so python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value %.0f e2e %.0f stage %s' % (d['value'], d['e2e']['value'], d['roofline']['stage_ms']))"; done
 done 2>&1 | tee gpurun_out/tune.log
