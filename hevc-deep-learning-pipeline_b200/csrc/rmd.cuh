@@ -580,7 +580,7 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
   const int g = lane >> 2, t = lane & 3;
   const bool has_flt = n == 16 || n == 32;
   // ---- phase 1: stage the region and its transpose; every warp fills a quarter of the reference line ----------
-  if (tid == 0) S.grp_ctr = 0;
+  if (tid == 0) S.grp_ctr = RMD_BW;
   {
     constexpr int wpr = rs >> 2, lgw = rs == 32 ? 3 : 2;
     const uint8_t *src = Y + (size_t)(py + ry0) * pitch + px + rx0;
@@ -624,11 +624,10 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
   __syncthreads();
 
   // ---- phase 2: the warps pull reduction groups (1 or 4 modes) from a block-wide counter ------------------------
-  for (;;) {
-    int q = 0;
-    if (lane == 0) q = atomicAdd(&S.grp_ctr, 1);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= ngroups) break;
+  int q = wid;                                  // first group static (the counter starts at RMD_BW), then dynamic
+  while (q < ngroups) {
+    int nq = 0;
+    if (lane == 0) nq = atomicAdd(&S.grp_ctr, 1);   // claim the next group now: the round trip hides behind this one
     const int mfirst = rs == 32 ? q : (q < 8 ? 4 * q : 24 + q);
     const int nm = rs == 32 ? 1 : (q < 8 ? 4 : 1);
     for (int mi = 0; mi < nm; mi++) {
@@ -719,6 +718,7 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
       }
     }
     __syncwarp();
+    q = __shfl_sync(0xffffffffu, nq, 0);
   }
   // ---- phase 3: rank ------------------------------------------------------------------------------------------
   if (n == 64) __threadfence();                 // this thread's atomicAdds are visible before the block counts itself
