@@ -23,7 +23,9 @@
 //   HEVCDL_BOUNDARY_FIX 1 = raise labels of picture-edge CTUs so partial CTUs tile (default 0 = reference)
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
 //                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
-//                     decisions follow the +-1 % BD-rate clause, not the bit-exact one) (default 0: HM's own pass)
+//                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
+//                     2 = exact mode: per PU, HM's reconstructed reference samples go to hevcdl_rmd_exact (bit-exact,
+//                     byte-identical bitstream, one synchronous call per PU) (default 0: HM's own pass)
 // There is no fallback: any library failure aborts the encoder with the library's error text.
 #include <cstdio>
 #include <cstdlib>
@@ -41,7 +43,11 @@ struct HevcdlSession {
   hevcdl_ctx *ctx = nullptr;
   int width = 0, height = 0;
   int frame = -1;               // frame currently resident on the device (-1: none)
-  bool gpu_rmd = false;         // HEVCDL_RMD=1: first-pass SATDs come from the device
+  bool gpu_rmd = false;         // HEVCDL_RMD=1: first-pass SATDs come from the device (batched, original-pixel references)
+  bool exact_rmd = false;       // HEVCDL_RMD=2: ... from hevcdl_rmd_exact fed HM's reconstructed references, PU by PU
+  unsigned ex_x = ~0u, ex_y = ~0u, ex_n = 0;      // PU whose 35 SATDs are cached in ex_satd
+  uint32_t ex_satd[35];
+  unsigned long long exact_calls = 0;
   hevcdl_frame_view view;       // results of `frame` (pinned host memory owned by the library)
   bool have_view = false;
   int ctu_first = 0, ctu_count = 0, cursor = 0;   // PU range of the CTU being compressed + last hit
@@ -61,8 +67,10 @@ struct HevcdlSession {
     cfg.width = w; cfg.height = h;
     cfg.slots = 2;
     cfg.precision = ((e = getenv("HEVCDL_PRECISION")) && !strcmp(e, "bf16")) ? HEVCDL_PREC_BF16_TC : HEVCDL_PREC_FP32;
-    cfg.rmd = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
-    gpu_rmd = cfg.rmd != 0;
+    const int rmd_mode = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
+    cfg.rmd = rmd_mode == 1;
+    gpu_rmd = rmd_mode == 1;
+    exact_rmd = rmd_mode == 2;
     cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
     cfg.weights_path = (e = getenv("HEVCDL_WEIGHTS")) ? e : HEVCDL_DEFAULT_WEIGHTS;
     const int rc = hevcdl_create(&cfg, &ctx);
@@ -119,9 +127,9 @@ struct HevcdlSession {
         hevcdl_stats_t st;
         if (!hevcdl_get_stats(ctx, &st))
           fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches, "
-                          "first-pass SATDs served %llu / missed %llu\n",
+                          "first-pass SATDs served %llu / missed %llu, exact PU calls %llu\n",
                   (unsigned long long)st.frames, (unsigned long long)st.ctus, st.ms_cnn, st.ms_rmd,
-                  (unsigned long long)st.kernel_launches, hook_hits, hook_misses);
+                  (unsigned long long)st.kernel_launches, hook_hits, hook_misses, exact_calls);
       }
       hevcdl_destroy(ctx);
     }
@@ -166,8 +174,36 @@ Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
 }
 
 // First-pass SATD hook (rmd_hook.h): called from the reference's estIntraPredLumaQT mode loop.
-bool hevcdl_hm_rmd_satd( TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode, unsigned* sad )
+bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode,
+                         const short* org, unsigned orgStride, unsigned* sad )
 {
-  if ( !g_session.gpu_rmd || !g_session.have_view ) return false;
-  return g_session.lookup( pcCU->getCUPelX() + x0InCu, pcCU->getCUPelY() + y0InCu, width, mode, sad );
+  HevcdlSession &S = g_session;
+  const unsigned x = pcCU->getCUPelX() + x0InCu, y = pcCU->getCUPelY() + y0InCu;
+  if ( S.exact_rmd && S.ctx )
+  {
+    if ( mode == 0 || S.ex_x != x || S.ex_y != y || S.ex_n != width )   // first mode of a PU: one device call for all 35
+    {
+      const unsigned n = width, roiW = 2 * n + 1;
+      // HM's unfiltered reference samples of this PU (TComPattern.cpp:166-176): (2n+1) x (2n+1) raster, row 0 = corner + above,
+      // column 0 = corner + left.  Library layout: left column bottom-up, corner, above row left to right.
+      const Pel* ext = pred->getPredictorPtr( COMPONENT_Y, false );
+      int16_t line[4 * 64 + 1];
+      for ( unsigned i = 0; i < 2 * n; i++ ) line[i] = (int16_t)ext[ (2 * n - i) * roiW ];
+      line[2 * n] = (int16_t)ext[0];
+      for ( unsigned k = 0; k < 2 * n; k++ ) line[2 * n + 1 + k] = (int16_t)ext[1 + k];
+      uint8_t blk[64 * 64];
+      for ( unsigned r = 0; r < n; r++ )
+        for ( unsigned cidx = 0; cidx < n; cidx++ ) blk[r * n + cidx] = (uint8_t)org[r * orgStride + cidx];
+      const uint8_t size8 = (uint8_t)n;
+      const int rc = hevcdl_rmd_exact( S.ctx, 1, &size8, blk, line, NULL, NULL, NULL, 0.0, S.ex_satd, NULL, NULL );
+      if ( rc ) HevcdlSession::die( "hevcdl_rmd_exact", rc, S.ctx );
+      S.ex_x = x; S.ex_y = y; S.ex_n = n;
+      S.exact_calls++;
+    }
+    *sad += S.ex_satd[mode];
+    S.hook_hits++;
+    return true;
+  }
+  if ( !S.gpu_rmd || !S.have_view ) return false;
+  return S.lookup( x, y, width, mode, sad );
 }

@@ -3,10 +3,17 @@
  * hm_plugin/Makefile wraps the two statements of the first-pass mode loop of TEncSearch::estIntraPredLumaQT that
  * compute one mode's SATD (HM_dl/source/Lib/TLibEncoder/TEncSearch.cpp:2303 predIntraAng(...) and :2306
  * uiSad += distParam.DistFunc(...)) in `if ( !hevcdl_hm_rmd_satd(...) ) { ... }` with sed at build time (the edited
- * copy lives in a temp dir and is never stored).  When the session runs with HEVCDL_RMD=1 the hook supplies the SATD
- * the B200 computed for that (PU, mode) against original-picture references and the two statements are skipped;
- * mode bits, lambda, xUpdateCandList and the MPM append stay the reference's.  With HEVCDL_RMD=0 it returns false
- * and the reference code runs unchanged. */
+ * copy lives in a temp dir and is never stored).  HEVCDL_RMD selects what the hook does:
+ *   0  returns false: the reference code runs unchanged (byte-identical bitstreams);
+ *   1  batched mode: supplies the SATD the B200 computed for that (PU, mode) against ORIGINAL-picture references for the
+ *      whole frame up front (BD-rate clause); the two statements are skipped;
+ *   2  exact mode: on the first mode of a PU hands the PU's original block and the RECONSTRUCTED reference samples HM just
+ *      built (TComPattern.cpp:119-324, read back through TComPrediction::getPredictorPtr) to hevcdl_rmd_exact and serves the
+ *      35 SATDs from that one call: bit-exact, so the bitstream is again byte-identical to the reference -- a parity
+ *      demonstration of the device code inside the real encoder (one synchronous call per PU: not a speed-up).
+ * Mode bits, lambda, xUpdateCandList and the MPM append stay the reference's in every mode. */
 #pragma once
 class TComDataCU;
-bool hevcdl_hm_rmd_satd( TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode, unsigned* sad );
+class TComPrediction;
+bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode,
+                         const short* org, unsigned orgStride, unsigned* sad );

@@ -95,3 +95,28 @@ def test_dropin_first_pass_satd_served_by_the_device(tmp_path, built, host, pkg)
     assert m and int(m.group(2)) == 0 and int(m.group(1)) == 35 * npu, (r["stderr"][-300:], npu)
     ok, out = hm_util.decode_ok(str(tmp_path))
     assert ok, out[-400:]
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,qp", [(192, 128, 32), (256, 192, 22)])
+def test_dropin_exact_rmd_bitstream_equals_reference(tmp_path, built, host, pkg, w, h, qp):
+    """HEVCDL_RMD=2: the 35 first-pass SATDs of every PU come from hevcdl_rmd_exact fed HM's own reconstructed
+    reference samples.  The device code is bit-exact, so the bitstream must again be byte-identical to the unmodified
+    reference encoder fed the same labels -- thousands of PUs of every size with real reconstruction, inside the encoder."""
+    import re
+    frames = [pkg.synth.synth_frame(w, h, 40 + i) for i in range(2)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    dp = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=False)
+    for f, (Y, U, V) in enumerate(frames):
+        hm_util.write_pred(str(a / "pred"), f, dp.predict_frame(Y, U, V, frame=f))
+    dp.close()
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp)
+    rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, env={"HEVCDL_PRECISION": "fp32", "HEVCDL_RMD": "2", "HEVCDL_VERBOSE": "1"})
+    assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-400:])
+    m = re.search(r"exact PU calls (\d+)", rb["stderr"])
+    assert m and int(m.group(1)) > 100
+    assert ra["sha1"] == rb["sha1"], (ra["bytes"], rb["bytes"], ra["kbps"], rb["kbps"])

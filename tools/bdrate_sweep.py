@@ -57,7 +57,8 @@ def main():
         kinds = [("anchor", "anchor", None), ("hm_dl", "ref", None), ("dropin_fp32", "hevcdl", {"HEVCDL_PRECISION": "fp32"}),
                  ("dropin_bf16", "hevcdl", {"HEVCDL_PRECISION": "bf16"}),
                  ("dropin_gpu_rmd", "hevcdl", {"HEVCDL_PRECISION": "fp32", "HEVCDL_RMD": "1"}),
-                 ("dropin_bf16_gpu_rmd", "hevcdl", {"HEVCDL_PRECISION": "bf16", "HEVCDL_RMD": "1"})]
+                 ("dropin_bf16_gpu_rmd", "hevcdl", {"HEVCDL_PRECISION": "bf16", "HEVCDL_RMD": "1"}),
+                 ("dropin_exact_rmd", "hevcdl", {"HEVCDL_PRECISION": "fp32", "HEVCDL_RMD": "2"})]
         for name, kind, env in kinds:
             rows = []
             for qp in qps:
@@ -83,11 +84,13 @@ def main():
                  "dropin_gpu_rmd_vs_hm_dl": cmp("dropin_gpu_rmd", "hm_dl"), "dropin_gpu_rmd_vs_anchor": cmp("dropin_gpu_rmd", "anchor"),
                  "dropin_bf16_gpu_rmd_vs_hm_dl": cmp("dropin_bf16_gpu_rmd", "hm_dl"),
                  "dropin_bf16_gpu_rmd_vs_anchor": cmp("dropin_bf16_gpu_rmd", "anchor")}
+    rep["dropin_exact_rmd_bitstreams_identical_to_hm_dl"] = all(x["sha1"] == y["sha1"] for x, y in zip(rep["runs"]["dropin_exact_rmd"], rep["runs"]["hm_dl"]))
     rep["dropin_fp32_bitstreams_identical_to_hm_dl"] = all(x["sha1"] == y["sha1"] for x, y in zip(rep["runs"]["dropin_fp32"], rep["runs"]["hm_dl"]))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(rep, open(a.out, "w"), indent=1)
     print(json.dumps(rep["bd"], indent=1))
     print("dropin fp32 bitstreams identical to the reference's:", rep["dropin_fp32_bitstreams_identical_to_hm_dl"])
+    print("dropin exact-RMD bitstreams identical to the reference's:", rep["dropin_exact_rmd_bitstreams_identical_to_hm_dl"])
 
 
 if __name__ == "__main__":
