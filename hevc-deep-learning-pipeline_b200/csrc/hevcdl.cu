@@ -85,6 +85,7 @@ struct hevcdl_ctx {
   hevcdl_stats_t stats{};
   // scratch for hevcdl_rmd_exact
   void *dExact = nullptr;
+  void *hExact = nullptr;              // pinned mirror of dExact
   size_t exactCap = 0;
 };
 
@@ -500,6 +501,7 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     if (s.evT2) cudaEventDestroy(s.evT2);
   }
   cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact);
+  if (ctx->hExact) cudaFreeHost(ctx->hExact);
   tc_release(&ctx->tc);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
@@ -637,39 +639,40 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
   const size_t total = b_sizes + b_org + b_ooff + b_lines + b_loff + b_bits + b_mpm + b_madd + b_satd + b_cand + b_nc;
   if (total > ctx->exactCap) {
     cudaFree(ctx->dExact); ctx->dExact = nullptr; ctx->exactCap = 0;
-    CK(cudaMalloc(&ctx->dExact, total));
-    ctx->exactCap = total;
+    if (ctx->hExact) { cudaFreeHost(ctx->hExact); ctx->hExact = nullptr; }
+    const size_t cap = total < 65536 ? 65536 : 2 * total;     // per-PU callers vary the size call by call: grow rarely
+    CK(cudaMalloc(&ctx->dExact, cap));
+    CK(cudaMallocHost(&ctx->hExact, cap));
+    ctx->exactCap = cap;
   }
-  uint8_t *p = (uint8_t *)ctx->dExact;
-  uint8_t *d_sizes = p; p += b_sizes;
-  uint8_t *d_org = p; p += b_org;
-  int *d_ooff = (int *)p; p += b_ooff;
-  int16_t *d_lines = (int16_t *)p; p += b_lines;
-  int *d_loff = (int *)p; p += b_loff;
-  uint32_t *d_bits = (uint32_t *)p; p += b_bits;
-  int8_t *d_mpm = (int8_t *)p; p += b_mpm;
-  uint8_t *d_madd = p; p += b_madd;
-  uint32_t *d_satd = (uint32_t *)p; p += b_satd;
-  uint8_t *d_cand = p; p += b_cand;
-  uint8_t *d_nc = p;
+  // one pinned mirror with the device layout: a single copy in, a single copy out (the call is latency-bound:
+  // HM's exact mode makes one per PU)
+  const size_t o_sizes = 0, o_org = o_sizes + b_sizes, o_ooff = o_org + b_org, o_lines = o_ooff + b_ooff, o_loff = o_lines + b_lines,
+               o_bits = o_loff + b_loff, o_mpm = o_bits + b_bits, o_madd = o_mpm + b_mpm, o_satd = o_madd + b_madd,
+               o_cand = o_satd + b_satd, o_nc = o_cand + b_cand;
+  uint8_t *hp = (uint8_t *)ctx->hExact, *dp = (uint8_t *)ctx->dExact;
+  memcpy(hp + o_sizes, sizes, n);
+  memcpy(hp + o_org, org, org_off[n]);
+  memcpy(hp + o_ooff, org_off.data(), (size_t)n * 4);
+  memcpy(hp + o_lines, lines, (size_t)line_off[n] * 2);
+  memcpy(hp + o_loff, line_off.data(), (size_t)n * 4);
+  if (bits) memcpy(hp + o_bits, bits, (size_t)n * 35 * 4);
+  if (mpm) memcpy(hp + o_mpm, mpm, (size_t)n * 3);
+  if (mpm_add) memcpy(hp + o_madd, mpm_add, n);
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(d_sizes, sizes, n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_org, org, org_off[n], cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_ooff, org_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_lines, lines, (size_t)line_off[n] * 2, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_loff, line_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  if (bits) CK(cudaMemcpyAsync(d_bits, bits, (size_t)n * 35 * 4, cudaMemcpyHostToDevice, st));
-  if (mpm) CK(cudaMemcpyAsync(d_mpm, mpm, (size_t)n * 3, cudaMemcpyHostToDevice, st));
-  if (mpm_add) CK(cudaMemcpyAsync(d_madd, mpm_add, n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp, hp, o_satd, cudaMemcpyHostToDevice, st));
   const int grid = n < 16 * ctx->numSMs ? n : 16 * ctx->numSMs;
-  k_rmd_exact<<<grid, 128, 0, st>>>(n, d_sizes, d_org, d_ooff, d_lines, d_loff, bits ? d_bits : nullptr,
-                                    mpm ? d_mpm : nullptr, mpm_add ? d_madd : nullptr, sqrt_lambda, d_satd, d_cand, d_nc);
+  k_rmd_exact<<<grid, 128, 0, st>>>(n, dp + o_sizes, dp + o_org, (const int *)(dp + o_ooff), (const int16_t *)(dp + o_lines),
+                                    (const int *)(dp + o_loff), bits ? (const uint32_t *)(dp + o_bits) : nullptr,
+                                    mpm ? (const int8_t *)(dp + o_mpm) : nullptr, mpm_add ? dp + o_madd : nullptr, sqrt_lambda,
+                                    (uint32_t *)(dp + o_satd), dp + o_cand, dp + o_nc);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
-  if (satd) CK(cudaMemcpyAsync(satd, d_satd, (size_t)n * 35 * 4, cudaMemcpyDeviceToHost, st));
-  if (cand) CK(cudaMemcpyAsync(cand, d_cand, (size_t)n * 10, cudaMemcpyDeviceToHost, st));
-  if (ncand) CK(cudaMemcpyAsync(ncand, d_nc, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hp + o_satd, dp + o_satd, total - o_satd, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (satd) memcpy(satd, hp + o_satd, (size_t)n * 35 * 4);
+  if (cand) memcpy(cand, hp + o_cand, (size_t)n * 10);
+  if (ncand) memcpy(ncand, hp + o_nc, n);
   return HEVCDL_OK;
 }
 
