@@ -8,7 +8,9 @@
 //                  the (R,G) / (B,0) planes), batch-stat BN + ReLU + max-pool in the epilogue -> cat
 //   K2 k_tc_conv2: conv2 (M = 8x16 pixels, N = 64 channels, K = 9 taps x 32 channels)      -> a2
 //   K3 k_tc_conv3: conv3 (M = 128 channels, N = 256 = 4 samples x 8x8 pixels, K = 9 x 64)  -> features
-//   K4 k_tc_fc   : fc1/fc2 on tensor cores for 128 samples per CTA, fc3 + argmax + label rules
+//   K4 k_tc_fc   : fc1/fc2 on tensor cores for 32 samples per CTA, fc3 + argmax + label rules + per-CTU PU/item counts
+// One launch covers the CTUs of up to MAX_BATCH frames (FrameBatch, common.cuh); every kernel starts with its prologue
+// under programmatic dependent launch and waits for its predecessor only before touching the frame's data.
 //
 // All activations operands are read by the tensor core straight out of padded planes through
 // sliding-window shared-memory descriptors (K-major, no swizzle: 16-byte units = one pixel x 8
@@ -46,7 +48,7 @@ struct TcParams {
   int npad = 0;                    // samples padded to a multiple of 128
 };
 
-constexpr int TC_THREADS = 288;    // warps 0-7: staging + epilogue, warp 8: loads + MMA issue
+constexpr int TC_THREADS = 288;    // K1, K3, K4: warps 0-7 staging + epilogue, warp 8 loads + MMA issue (K2: 16 + 1 warps)
 #define EPI_BAR_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
 #define EPI2_BAR_SYNC() asm volatile("bar.sync 1, 512;" ::: "memory")   // kernels with 16 epilogue warps
 

@@ -1,4 +1,5 @@
-// rmd.cuh -- K6: label-driven PU enumeration and the 35-mode intra SATD ("RMD") pass.
+// rmd.cuh -- K6: label-driven PU / work-item plan and the 35-mode intra SATD ("RMD") pass (batched over the frames
+// of a launch), plus the exact single-PU entry point.
 //
 // Replaces, for every PU of a frame at once, the first pass of TEncSearch::estIntraPredLumaQT
 // (HM TLibEncoder/TEncSearch.cpp:2266-2346): reference-sample construction and smoothing
