@@ -577,7 +577,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
           mbar_expect_tx(&bar_afull[j], 2 * A2_PLANE);
           bulk_g2s(sm + K3_A2 + j * 2 * A2_PLANE, a2 + (size_t)blockIdx.x * A2_BYTES + j * 2 * A2_PLANE, 2 * A2_PLANE, &bar_afull[j]);
         }
-      mbar_wait(bar_w, 0);
+      MBAR_WAIT(bar_w, 0, 8);
       const uint32_t sb = smem_u32(sm);
       const uint64_t dw = smem_desc(sb + K3_W, 128, 256);
       uint32_t it = 0;
@@ -951,7 +951,8 @@ inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int threads
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("HEVCDL_NO_PDL") != nullptr;   // timing experiments: plain stream order
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

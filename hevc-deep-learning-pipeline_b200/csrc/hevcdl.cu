@@ -475,8 +475,8 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
       fprintf(stderr, "hevcdl trace (block 0 cycles, summed over all launches; epilogue sites are summed over the epilogue warps):\n"
                       " K1: total %llu | mma: w %llu empty %llu | epi: full %llu\n"
                       " K2: total %llu | mma: cfree %llu cfull %llu empty %llu | epi: full %llu\n"
-                      " K3: total %llu | mma: empty %llu afull %llu afree %llu | epi: full %llu\n",
-              tr[16], tr[0], tr[1], tr[2], tr[17], tr[4], tr[5], tr[6], tr[7], tr[18], tr[9], tr[10], tr[11], tr[12]);
+                      " K3: total %llu | mma: w %llu empty %llu afull %llu afree %llu | epi: full %llu\n",
+              tr[16], tr[0], tr[1], tr[2], tr[17], tr[4], tr[5], tr[6], tr[7], tr[18], tr[8], tr[9], tr[10], tr[11], tr[12]);
       memset(tr, 0, sizeof tr);
       cudaMemcpyToSymbol(tc::g_trace, tr, sizeof tr);
     }

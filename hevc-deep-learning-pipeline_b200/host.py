@@ -167,11 +167,20 @@ class DepthPredictor:
         v = FrameView()
         self._ck(self.lib.hevcdl_frame_view_get(self.h, frame, int(want_pus and self.rmd), C.byref(v)), "frame_view_get")
 
+        cache = self.__dict__.setdefault("_views", {})     # slot buffers are stable: wrap each (pointer, length) once
+
         def arr(ptr, ctype, n, shape, dtype=None):
             if not ptr or n == 0:
                 return np.empty(shape, dtype or np.dtype(ctype))
-            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
-            return (a.view(dtype) if dtype is not None else a).reshape(shape)
+            key = (ptr, n, ctype)
+            a = cache.get(key)
+            if a is None:
+                if len(cache) > 4096:
+                    cache.clear()
+                a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+                a = (a.view(dtype) if dtype is not None else a).reshape(shape)
+                cache[key] = a
+            return a
         n, m = v.nctu, v.npu
         return {"labels": arr(v.labels, C.c_uint8, n * 16, (n, 16)), "logits": arr(v.logits, C.c_float, n * 64, (n, 4, 16)),
                 "ctu_off": arr(v.ctu_off, C.c_int32, n + 1 if v.ctu_off else 0, (n + 1 if v.ctu_off else 0,)),
