@@ -774,6 +774,35 @@ int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size
   return HEVCDL_OK;
 }
 
+int hevcdl_debug_rerun_rmd(hevcdl_ctx *ctx, int frame, const uint8_t *labels) {
+  if (!ctx || !labels) return HEVCDL_E_INVAL;
+  if (!ctx->cfg.rmd) { ctx->err = "context created with rmd=0"; return HEVCDL_E_INVAL; }
+  cudaSetDevice(ctx->cfg.device);
+  Slot *s = find_slot(ctx, frame);
+  if (!s) return HEVCDL_E_NOFRAME;
+  int rc = finish_slot(ctx, s);
+  if (rc) return rc;
+  CK(cudaEventSynchronize(s->evRmd));
+  const FrameGeom g = ctx->geo;
+  cudaStream_t st = ctx->stream;
+  memcpy(s->hLabels, labels, (size_t)g.nctu * 16);
+  CK(cudaMemcpyAsync(s->dLabels, s->hLabels, (size_t)g.nctu * 16, cudaMemcpyHostToDevice, st));
+  k_rmd_counts<<<(g.nctu + 255) / 256, 256, 0, st>>>(s->dLabels, g, s->dCtuCnt);
+  RmdBatch rb{};
+  rb.n = 1;
+  rb.Y[0] = s->dY; rb.labels[0] = s->dLabels; rb.ctu_cnt[0] = s->dCtuCnt; rb.ctu_off[0] = s->dCtuOff;
+  rb.pus[0] = s->dPus; rb.satd[0] = s->dSatd; rb.cand[0] = s->dCand;
+  launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, st, rb, g, ctx->rmdBlocks, s->dItems, s->dCtrl);
+  launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, st, rb, g, ctx->pitch, (const RmdItem *)s->dItems, s->dCtrl);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches += 3;
+  CK(cudaEventRecord(s->evRmd, st));
+  CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  s->pusFetched = false;
+  return HEVCDL_OK;
+}
+
 int hevcdl_get_stats(hevcdl_ctx *ctx, hevcdl_stats_t *out) {
   if (!ctx || !out) return HEVCDL_E_INVAL;
   *out = ctx->stats;

@@ -464,6 +464,16 @@ k_rmd_plan(const RmdBatch rb, FrameGeom geo, int items_grid, RmdItem *__restrict
   }
 }
 
+// Test hook support: per-CTU counts for labels that did not come from the CNN kernels (which write them themselves).
+__global__ void __launch_bounds__(256)
+k_rmd_counts(const uint8_t *__restrict__ labels, FrameGeom geo, uint32_t *__restrict__ ctu_cnt) {
+  const int ctu = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctu >= geo.nctu) return;
+  uint8_t lab[16];
+  *reinterpret_cast<uint4 *>(lab) = *reinterpret_cast<const uint4 *>(labels + (size_t)ctu * 16);
+  ctu_cnt[ctu] = ctu_plan_counts(lab, ctu % geo.ctu_w, ctu / geo.ctu_w, geo.W, geo.H);
+}
+
 struct RmdWarpS {
   uint32_t tab[200];              // pair table of a negative-angle mode: tab[k + n] = ext[k] | ext[k+1] << 16
   float red[16][RED_P];           // per-lane block partial sums of one reduction group (16 blocks)

@@ -21,7 +21,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_get_stats",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_get_stats",
     "hevcdl_stream",
 ]
 
@@ -82,6 +82,7 @@ def load_library():
     L.hevcdl_bench_resident.argtypes = [vp, vp, ip, ip, C.POINTER(C.c_float), C.POINTER(ip)]
     L.hevcdl_bench_e2e.argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64)]
+    L.hevcdl_debug_rerun_rmd.argtypes = [vp, ip, vp]
     L.hevcdl_debug_copy.argtypes = [vp, ip, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hevcdl_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hevcdl_stream.argtypes = [vp]
@@ -249,6 +250,12 @@ class DepthPredictor:
         self._ck(self.lib.hevcdl_bench_e2e(self.h, first_id, iters, depth, n, ys, us, vs, frames[0][0].strides[0],
                                            frames[0][1].strides[0], C.byref(sec), C.byref(nb), C.byref(chk)), "bench_e2e")
         return sec.value, nb.value, chk.value
+
+    def rerun_rmd(self, frame, labels):
+        """Test hook: K6 of a finished frame again with the given labels [nctu,16] (e.g. labels read from the reference's files)."""
+        lab = np.ascontiguousarray(labels, np.uint8)
+        assert lab.shape == (self.nctu, 16)
+        self._ck(self.lib.hevcdl_debug_rerun_rmd(self.h, frame, _ptr(lab)), "debug_rerun_rmd")
 
     def debug_copy(self, which):
         """Tensor-core path intermediates of the last frame (0 cat, 1 a2, 2 features) as raw bf16 bits."""

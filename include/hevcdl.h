@@ -158,6 +158,12 @@ int hevcdl_bench_e2e(hevcdl_ctx *ctx, int first_id, int iters, int depth, int nb
  * features in the fc1 operand layout.  *size receives the byte size; dst may be NULL to query it. */
 int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size_t *size);
 
+/* Test hook: run the RMD pass (K6) of a finished frame again with caller-supplied labels [nctu*16] instead of the CNN's --
+ * the reference's own interface hands labels over as files (use_model.py:121-125), and the CNN never predicts some
+ * cases (64x64 CUs on ordinary content) that K6 must still handle.  Synchronous; afterwards the frame's label and PU
+ * getters return the new labels and their PU lists. */
+int hevcdl_debug_rerun_rmd(hevcdl_ctx *ctx, int frame, const uint8_t *labels);
+
 int hevcdl_get_stats(hevcdl_ctx *ctx, hevcdl_stats_t *out);
 /* CUDA stream handle (cudaStream_t) of the context, for callers that time with their own events */
 void *hevcdl_stream(hevcdl_ctx *ctx);

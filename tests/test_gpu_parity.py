@@ -297,3 +297,44 @@ def test_tensor_core_path_and_k6_at_full_sizes(built, host, oracle, weights, pkg
         assert (satd[sl] == osatd).all()
     dp.release(0)
     dp.close()
+
+
+def test_k6_every_label_pattern_including_64x64_vs_oracle(built, host, oracle, pkg):
+    """The CNN never predicts 64x64 CUs on ordinary content, K6 must still handle them (four quadrant work items
+    accumulating with atomics, ranked by the last one to finish).  Labels are injected through the test hook: all-0
+    CTUs, uniform 1/2/3, random consistent mixtures, on a picture with partial CTUs; everything bit-exact vs the oracle."""
+    w, h = 416, 240
+    Y, U, V = pkg.synth.synth_frame(w, h, 7, "noise")
+    Y = np.ascontiguousarray(Y); Y[:, :200] = (np.arange(200)[None, :] // 3 + 40).astype(np.uint8)
+    dp = _mk(host, w, h, 1, rmd=True)
+    dp.submit(0, Y, U, V)
+    dp.wait(0)
+    nctu = dp.nctu
+    rng = np.random.default_rng(5)
+    pats = [np.zeros((nctu, 16), np.uint8), np.full((nctu, 16), 1, np.uint8), np.full((nctu, 16), 2, np.uint8), np.full((nctu, 16), 3, np.uint8)]
+    mix = np.zeros((nctu, 16), np.uint8)
+    for c in range(nctu):
+        if c % 3 == 0:
+            continue                                           # label 0: one 64x64 CU
+        for q, idx in enumerate(([0, 1, 4, 5], [2, 3, 6, 7], [8, 9, 12, 13], [10, 11, 14, 15])):
+            mix[c, idx] = 1 if rng.random() < 0.4 else rng.integers(2, 4, 4)
+    pats.append(mix)
+    seen = set()
+    for lab in pats:
+        dp.rerun_rmd(0, lab)
+        v = dp.view(0)
+        pus, satd, cand = v["pus"], v["satd"], v["cand"]
+        assert (v["labels"] == lab).all()
+        opu, osatd = oracle.frame_rmd(Y, lab)
+        assert len(opu) == len(pus), (len(opu), len(pus))
+        if len(pus):
+            assert (pus["size"] == opu[:, 2]).all() and (pus["x"] == opu[:, 0]).all() and (pus["y"] == opu[:, 1]).all()
+            assert (satd == osatd).all()
+            assert (cand[:, 0] == satd.argmin(axis=1)).all()
+            keep = np.where(pus["size"] >= 16, 3, 8)
+            for i in range(len(pus)):
+                ref = oracle.cand_list(osatd[i], np.zeros(35, np.uint32), 0.0, int(pus["size"][i]), np.zeros(3, np.int32), 0)
+                assert (cand[i, :keep[i]] == ref[:keep[i]]).all() and (cand[i, keep[i]:] == 255).all(), i
+            seen |= set(int(x) for x in np.unique(pus["size"]))
+    assert seen == {64, 32, 16, 8, 4}, seen
+    dp.release(0); dp.close()
