@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 
 #include "TLibEncoder/TEncCu.h"
 #include "TLibEncoder/TEncTop.h"
@@ -72,7 +73,17 @@ struct HevcdlSession {
     gpu_rmd = rmd_mode == 1;
     exact_rmd = rmd_mode == 2;
     cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
+    // weights: HEVCDL_WEIGHTS, else the path baked in at build time, else <dir of this executable>/../../weights/
+    static char relpath[4096];
     cfg.weights_path = (e = getenv("HEVCDL_WEIGHTS")) ? e : HEVCDL_DEFAULT_WEIGHTS;
+    if (!e && access(cfg.weights_path, R_OK) != 0) {
+      const ssize_t len = readlink("/proc/self/exe", relpath, sizeof(relpath) - 64);
+      if (len > 0) {
+        relpath[len] = 0;
+        char *slash = strrchr(relpath, '/');
+        if (slash) { strcpy(slash, "/../../weights/hevc_encoder_model.hdlw"); cfg.weights_path = relpath; }
+      }
+    }
     const int rc = hevcdl_create(&cfg, &ctx);
     if (rc) die("hevcdl_create", rc, nullptr);
     width = w; height = h;
