@@ -215,18 +215,18 @@ def run_b200(args, rank, world, local_rank):
     # (a) driven from Python through host.DepthPredictor (ctypes); (b) the same C-ABI calls driven from C
     # (hevcdl_bench_e2e: submit_frame_u8 / frame_view_get / release_frame, host steady clock).  The headline e2e is (b);
     # (a) is reported as e2e.python_value.
-    e2e_steps(max(3, args.warmup), 1000)
+    e2e_iters = max(args.steps, 200)                 # a 40-frame loop lasts ~6 ms: time at least 200 frames and scale
+    e2e_steps(max(3, args.warmup) + 2 * depth, 1000)
     d2h_bytes[0] = 0
     barrier()
     t0 = time.perf_counter()
-    e2e_steps(args.steps, 2000)
+    e2e_steps(e2e_iters, 2000)
     torch.cuda.synchronize()
-    dt_py = maxr(time.perf_counter() - t0)
+    dt_py = maxr(time.perf_counter() - t0) * args.steps / e2e_iters
     barrier()
     planes = [(Y, U, V) for (_, Y, U, V) in pinned]
-    dp.bench_e2e(3000, max(3, args.warmup), depth, planes)
+    dp.bench_e2e(3000, max(3, args.warmup) + 2 * depth, depth, planes)
     barrier()
-    e2e_iters = max(args.steps, 200)
     sec, nb, _ = dp.bench_e2e(4000, e2e_iters, depth, planes)
     dt = maxr(sec) * args.steps / e2e_iters
     d2h_bytes[0] = nb * args.steps // e2e_iters
@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--pool", type=int, default=48)
     ap.add_argument("--depth", type=int, default=0, help="frames in flight in the e2e measurement (0: three launch batches)")
-    ap.add_argument("--batch", type=int, default=2, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
+    ap.add_argument("--batch", type=int, default=4, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
     ap.add_argument("--ref-ctus", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
