@@ -682,29 +682,34 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 // fc1 streams its 1 MB of bf16 weights through every CTA, so the sample tile is kept small (more CTAs in flight,
 // 4x less MMA and epilogue time per CTA) rather than large.
 // ================================================================================================
-#ifndef HEVCDL_FC_NT
-#define HEVCDL_FC_NT 32
-#endif
-#ifndef HEVCDL_FC_NSTAGE
-#define HEVCDL_FC_NSTAGE 4
-#endif
-constexpr int FC_NT = HEVCDL_FC_NT;
-constexpr int FC_KPH = FC_NT <= 32 ? 4 : (FC_NT <= 64 ? 2 : 1);   // K-phases = independent accumulators per output tile
-constexpr int K4_STAGE = 32768 + FC_NT * 128, K4_NSTAGE = HEVCDL_FC_NSTAGE;     // fc1 weights [256 x 64] + features [FC_NT x 64], bf16
-constexpr int K4_BAR = K4_NSTAGE * K4_STAGE;
-constexpr int K4_FC2W = (K4_BAR + 128 + 1023) / 1024 * 1024;     // fc2 weights, loaded in the prologue
-constexpr int K4_F3W = K4_FC2W + SZ_FC2;                           // fc3 weights transposed, fp32 [64][16]
-constexpr int K4_SMEM = K4_F3W + 4096;
-static_assert(K4_SMEM <= 227 * 1024, "K4 shared memory");
-static_assert(3 * FC_KPH * FC_NT <= 512, "K4 tensor memory: 2*KPH fc1 + KPH fc2 accumulators");
-// after the fc1 K loop the stage memory is reused:
-constexpr int K4_H1 = 0 /* bf16 fc2 operand [FC_NT/8][32][8][8] */, K4_H2 = K4_H1 + FC_NT * 512 /* fp32 [FC_NT][65] */,
-              K4_LG = K4_H2 + (FC_NT * 65 * 4 + 15) / 16 * 16 /* fp32 [FC_NT][16] */;
-static_assert(K4_LG + FC_NT * 16 * 4 <= K4_BAR, "K4 epilogue scratch must fit in the stage memory");
+// Two instantiations: 32-sample tiles (a single frame: 64 CTAs, the tile count is what keeps the SMs busy) and 64-sample
+// tiles (launch batches whose 32-sample tiles would not fit in one wave: half the weight traffic through L2).
+template <int NT_, int NSTAGE_>
+struct FcCfg {
+  static constexpr int NT = NT_, NSTAGE = NSTAGE_;
+  static constexpr int KPH = NT <= 32 ? 4 : (NT <= 64 ? 2 : 1);   // K-phases = independent accumulators per output tile
+  static constexpr int STAGE = 32768 + NT * 128;                  // fc1 weights [256 x 64] + features [NT x 64], bf16
+  static constexpr int BAR = NSTAGE * STAGE;
+  static constexpr int FC2W = (BAR + 128 + 1023) / 1024 * 1024;   // fc2 weights, loaded in the prologue
+  static constexpr int F3W = FC2W + SZ_FC2;                       // fc3 weights transposed, fp32 [64][16]
+  static constexpr int SMEM = F3W + 4096;
+  // after the fc1 K loop the stage memory is reused:
+  static constexpr int H1 = 0 /* bf16 fc2 operand [NT/8][32][8][8] */, H2 = H1 + NT * 512 /* fp32 [NT][65] */,
+                       LG = H2 + (NT * 65 * 4 + 15) / 16 * 16 /* fp32 [NT][16] */;
+  static_assert(SMEM <= 227 * 1024, "K4 shared memory");
+  static_assert(3 * KPH * NT <= 512, "K4 tensor memory: 2*KPH fc1 + KPH fc2 accumulators");
+  static_assert(LG + NT * 16 * 4 <= BAR, "K4 epilogue scratch must fit in the stage memory");
+  static_assert(NSTAGE <= 6, "barrier slots");
+};
+using FcSmall = FcCfg<32, 4>;
+using FcLarge = FcCfg<64, 3>;
 
+template <class CFG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, const uint8_t *__restrict__ feats, int npad, int boundary_fix) {
   using namespace tc;
+  constexpr int FC_NT = CFG::NT, FC_KPH = CFG::KPH, K4_NSTAGE = CFG::NSTAGE, K4_STAGE = CFG::STAGE, K4_BAR = CFG::BAR, K4_FC2W = CFG::FC2W,
+                K4_F3W = CFG::F3W, K4_H1 = CFG::H1, K4_H2 = CFG::H2, K4_LG = CFG::LG;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
   uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K4_BAR);   // [K4_NSTAGE]
@@ -712,7 +717,6 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
   uint64_t *bar_done = bar_full + 12;                                // fc1 accumulators complete
   uint64_t *bar_w2 = bar_full + 13;                                 // fc2 weights landed
   uint64_t *bar_done2 = bar_full + 14;
-  static_assert(K4_NSTAGE <= 6, "barrier slots");
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nt = blockIdx.x;   // sample tile
@@ -937,7 +941,8 @@ inline int tc_configure(std::string &err) {
   if (cudaFuncSetAttribute(k_tc_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(k_tc_conv2, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(k_tc_conv3, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(k_tc_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(k_tc_fc<FcSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcSmall::SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tc_fc<FcLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcLarge::SMEM) != cudaSuccess) {
     err = std::string("tensor-core kernels: shared-memory attribute: ") + cudaGetErrorString(cudaGetLastError());
     return HEVCDL_E_CUDA;
   }
@@ -967,7 +972,10 @@ inline int tc_launch(const TcParams &p, const FrameBatch &fb, FrameGeom g, int p
   tc_launch_pdl(k_tc_l1, grid, TC_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat);
   tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2);
   tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad);
-  tc_launch_pdl(k_tc_fc, npad / FC_NT, TC_THREADS, K4_SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
+  if (npad / FcSmall::NT > num_sms)             // more 32-sample tiles than SMs: 64-sample tiles halve the weight traffic
+    tc_launch_pdl(k_tc_fc<FcLarge>, npad / FcLarge::NT, TC_THREADS, FcLarge::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
+  else
+    tc_launch_pdl(k_tc_fc<FcSmall>, npad / FcSmall::NT, TC_THREADS, FcSmall::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
   return 4;
 }
 
