@@ -76,9 +76,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_pool(synth, w, h, n, rank):
+def make_pool(synth, w, h, n, rank, kind="mixed"):
     """n distinct frames: a few seeded base frames plus cyclic shifts (content differs per frame)."""
-    base = [synth.synth_frame(w, h, rank * 8 + i) for i in range(min(n, 4))]
+    base = [synth.synth_frame(w, h, rank * 8 + i, kind) for i in range(min(n, 4))]
     pool = []
     for i in range(n):
         Y, U, V = base[i % len(base)]
@@ -143,7 +143,7 @@ def run_b200(args, rank, world, local_rank):
     w, h = args.width, args.height
     prec = host.PREC_BF16_TC if args.precision == "bf16" else host.PREC_FP32
     pool_n = args.pool
-    pool = make_pool(pkg.synth, w, h, pool_n, rank)
+    pool = make_pool(pkg.synth, w, h, pool_n, rank, args.content)
     dp = host.DepthPredictor(w, h, device=local_rank, slots=pool_n, precision=prec, rmd=True, batch=args.batch)
     nctu = dp.nctu
     frame_bytes = w * h * 3 // 2
@@ -248,7 +248,7 @@ def run_b200(args, rank, world, local_rank):
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec else "f32", "data": "synthetic",
         "config": {"workload": "1 frame %dx%d all-intra QP32 per step (%d CTUs), CNN labels + 35-mode SATD (RMD) on 1 B200 per rank" % (w, h, nctu),
-                   "precision": args.precision, "frames_per_cnn_launch": args.batch, "frames_sharded": "frame f -> rank f mod N, no data-path collective",
+                   "precision": args.precision, "content": args.content, "frames_per_cnn_launch": args.batch, "frames_sharded": "frame f -> rank f mod N, no data-path collective",
                    "l2": "inputs rotate over %d resident frames per rank (%.0f MB planes + outputs > 126 MB L2)" % (pool_n, pool_n * frame_bytes / 1e6),
                    "pus_per_frame": npu_total / pool_n},
         "clocks": clocks,
@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--pool", type=int, default=48)
+    ap.add_argument("--content", default="mixed", choices=["mixed", "noise", "flat"], help="synthetic content (SURVEY.md 8(d)); noise / flat are the stress cases")
     ap.add_argument("--depth", type=int, default=0, help="frames in flight in the e2e measurement (0: three launch batches)")
     ap.add_argument("--batch", type=int, default=4, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
     ap.add_argument("--ref-ctus", type=int, default=24)
