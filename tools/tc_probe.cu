@@ -23,6 +23,8 @@ struct Args {
   uint32_t a_start, a_lbo, a_sbo, a_kstep;   // descriptor parameters (bytes); a_kstep: start advance per K-step
   uint32_t b_start, b_lbo, b_sbo, b_kstep;
   int M, N, ksteps, reps, nacc;
+  int bg;                       // background activity of warps 1-3 while warp 0 issues: 0 none, 1 tcgen05.ld, 2 shared-memory traffic, 3 bulk copies
+  const uint8_t *gsrc;          // source of the background bulk copies
   float *D;                     // [128][N]
   long long *cycles;
 };
@@ -44,6 +46,34 @@ __global__ void __launch_bounds__(128, 1) k_probe(Args a) {
   const uint32_t tbase = tmem_slot;
   const uint32_t idesc = idesc_bf16(a.M, a.N);
   long long t0 = 0, t1 = 0;
+  __shared__ volatile int stop_flag;
+  __shared__ __align__(8) uint64_t bgbar;
+  if (tid == 0) { stop_flag = 0; mbar_init(&bgbar, 1); mbar_init_fence(); }
+  __syncthreads();
+  if (warp != 0 && a.bg) {
+    float acc = 0.f;
+    uint32_t ph = 0;
+    while (!stop_flag) {
+      if (a.bg == 1) {                       // TMEM reads of columns the MMAs do not touch
+        float v[32];
+        tmem_ld32(tmem_addr(tbase, warp * 32, 256 + 32 * (warp & 1)), v);
+        tmem_ld_wait();
+        acc += v[lane & 31];
+      } else if (a.bg == 2) {                // shared-memory loads/stores in a scratch region behind the operands
+        volatile float *scr = reinterpret_cast<volatile float *>(sm + 96 * 1024);
+        for (int i = 0; i < 16; i++) { acc += scr[(tid + 32 * i) & 1023]; scr[(tid * 3 + i) & 1023] = acc; }
+      } else if (a.bg == 3 && warp == 1) {   // bulk copies global -> shared (16 KB each)
+        if (lane == 0) {
+          mbar_expect_tx(&bgbar, 16384);
+          bulk_g2s(sm + 96 * 1024, a.gsrc, 16384, &bgbar);
+          mbar_wait(&bgbar, ph & 1);
+          ph++;
+        }
+        __syncwarp();
+      }
+    }
+    if (acc == 123.f) a.cycles[3] = 1;
+  }
   if (warp == 0 && elect_one()) {
     const uint32_t sa = smem_u32(sm) + a.a_start, sb = smem_u32(smb) + a.b_start;
     const uint64_t da = smem_desc(sa, a.a_lbo, a.a_sbo), db = smem_desc(sb, a.b_lbo, a.b_sbo);
@@ -71,6 +101,7 @@ __global__ void __launch_bounds__(128, 1) k_probe(Args a) {
     t1 = clock64();
     if (a.cycles) a.cycles[1] = ti - t0;
     if (a.cycles) a.cycles[0] = t1 - t0;
+    stop_flag = 1;
   }
   __syncthreads();
   fence_after_sync();
@@ -146,7 +177,7 @@ int main() {
     CK(cudaMalloc(&dA, pa.size() * 2)); CK(cudaMalloc(&dB, pb.size() * 2)); CK(cudaMalloc(&dD, M * N * 4));
     CK(cudaMemcpy(dA, pa.data(), pa.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dB, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
-    Args a{dA, dB, (int)pa.size() * 2, (int)pb.size() * 2, 0, 128, (K / 8) * 128, 256, 0, 128, (K / 8) * 128, 256, M, N, K / 16, 1, 1, dD, d_cyc};
+    Args a{dA, dB, (int)pa.size() * 2, (int)pb.size() * 2, 0, 128, (K / 8) * 128, 256, 0, 128, (K / 8) * 128, 256, M, N, K / 16, 1, 1, 0, nullptr, dD, d_cyc};
     k_probe<<<1, 128, 64 * 1024>>>(a);
     CK(cudaDeviceSynchronize());
     std::vector<float> D(M * N);
@@ -180,7 +211,7 @@ int main() {
     CK(cudaMemcpy(dB, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
     const int row0 = 2, col0 = 3;   // window origin: NOT 128-byte aligned
     Args a{dA, dB, (int)pp.size() * 2, (int)pb.size() * 2, (uint32_t)((row0 * pitch_u + col0) * 16), 16, pitch_u * 16, 0,
-           0, 128, 256, 0, 128, N, 1, 1, 1, dD, d_cyc};
+           0, 128, 256, 0, 128, N, 1, 1, 1, 0, nullptr, dD, d_cyc};
     k_probe<<<1, 128, 64 * 1024>>>(a);
     CK(cudaDeviceSynchronize());
     std::vector<float> D(128 * N);
@@ -207,7 +238,7 @@ int main() {
       for (int N : Ns)
         for (int nacc : {1, 4}) {
           if (nacc == 4 && N > 128) continue;
-          Args a{dA, dB, 32 * 1024, 32 * 1024, 0, 16u, 192u, 0, 0, 128, 256, 0, M, N, 1, 512, nacc, nullptr, d_cyc};
+          Args a{dA, dB, 32 * 1024, 32 * 1024, 0, 16u, 192u, 0, 0, 128, 256, 0, M, N, 1, 512, nacc, 0, nullptr, nullptr, d_cyc};
           k_probe<<<1, 128, 80 * 1024>>>(a);
           CK(cudaDeviceSynchronize());
           long long c[2];
@@ -234,7 +265,7 @@ int main() {
         {"canonical A + canonical B, N=256", 128, 256, 4096, 128, 256, 0, 256, 1},
     };
     for (const Cfg &c : cfgs) {
-      Args a{dA, dB, 48 * 1024, 48 * 1024, 0, c.alb, c.asb, c.aks, 0, c.blb, c.bsb, c.bks, 128, c.N, c.nacc == 1 ? 8 : 1, c.nacc == 1 ? 64 : 512, c.nacc, nullptr, d_cyc};
+      Args a{dA, dB, 48 * 1024, 48 * 1024, 0, c.alb, c.asb, c.aks, 0, c.blb, c.bsb, c.bks, 128, c.N, c.nacc == 1 ? 8 : 1, c.nacc == 1 ? 64 : 512, c.nacc, 0, nullptr, nullptr, d_cyc};
       k_probe<<<1, 128, 100 * 1024>>>(a);
       CK(cudaDeviceSynchronize());
       long long cy[2];
@@ -243,6 +274,24 @@ int main() {
       printf("test5 %-78s nacc=%d: %.1f cycles/MMA (%.0f B of operands -> %.0f B/cycle; math floor %.0f)\n", c.name, c.nacc, cy[0] / 512.0, bytes,
              bytes / (cy[0] / 512.0), 128.0 * c.N / 256);
     }
+  }
+
+  // ---- test 6: the same MMAs while the other warps of the CTA keep TMEM / shared memory / the bulk-copy engine busy ----
+  {
+    __nv_bfloat16 *dA, *dB;
+    uint8_t *gsrc;
+    CK(cudaMalloc(&dA, 64 * 1024)); CK(cudaMalloc(&dB, 64 * 1024)); CK(cudaMalloc(&gsrc, 64 * 1024));
+    CK(cudaMemset(dA, 0, 64 * 1024)); CK(cudaMemset(dB, 0, 64 * 1024)); CK(cudaMemset(gsrc, 0, 64 * 1024));
+    const char *bgname[4] = {"idle", "tcgen05.ld", "shared-memory traffic", "bulk copies"};
+    for (int N : {64, 128})
+      for (int bg = 0; bg < 4; bg++) {
+        Args a{dA, dB, 48 * 1024, 48 * 1024, 0, 8192u, 288u, 16u, 0, 128, 256, (uint32_t)(N * 32), 128, N, 1, 512, 4, bg, gsrc, nullptr, d_cyc};
+        k_probe<<<1, 128, 120 * 1024>>>(a);
+        CK(cudaDeviceSynchronize());
+        long long cy[2];
+        CK(cudaMemcpy(cy, d_cyc, 16, cudaMemcpyDeviceToHost));
+        printf("test6 window A + canonical B, N=%3d, 4 accumulators, other warps: %-22s %.1f cycles/MMA\n", N, bgname[bg], cy[0] / 512.0);
+      }
   }
 
   // ---- test 4: tcgen05.ld throughput ------------------------------------------------------------
