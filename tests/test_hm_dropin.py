@@ -120,3 +120,54 @@ def test_dropin_exact_rmd_bitstream_equals_reference(tmp_path, built, host, pkg,
     m = re.search(r"exact PU calls (\d+)", rb["stderr"])
     assert m and int(m.group(1)) > 100
     assert ra["sha1"] == rb["sha1"], (ra["bytes"], rb["bytes"], ra["kbps"], rb["kbps"])
+
+
+BITSTREAM_CFG = """InputFile : {yuv}
+InputBitDepth : 8
+InputChromaFormat : 420
+FrameRate : 30
+FrameSkip : 0
+SourceWidth : {w}
+SourceHeight : {h}
+FramesToBeEncoded : {n}
+Level : 3.1
+"""
+SHIM = """import runpy, sys
+sys.path.insert(0, {root!r})
+sys.argv = ["sidecar", {cmd!r}]
+runpy.run_module("hevc-deep-learning-pipeline_b200.sidecar", run_name="__main__")
+"""
+
+
+def test_sidecar_parses_bitstream_cfg_by_line_index_and_resets_pred(tmp_path, monkeypatch):
+    import importlib
+    sidecar = importlib.import_module("hevc-deep-learning-pipeline_b200.sidecar")
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "bitstream.cfg").write_text(BITSTREAM_CFG.format(yuv="C:\\\\seq\\\\a.yuv", w=416, h=240, n=6))
+    cfg = sidecar.parse_bitstream_cfg()
+    assert cfg == {"input": "C:\\\\seq\\\\a.yuv", "frame_rate": "30", "width": 416, "height": 240, "frames": 6}
+    (tmp_path / "pred").mkdir(); (tmp_path / "pred" / "stale").mkdir()
+    sidecar.main(["gen_frames"])
+    assert os.path.isdir("pred") and os.listdir("pred") == []
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_unmodified_reference_encoder_with_the_b200_sidecar(tmp_path, built, pkg):
+    """The whole reference system, unmodified binary included: TAppEncoder_ref runs `python gen_frames.py` and
+    `python use_model.py` from its working directory (encmain.cpp:53-58,105-108) and polls ./pred; the two scripts here
+    are one-line shims onto this repo's sidecar module.  The stream must equal the drop-in encoder's."""
+    w, h, n = 192, 128, 3
+    frames = [pkg.synth.synth_frame(w, h, 50 + i) for i in range(n)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    (a / "bitstream.cfg").write_text(BITSTREAM_CFG.format(yuv="in.yuv", w=w, h=h, n=n))
+    (a / "gen_frames.py").write_text(SHIM.format(root=hm_util.ROOT, cmd="gen_frames"))
+    (a / "use_model.py").write_text(SHIM.format(root=hm_util.ROOT, cmd="use_model"))
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, n, 32)
+    rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, n, 32, env={"HEVCDL_PRECISION": "fp32"})
+    assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-600:], rb["stderr"][-400:])
+    assert sorted(os.listdir(a / "pred")) == ["0", "1", "2"] and len(os.listdir(a / "pred" / "0")) == 6
+    assert ra["sha1"] == rb["sha1"]
