@@ -68,7 +68,9 @@ def use_model(args):
         dp.write_pred_files(dp.labels(f), "./pred", f)     # use_model.py:121-125: temp name, then rename
         dp.release(f)
 
-    for f in range(nframes):
+    # all-intra frames are independent: with --world G each of G processes (one per GPU) takes frames f = rank mod G
+    # and reads them at byte offset f * W * H * 3/2; they all publish into the same ./pred
+    for f in host.rank_frames(nframes, args.rank, args.world):
         fr = yuv[f * fbytes:(f + 1) * fbytes]
         Y = fr[:w * h].reshape(h, w)
         U = fr[w * h:w * h * 5 // 4].reshape(h // 2, w // 2)
@@ -80,7 +82,7 @@ def use_model(args):
     for f in inflight:
         publish(f)
     dp.close()
-    print("hevcdl sidecar: %d frames, %d CTUs each" % (nframes, dp.nctu))
+    print("hevcdl sidecar rank %d/%d: %d of %d frames, %d CTUs each" % (args.rank, args.world, len(host.rank_frames(nframes, args.rank, args.world)), nframes, dp.nctu))
 
 
 def main(argv=None):
@@ -90,7 +92,9 @@ def main(argv=None):
     um = sub.add_parser("use_model")
     um.add_argument("--precision", default=os.environ.get("HEVCDL_PRECISION", "fp32"), choices=["fp32", "bf16"])
     um.add_argument("--batch", type=int, default=1)
-    um.add_argument("--device", type=int, default=int(os.environ.get("HEVCDL_DEVICE", "0")))
+    um.add_argument("--device", type=int, default=int(os.environ.get("HEVCDL_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    um.add_argument("--rank", type=int, default=int(os.environ.get("RANK", "0")))
+    um.add_argument("--world", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     args = ap.parse_args(argv)
     (gen_frames if args.cmd == "gen_frames" else use_model)(args)
 
