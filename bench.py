@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 PKG = "hevc-deep-learning-pipeline_b200"
 
 FLOP_PER_CTU = 99.49e6        # CNN MACs*2 with conv64 evaluated once per CTU
+WORKLOAD = "1 frame %dx%d all-intra QP32 per step (%d CTUs), CNN labels + 35-mode SATD (RMD)"   # BASELINE.json configs[1]
 INTOP_PER_CTU = 1.72e6        # ~420 integer ops per luma pixel for the 35-mode RMD pass (NxN trials not counted)
 BYTES_PER_CTU = 6144 + 400    # 64x64 Y + 2x32x32 C in, labels + candidate lists out
 
@@ -127,7 +128,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "intra CTUs/sec", "value": v, "unit": "CTU/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1 frame %dx%d all-intra QP32, CNN labels + 35-mode SATD (RMD)" % (w, h)},
+        "config": {"workload": WORKLOAD % (w, h, nctu), "arm": "the reference's CPU path on the host cores: %d CTUs of the frame per step" % n_ctus},
         "cpu_baseline": {"value": v, "unit": "CTU/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -247,7 +248,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": "intra CTUs/sec", "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec else "f32", "data": "synthetic",
-        "config": {"workload": "1 frame %dx%d all-intra QP32 per step (%d CTUs), CNN labels + 35-mode SATD (RMD) on 1 B200 per rank" % (w, h, nctu),
+        "config": {"workload": WORKLOAD % (w, h, nctu), "arm": "one B200 per rank",
                    "precision": args.precision, "content": args.content, "frames_per_cnn_launch": args.batch, "frames_sharded": "frame f -> rank f mod N, no data-path collective",
                    "l2": "inputs rotate over %d resident frames per rank (%.0f MB planes + outputs > 126 MB L2)" % (pool_n, pool_n * frame_bytes / 1e6),
                    "pus_per_frame": npu_total / pool_n},
