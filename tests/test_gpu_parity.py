@@ -338,3 +338,56 @@ def test_k6_every_label_pattern_including_64x64_vs_oracle(built, host, oracle, p
             seen |= set(int(x) for x in np.unique(pus["size"]))
     assert seen == {64, 32, 16, 8, 4}, seen
     dp.release(0); dp.close()
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (64, 8), (8, 72), (72, 200), (200, 136), (1016, 56)])
+@pytest.mark.parametrize("prec", [0, 1])
+def test_odd_geometries_vs_oracle(built, host, oracle, weights, pkg, w, h, prec):
+    """Picture sizes that are multiples of 8 but not of 64 (the minimum HM accepts, TAppEncCfg.cpp:2176): partial CTUs on
+    both edges, single-CTU and single-row pictures.  Labels vs the oracle (margin rule), K6 bit-exact for the labels used."""
+    Y, U, V = pkg.synth.synth_frame(w, h, 3, "noise" if w * h < 4096 else "mixed")
+    for fix in (False, True):
+        dp = _mk(host, w, h, prec, rmd=True, boundary_fix=fix)
+        dp.submit(0, Y, U, V)
+        v = dp.view(0)
+        lab, lg, pus, satd = v["labels"].copy(), v["logits"].copy(), v["pus"].copy(), v["satd"].copy()
+        dp.release(0); dp.close()
+        if not fix:
+            olab, olg, mar = oracle.frame_labels(weights, Y, U, V, want_logits=True)
+            assert np.abs(lg - olg).max() < (2e-3 if prec == 0 else 1.0)
+            assert unsafe_label_mismatches(lab, olab, mar, EPS[prec])[0] == 0
+        opu, osatd = oracle.frame_rmd(Y, lab)
+        assert len(opu) == len(pus)
+        if len(pus):
+            assert (pus["x"] == opu[:, 0]).all() and (pus["y"] == opu[:, 1]).all() and (pus["size"] == opu[:, 2]).all()
+            assert (satd == osatd).all()
+        if fix:                                                # the evaluated 2Nx2N PUs tile the picture exactly once
+            cover = np.zeros((h, w), np.int32)
+            for p in pus[pus["part"] == 0]:
+                cover[p["y"]:p["y"] + p["size"], p["x"]:p["x"] + p["size"]] += 1
+            assert (cover == 1).all()
+
+
+def test_two_contexts_interleaved(built, host, pkg):
+    """Two contexts of different geometry and precision used alternately from one thread (their kernels share the GPU and
+    may overlap): every frame's results equal the ones a single context gives."""
+    fa = [pkg.synth.synth_frame(416, 240, 60 + i) for i in range(4)]
+    fb = [pkg.synth.synth_frame(256, 192, 70 + i) for i in range(4)]
+    ref_a = _mk(host, 416, 240, 1, rmd=True); want_a = []
+    for i, f in enumerate(fa):
+        ref_a.submit(i, *f); v = ref_a.view(i); want_a.append((v["labels"].copy(), v["satd"].copy())); ref_a.release(i)
+    ref_a.close()
+    ref_b = _mk(host, 256, 192, 0, rmd=True); want_b = []
+    for i, f in enumerate(fb):
+        ref_b.submit(i, *f); v = ref_b.view(i); want_b.append((v["labels"].copy(), v["satd"].copy())); ref_b.release(i)
+    ref_b.close()
+    a = _mk(host, 416, 240, 1, rmd=True, slots=4, batch=2)
+    b = _mk(host, 256, 192, 0, rmd=True, slots=4)
+    for i in range(4):
+        a.submit(i, *fa[i]); b.submit(i, *fb[i])
+    for i in (3, 0, 2, 1):
+        va, vb = a.view(i), b.view(i)
+        assert (va["labels"] == want_a[i][0]).all() and (va["satd"] == want_a[i][1]).all()
+        assert (vb["labels"] == want_b[i][0]).all() and (vb["satd"] == want_b[i][1]).all()
+        a.release(i); b.release(i)
+    a.close(); b.close()
