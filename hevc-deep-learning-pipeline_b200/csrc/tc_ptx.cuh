@@ -119,8 +119,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef HEVCDL_GUARD_WAITS   // tuning builds of new synchronisation: a lost arrival traps instead of hanging the device
+  for (uint32_t n = 0; !mbar_try_wait(bar, parity); n++)
+    if (n > (1u << 26)) __trap();
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // Tuning builds only (-DHEVCDL_TRACE): cycles block 0 spends in each mbarrier wait site, dumped by hevcdl_destroy.
