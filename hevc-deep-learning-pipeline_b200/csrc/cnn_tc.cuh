@@ -48,7 +48,7 @@ struct TcParams {
   int npad = 0;                    // samples padded to a multiple of 128
 };
 
-constexpr int TC_THREADS = 288;    // K1, K3, K4: warps 0-7 staging + epilogue, warp 8 loads + MMA issue (K2: 16 + 1 warps)
+constexpr int TC_THREADS = 288;    // K3, K4: warps 0-7 epilogue, warp 8 loads + MMA issue (K1: + 3 staging warps, K2: 16 + 1 warps)
 #define EPI_BAR_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
 #define EPI2_BAR_SYNC() asm volatile("bar.sync 1, 512;" ::: "memory")   // kernels with 16 epilogue warps
 
@@ -112,19 +112,27 @@ __device__ __forceinline__ uint4 pack8_bf16(const float *y) {
 constexpr int P64_PITCH = 68, P64_BYTES = 68 * 68 * 4;   // (R,G) or (B,0) bf16 pairs, 2-pixel zero halo
 constexpr int P1_PITCH = 36, P1_BYTES = 36 * 36 * 4;
 constexpr int K1_W = 0, K1_P64 = K1_W + SZ_L1W, K1_P1 = K1_P64 + 2 * P64_BYTES, K1_RED = K1_P1 + 8 * P1_BYTES,
-              K1_BAR = K1_RED + 2 * 8 * 16 * 4, K1_SMEM = K1_BAR + 64;
+              K1_BAR = K1_RED + 2 * 8 * 16 * 4, K1_SMEM = K1_BAR + 128;
 
-// 8 epilogue warps (warp = TMEM lane quarter + 4 * channel half) + 1 TMA/MMA warp.  A 16-epilogue-warp variant (4
-// channels per thread) was measured slower (40.9 vs 37 us per 1080p frame): twice the TMEM load instructions and
+// 8 epilogue warps (warp = TMEM lane quarter + 4 * channel half) + 1 TMA/MMA warp + 3 staging warps.  A 16-epilogue-warp
+// variant (4 channels per thread) was measured slower (40.9 vs 37 us per 1080p frame): twice the TMEM load instructions and
 // duplicated reduction work outweigh the extra latency hiding.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// The three roles run decoupled, one CTU apart: the staging warps fill the input planes of CTU j+1 as soon as the MMAs of
+// CTU j have finished reading them (conv64 planes after tile pair 1, quadrant planes after pair 3), the MMA thread starts
+// CTU j+1 as soon as planes and a TMEM slot are available, so the epilogue warps -- the bottleneck -- never wait for
+// staging or for the first pair's MMA latency.
+constexpr int K1_THREADS = 12 * 32, K1_MMA_WARP = 8, K1_STAGE_THREADS = 96, K1_STAGE_ITERS = (1024 + K1_STAGE_THREADS - 1) / K1_STAGE_THREADS;
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
 k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t *__restrict__ blob, uint8_t *__restrict__ cat) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
-  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K1_BAR);   // [2]
-  uint64_t *bar_empty = bar_full + 2;                               // [2]
+  uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + K1_BAR);   // [2] accumulators of a tile pair complete
+  uint64_t *bar_empty = bar_full + 2;                               // [2] ... read back by the 8 epilogue warps
   uint64_t *bar_w = bar_full + 4;
+  uint64_t *bar_pfull = bar_full + 5;                               // [2] conv64 planes / quadrant planes staged (3 staging warps)
+  uint64_t *bar_pfree = bar_full + 7;                               // [2] ... no longer read by the tensor core
   float *red = reinterpret_cast<float *>(sm + K1_RED);              // [2][8 warps][16]
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,89 +142,103 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
     mbar_init(&bar_empty[0], 8); mbar_init(&bar_empty[1], 8);
     mbar_init(bar_w, 1);
+    mbar_init(&bar_pfull[0], K1_STAGE_THREADS / 32); mbar_init(&bar_pfull[1], K1_STAGE_THREADS / 32);
+    mbar_init(&bar_pfree[0], 1); mbar_init(&bar_pfree[1], 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);
-  for (int i = tid; i < (2 * P64_BYTES + 8 * P1_BYTES) / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm + K1_P64)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == K1_MMA_WARP) tmem_alloc(&tmem_slot, 512);
+  for (int i = tid; i < (2 * P64_BYTES + 8 * P1_BYTES) / 16; i += K1_THREADS) reinterpret_cast<uint4 *>(sm + K1_P64)[i] = make_uint4(0, 0, 0, 0);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = tmem_slot;
-  if (warp == 8 && elect_one()) {
+  if (warp == K1_MMA_WARP && elect_one()) {
     mbar_expect_tx(bar_w, SZ_L1W);
     for (int i = 0; i < 24; i++) bulk_g2s(sm + K1_W + i * 4096, blob + OFF_L1W + i * 4096, 4096, bar_w);
   }
   const uint32_t idesc = idesc_bf16(128, 128);
-  uint32_t npair = 0;   // running count of tile pairs (same sequence in every role)
-
-  // raw samples of the next CTU, fetched one CTU ahead so the HBM/L2 latency hides behind the epilogue
-  uint32_t pf_y[4] = {0, 0, 0, 0}, pf_u[4] = {0, 0, 0, 0}, pf_v[4] = {0, 0, 0, 0};
   const int total = geo.nctu * fb.n;            // CTUs of all frames of this launch
-  auto prefetch_ctu = [&](int cg) {
-    const int f = cg / geo.nctu, c = cg - f * geo.nctu;
-    const uint8_t *__restrict__ Y = fb.Y[f], *__restrict__ U = fb.U[f], *__restrict__ V = fb.V[f];
-    const int cx = c % geo.ctu_w, cy = c / geo.ctu_w;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int it = tid + 256 * k, y = it >> 4, x4 = (it & 15) * 4;
-      const int gy = cy * 64 + y, gx = cx * 64 + x4;
-      pf_y[k] = 0; pf_u[k] = 0; pf_v[k] = 0;
-      if (gy < geo.H && gx < geo.W) {             // W is a multiple of 8: 4 pixels are in or out together
-        pf_y[k] = __ldg(reinterpret_cast<const uint32_t *>(Y + (size_t)gy * pitch + gx));
-        pf_u[k] = __ldg(reinterpret_cast<const uint16_t *>(U + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
-        pf_v[k] = __ldg(reinterpret_cast<const uint16_t *>(V + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
-      }
-    }
-  };
   pdl_wait();                                   // prologue done; from here on global memory of the frame is touched
   const long long trace_t0 = clock64(); (void)trace_t0;
-  if (warp < 8 && (int)blockIdx.x < total) prefetch_ctu(blockIdx.x);
 
-  for (int ctu = blockIdx.x; ctu < total; ctu += gridDim.x) {
-    const int ctu_l = ctu % geo.nctu;           // CTU address inside its frame
-    const int ctu_x = ctu_l % geo.ctu_w, ctu_y = ctu_l / geo.ctu_w;
-    // ---- staging: (R,G) and (B,0) planes of the CTU and of its four zero-padded quadrants ----
-    if (warp < 8) {
+  if (warp > K1_MMA_WARP) {
+    // ---- staging: (R,G) and (B,0) planes of the CTU and of its four zero-padded quadrants ----------
+    const int stid = tid - (K1_MMA_WARP + 1) * 32;
+    uint32_t j = 0;                               // CTUs done by this CTA
+#pragma unroll 1
+    for (int ctu = blockIdx.x; ctu < total; ctu += gridDim.x, j++) {
+      const int f = ctu / geo.nctu, ctu_l = ctu - f * geo.nctu;
+      const uint8_t *__restrict__ Y = fb.Y[f], *__restrict__ U = fb.U[f], *__restrict__ V = fb.V[f];
+      const int ctu_x = ctu_l % geo.ctu_w, ctu_y = ctu_l / geo.ctu_w;
+      uint32_t yv[K1_STAGE_ITERS], uv[K1_STAGE_ITERS], vv[K1_STAGE_ITERS];
 #pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        const int it = tid + 256 * kk;
-        const int y = it >> 4, x4 = (it & 15) * 4;
+      for (int k = 0; k < K1_STAGE_ITERS; k++) {  // raw samples first: the loads fly while the planes are still being read
+        const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
         const int gy = ctu_y * 64 + y, gx = ctu_x * 64 + x4;
-        const uint32_t yv = pf_y[kk], uv = pf_u[kk], vv = pf_v[kk];
-        const bool in = gy < geo.H && gx < geo.W;
-        uint32_t rg[4], b0[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          int r = 0, g = 0, b = 0;
-          if (in) yuv2rgb((yv >> (8 * k)) & 255, (uv >> (8 * (k >> 1))) & 255, (vv >> (8 * (k >> 1))) & 255, r, g, b);
-          rg[k] = pack_bf16((float)r, (float)g);
-          b0[k] = pack_bf16((float)b, 0.f);
+        yv[k] = 0; uv[k] = 0; vv[k] = 0;
+        if (it < 1024 && gy < geo.H && gx < geo.W) {   // W is a multiple of 8: 4 pixels are in or out together
+          yv[k] = __ldg(reinterpret_cast<const uint32_t *>(Y + (size_t)gy * pitch + gx));
+          uv[k] = __ldg(reinterpret_cast<const uint16_t *>(U + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
+          vv[k] = __ldg(reinterpret_cast<const uint16_t *>(V + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
         }
-        uint8_t *d64 = sm + K1_P64 + ((y + 2) * P64_PITCH + x4 + 2) * 4;
-        *reinterpret_cast<uint2 *>(d64) = make_uint2(rg[0], rg[1]);
-        *reinterpret_cast<uint2 *>(d64 + 8) = make_uint2(rg[2], rg[3]);
-        *reinterpret_cast<uint2 *>(d64 + P64_BYTES) = make_uint2(b0[0], b0[1]);
-        *reinterpret_cast<uint2 *>(d64 + P64_BYTES + 8) = make_uint2(b0[2], b0[3]);
-        const int q = (y >> 5) * 2 + (x4 >> 5);
-        uint8_t *d1 = sm + K1_P1 + q * 2 * P1_BYTES + (((y & 31) + 2) * P1_PITCH + (x4 & 31) + 2) * 4;
-        *reinterpret_cast<uint2 *>(d1) = make_uint2(rg[0], rg[1]);
-        *reinterpret_cast<uint2 *>(d1 + 8) = make_uint2(rg[2], rg[3]);
-        *reinterpret_cast<uint2 *>(d1 + P1_BYTES) = make_uint2(b0[0], b0[1]);
-        *reinterpret_cast<uint2 *>(d1 + P1_BYTES + 8) = make_uint2(b0[2], b0[3]);
+      }
+      uint32_t rg[K1_STAGE_ITERS][4], b0[K1_STAGE_ITERS][4];
+#pragma unroll
+      for (int k = 0; k < K1_STAGE_ITERS; k++) {
+        const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
+        const bool in = it < 1024 && ctu_y * 64 + y < geo.H && ctu_x * 64 + x4 < geo.W;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          int r = 0, g = 0, b = 0;
+          if (in) yuv2rgb((yv[k] >> (8 * i)) & 255, (uv[k] >> (8 * (i >> 1))) & 255, (vv[k] >> (8 * (i >> 1))) & 255, r, g, b);
+          rg[k][i] = pack_bf16((float)r, (float)g);
+          b0[k][i] = pack_bf16((float)b, 0.f);
+        }
+      }
+      if (j) MBAR_WAIT(&bar_pfree[0], (j - 1) & 1, 3);
+#pragma unroll
+      for (int k = 0; k < K1_STAGE_ITERS; k++) {
+        const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
+        if (it < 1024) {
+          uint8_t *d64 = sm + K1_P64 + ((y + 2) * P64_PITCH + x4 + 2) * 4;
+          *reinterpret_cast<uint2 *>(d64) = make_uint2(rg[k][0], rg[k][1]);
+          *reinterpret_cast<uint2 *>(d64 + 8) = make_uint2(rg[k][2], rg[k][3]);
+          *reinterpret_cast<uint2 *>(d64 + P64_BYTES) = make_uint2(b0[k][0], b0[k][1]);
+          *reinterpret_cast<uint2 *>(d64 + P64_BYTES + 8) = make_uint2(b0[k][2], b0[k][3]);
+        }
       }
       fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_pfull[0]);
+      if (j) MBAR_WAIT(&bar_pfree[1], (j - 1) & 1, 4);
+#pragma unroll
+      for (int k = 0; k < K1_STAGE_ITERS; k++) {
+        const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
+        if (it < 1024) {
+          const int q = (y >> 5) * 2 + (x4 >> 5);
+          uint8_t *d1 = sm + K1_P1 + q * 2 * P1_BYTES + (((y & 31) + 2) * P1_PITCH + (x4 & 31) + 2) * 4;
+          *reinterpret_cast<uint2 *>(d1) = make_uint2(rg[k][0], rg[k][1]);
+          *reinterpret_cast<uint2 *>(d1 + 8) = make_uint2(rg[k][2], rg[k][3]);
+          *reinterpret_cast<uint2 *>(d1 + P1_BYTES) = make_uint2(b0[k][0], b0[k][1]);
+          *reinterpret_cast<uint2 *>(d1 + P1_BYTES + 8) = make_uint2(b0[k][2], b0[k][3]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_pfull[1]);
     }
-    __syncthreads();
-    if (warp < 8 && ctu + (int)gridDim.x < total) prefetch_ctu(ctu + gridDim.x);
-
-    if (warp == 8) {
-      // ---- MMA issue: 4 tile pairs (conv64 quarters 0-1, 2-3; conv1 quadrants 0-1, 2-3) ----------
-      if (elect_one()) {
-        MBAR_WAIT(bar_w, 0, 0);
-        const uint32_t sb = smem_u32(sm);
+  } else if (warp == K1_MMA_WARP) {
+    // ---- MMA issue: 4 tile pairs per CTU (conv64 quarters 0-1, 2-3; conv1 quadrants 0-1, 2-3) --------
+    if (elect_one()) {
+      MBAR_WAIT(bar_w, 0, 0);
+      const uint32_t sb = smem_u32(sm);
+      uint32_t j = 0, npair = 0;                  // CTUs done, running count of tile pairs (same sequence in the epilogue)
+#pragma unroll 1
+      for (int ctu = blockIdx.x; ctu < total; ctu += gridDim.x, j++, npair += 4) {
 #pragma unroll 1
         for (int pi = 0; pi < 4; pi++) {
           const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
+          if ((pi & 1) == 0) MBAR_WAIT(&bar_pfull[pi >> 1], j & 1, 5);
           MBAR_WAIT(&bar_empty[p], (use & 1) ^ 1, 1);
           fence_after_sync();
           const bool c1 = pi >= 2;
@@ -241,19 +263,23 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
             mma_bf16_ss(d1, da1 + aofs, db + bofs, idesc, kb ? 1u : 0u);
           }
           mma_commit(&bar_full[p]);
+          if (pi & 1) mma_commit(&bar_pfree[pi >> 1]);   // the planes this half of the CTU read may be overwritten
         }
       }
-      __syncwarp();
-    } else {
-      // ---- epilogue: warp = (lane quarter, channel half) ---------------------------------------
-      const int lq = warp & 3, h = warp >> 2;
-      const int m = lq * 32 + lane, g = m >> 3, ii = m & 7;
-      const float g64r = __ldg(fp + F_G64 + 8 * h + (lane & 7)), b64r = __ldg(fp + F_B64 + 8 * h + (lane & 7));
-      const float g1r = __ldg(fp + F_G1 + 8 * h + (lane & 7)), b1r = __ldg(fp + F_B1 + 8 * h + (lane & 7));
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: warp = (lane quarter, channel half) -------------------------------------------
+    const int lq = warp & 3, h = warp >> 2;
+    const int m = lq * 32 + lane, g = m >> 3, ii = m & 7;
+    const float g64r = __ldg(fp + F_G64 + 8 * h + (lane & 7)), b64r = __ldg(fp + F_B64 + 8 * h + (lane & 7));
+    const float g1r = __ldg(fp + F_G1 + 8 * h + (lane & 7)), b1r = __ldg(fp + F_B1 + 8 * h + (lane & 7));
+    uint32_t rb = 0, npair = 0;
+#pragma unroll 1
+    for (int ctu = blockIdx.x; ctu < total; ctu += gridDim.x, npair += 4) {
       float s[8], q[8], pool64[4][8];
 #pragma unroll
       for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
-      uint32_t rb = 0;
 #pragma unroll 1
       for (int pi = 0; pi < 4; pi++) {
         const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
@@ -348,8 +374,6 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
         }
       }
     }
-    npair += 4;
-    __syncthreads();   // every MMA of this CTU has completed (the epilogue saw all four commits): planes are reusable
   }
   fence_before_sync();
   __syncthreads();
@@ -969,7 +993,7 @@ inline int tc_launch(const TcParams &p, const FrameBatch &fb, FrameGeom g, int p
   gt.nctu = g.nctu * fb.n;
   const int grid = gt.nctu < num_sms ? gt.nctu : num_sms;
   const int npad = ((4 * gt.nctu + 127) / 128) * 128;   // <= p.npad (sized for the largest batch); the feats layout follows the launch
-  tc_launch_pdl(k_tc_l1, grid, TC_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat);
+  tc_launch_pdl(k_tc_l1, grid, K1_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat);
   tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2);
   tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad);
   if (npad / FcSmall::NT > num_sms)             // more 32-sample tiles than SMs: 64-sample tiles halve the weight traffic
