@@ -668,30 +668,10 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
         __syncwarp();
         tbase = Wp.tab + n;
       }
-      // slabs: two horizontally adjacent 8x8 blocks each
-#pragma unroll 2
-      for (int sl = 0; sl < spm; sl++) {
-        const int by8 = (sl >> (lgnb - 1)) * 8, bx8 = ((2 * sl) & ((1 << lgnb) - 1)) * 8;
-        const uint8_t *op = o + by8 * ORG_P + bx8;
-        const uint32_t oa = *reinterpret_cast<const uint16_t *>(op), ob = *reinterpret_cast<const uint16_t *>(op + 8);
-        uint32_t Pa, Pb;
-        if (!slow) {
-          const int pos = (j0 + by8 + 1) * angle, di = pos >> 5, df = pos & 31;   // shared by the row of blocks
-          const uint32_t *tp = tbase + (i0 + bx8 + di + 1);
-          const uint32_t w0 = 32 - df;
-          Pa = ((w0 * tp[0] + df * tp[1] + 0x00100010u) >> 5) & 0x07FF07FFu;
-          Pb = ((w0 * tp[8] + df * tp[9] + 0x00100010u) >> 5) & 0x07FF07FFu;
-        } else if (mode < 2) {
-          Pa = predict_pair(c, S.line[0] + 2 * n, n, lg, mode, (rx0 + 2 * t) + bx8, (ry0 + g) + by8, dc);
-          Pb = predict_pair(c, S.line[0] + 2 * n, n, lg, mode, (rx0 + 2 * t) + bx8 + 8, (ry0 + g) + by8, dc);
-        } else {                                // pure H/V (angle 0, no interpolation) with the edge filter (n <= 16)
-          const int i = i0 + bx8, j = j0 + by8;
-          Pa = tbase[i + 1]; Pb = tbase[i + 9];
-          if (i == 0) {
-            const int p0 = clip255((int)(Pa & 0xFFFF) + ((c[-sg * (j + 1)] - c[0]) >> 1));
-            Pa = (Pa & 0xFFFF0000u) | (uint32_t)p0;
-          }
-        }
+      // slabs: two horizontally adjacent 8x8 blocks each, row of blocks by row of blocks.  The interpolation position
+      // depends on the row only; the common angular case gets its own loop so that nothing is decided per slab.
+      constexpr int spr = rs / 16;              // slabs per row of blocks
+      auto finish = [&](int slab, uint32_t oa, uint32_t ob, uint32_t Pa, uint32_t Pb) {
         // residuals as exact half2 (fp16 1024+v on both sides)
         const uint32_t Oa = __byte_perm(oa, 0x64u, 0x4140), Ob = __byte_perm(ob, 0x64u, 0x4140);
         Pa |= 0x64006400u; Pb |= 0x64006400u;
@@ -700,9 +680,47 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
         float c1[4], c2[4];
         mma_f16_16816(c1, a8, 0u, 0u, a8, *reinterpret_cast<const uint32_t *>(&da), *reinterpret_cast<const uint32_t *>(&db));
         mma_f16_16816(c2, a8, 0u, 0u, a8, pack_h2(c1[0], c1[1]), pack_h2(c1[2], c1[3]));
-        float *rr = &Wp.red[(mi * spm + sl) * 2][lane];
+        float *rr = &Wp.red[slab * 2][lane];
         rr[0] = fabsf(c2[0]) + fabsf(c2[1]);
         rr[RED_P] = fabsf(c2[2]) + fabsf(c2[3]);
+      };
+      if (!slow) {
+        const uint32_t *trow = tbase + (i0 + 1);
+        int pos = (j0 + 1) * angle;
+#pragma unroll RS == 32 ? 1 : 2
+        for (int by = 0; by < rs / 8; by++, pos += 8 * angle) {
+          const int di = pos >> 5, df = pos & 31;
+          const uint32_t *tp = trow + di;
+          const uint8_t *op = o + by * 8 * ORG_P;
+          const uint32_t w0 = 32 - df;
+#pragma unroll
+          for (int bx = 0; bx < spr; bx++) {
+            const uint32_t oa = *reinterpret_cast<const uint16_t *>(op + 16 * bx), ob = *reinterpret_cast<const uint16_t *>(op + 16 * bx + 8);
+            const uint32_t Pa = ((w0 * tp[16 * bx] + df * tp[16 * bx + 1] + 0x00100010u) >> 5) & 0x07FF07FFu;
+            const uint32_t Pb = ((w0 * tp[16 * bx + 8] + df * tp[16 * bx + 9] + 0x00100010u) >> 5) & 0x07FF07FFu;
+            finish(mi * spm + by * spr + bx, oa, ob, Pa, Pb);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int sl = 0; sl < spm; sl++) {
+          const int by8 = (sl >> (lgnb - 1)) * 8, bx8 = ((2 * sl) & ((1 << lgnb) - 1)) * 8;
+          const uint8_t *op = o + by8 * ORG_P + bx8;
+          const uint32_t oa = *reinterpret_cast<const uint16_t *>(op), ob = *reinterpret_cast<const uint16_t *>(op + 8);
+          uint32_t Pa, Pb;
+          if (mode < 2) {
+            Pa = predict_pair(c, S.line[0] + 2 * n, n, lg, mode, (rx0 + 2 * t) + bx8, (ry0 + g) + by8, dc);
+            Pb = predict_pair(c, S.line[0] + 2 * n, n, lg, mode, (rx0 + 2 * t) + bx8 + 8, (ry0 + g) + by8, dc);
+          } else {                              // pure H/V (angle 0, no interpolation) with the edge filter (n <= 16)
+            const int i = i0 + bx8, j = j0 + by8;
+            Pa = tbase[i + 1]; Pb = tbase[i + 9];
+            if (i == 0) {
+              const int p0 = clip255((int)(Pa & 0xFFFF) + ((c[-sg * (j + 1)] - c[0]) >> 1));
+              Pa = (Pa & 0xFFFF0000u) | (uint32_t)p0;
+            }
+          }
+          finish(mi * spm + sl, oa, ob, Pa, Pb);
+        }
       }
     }
     __syncwarp();
