@@ -209,7 +209,7 @@ __device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
 
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                               uint32_t b1) {
-  asm volatile(
+  asm(  // not volatile: a pure function of its operands, so the compiler may interleave the chains of neighbouring slabs
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
       : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
@@ -670,7 +670,6 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
       }
       // slabs: two horizontally adjacent 8x8 blocks each, row of blocks by row of blocks.  The interpolation position
       // depends on the row only; the common angular case gets its own loop so that nothing is decided per slab.
-      constexpr int spr = rs / 16;              // slabs per row of blocks
       auto finish = [&](int slab, uint32_t oa, uint32_t ob, uint32_t Pa, uint32_t Pb) {
         // residuals as exact half2 (fp16 1024+v on both sides)
         const uint32_t Oa = __byte_perm(oa, 0x64u, 0x4140), Ob = __byte_perm(ob, 0x64u, 0x4140);
@@ -685,20 +684,28 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
         rr[RED_P] = fabsf(c2[2]) + fabsf(c2[3]);
       };
       if (!slow) {
+        // two slabs at a time (32: one row of blocks, 16: both rows): all shared-memory loads of the pair are issued
+        // before the first slab's stores, so the two dependent chains (loads, interpolation, two MMAs) overlap
         const uint32_t *trow = tbase + (i0 + 1);
-        int pos = (j0 + 1) * angle;
-#pragma unroll RS == 32 ? 1 : 2
-        for (int by = 0; by < rs / 8; by++, pos += 8 * angle) {
-          const int di = pos >> 5, df = pos & 31;
-          const uint32_t *tp = trow + di;
-          const uint8_t *op = o + by * 8 * ORG_P;
-          const uint32_t w0 = 32 - df;
+#pragma unroll 1
+        for (int pr = 0; pr < spm / 2; pr++) {
+          uint32_t oa[2], ob[2], ta[2][2], tb[2][2], dfv[2];
 #pragma unroll
-          for (int bx = 0; bx < spr; bx++) {
-            const uint32_t oa = *reinterpret_cast<const uint16_t *>(op + 16 * bx), ob = *reinterpret_cast<const uint16_t *>(op + 16 * bx + 8);
-            const uint32_t Pa = ((w0 * tp[16 * bx] + df * tp[16 * bx + 1] + 0x00100010u) >> 5) & 0x07FF07FFu;
-            const uint32_t Pb = ((w0 * tp[16 * bx + 8] + df * tp[16 * bx + 9] + 0x00100010u) >> 5) & 0x07FF07FFu;
-            finish(mi * spm + by * spr + bx, oa, ob, Pa, Pb);
+          for (int h = 0; h < 2; h++) {
+            const int by = rs == 32 ? pr : h, bx = rs == 32 ? h : 0;
+            const int pos = (j0 + 1 + 8 * by) * angle, di = pos >> 5;
+            dfv[h] = pos & 31;
+            const uint32_t *tp = trow + di + 16 * bx;
+            const uint8_t *op = o + by * 8 * ORG_P + 16 * bx;
+            oa[h] = *reinterpret_cast<const uint16_t *>(op); ob[h] = *reinterpret_cast<const uint16_t *>(op + 8);
+            ta[h][0] = tp[0]; ta[h][1] = tp[1]; tb[h][0] = tp[8]; tb[h][1] = tp[9];
+          }
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const uint32_t df = dfv[h], w0 = 32 - df;
+            const uint32_t Pa = ((w0 * ta[h][0] + df * ta[h][1] + 0x00100010u) >> 5) & 0x07FF07FFu;
+            const uint32_t Pb = ((w0 * tb[h][0] + df * tb[h][1] + 0x00100010u) >> 5) & 0x07FF07FFu;
+            finish(mi * spm + 2 * pr + h, oa[h], ob[h], Pa, Pb);
           }
         }
       } else {
