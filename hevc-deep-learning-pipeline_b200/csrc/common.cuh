@@ -55,7 +55,7 @@ __host__ __device__ __forceinline__ void yuv2rgb(int y, int cb, int cr, int &r, 
 // Frames of one CNN launch.  All-intra frames are independent, so several frames of the same geometry can share a
 // launch: 510 CTUs of one 1080p frame leave 148 persistent CTAs with 3 or 4 CTUs each (86 % balance) and the fc
 // kernel with 64 CTAs; two frames give 6.9 -> 7 (98 %) and 128 CTAs.  Global CTU index g = frame * nctu + ctu.
-constexpr int MAX_BATCH = 4;
+constexpr int MAX_BATCH = 8;
 struct FrameBatch {
   const uint8_t *Y[MAX_BATCH], *U[MAX_BATCH], *V[MAX_BATCH];
   uint8_t *labels[MAX_BATCH];

@@ -173,7 +173,7 @@ class DepthPredictor:
         def arr(ptr, ctype, n, shape, dtype=None):
             if not ptr or n == 0:
                 return np.empty(shape, dtype or np.dtype(ctype))
-            key = (ptr, n, ctype)
+            key = (ptr, n, ctype, shape, dtype)     # pus and cand may alias by address across frames with different PU counts
             a = cache.get(key)
             if a is None:
                 if len(cache) > 4096:

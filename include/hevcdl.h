@@ -50,7 +50,7 @@ typedef struct {
   int32_t rmd;             /* 1: run the batched 35-mode SATD pass (K6) after the labels */
   int32_t boundary_fix;    /* 1: raise labels of picture-edge CTUs so partial CTUs tile (the
                               reference leaves them inconsistent); 0 = reference */
-  int32_t batch;           /* frames per CNN launch, 1..4 (0 = 1).  All-intra frames are independent; with batch > 1 the
+  int32_t batch;           /* frames per CNN launch, 1..8 (0 = 1).  All-intra frames are independent; with batch > 1 the
                               kernels of a frame start once `batch` frames have been submitted or when a pending frame is
                               asked for, whichever comes first.  Results do not depend on it.  Tensor-core path only. */
   const char *weights_path;/* HDLW blob made by tools/convert_weights.py */

@@ -197,12 +197,12 @@ def test_frame_view_is_the_same_bytes_as_the_copying_getters(built, host, pkg):
     dp2.release(0); dp.close(); dp2.close()
 
 
-@pytest.mark.parametrize("batch", [2, 3])
-def test_batched_launches_give_the_same_results(built, host, pkg, batch):
+@pytest.mark.parametrize("batch,nframes", [(2, 5), (3, 5), (8, 10)])
+def test_batched_launches_give_the_same_results(built, host, pkg, batch, nframes):
     """cfg.batch > 1: several frames share one CNN launch.  Frames are independent, so every output must be bit-identical
     to the batch=1 context -- including the odd frame whose batch never fills (launched when it is asked for)."""
     w, h = 416, 240
-    frames = [pkg.synth.synth_frame(w, h, 30 + i) for i in range(5)]
+    frames = [pkg.synth.synth_frame(w, h, 30 + i) for i in range(nframes)]
     ref = _mk(host, w, h, 1, rmd=True, slots=1)
     want = []
     for i, f in enumerate(frames):
@@ -211,16 +211,16 @@ def test_batched_launches_give_the_same_results(built, host, pkg, batch):
         want.append({k: v[k].copy() for k in v})
         ref.release(i)
     ref.close()
-    dp = _mk(host, w, h, 1, rmd=True, slots=6, batch=batch)
+    dp = _mk(host, w, h, 1, rmd=True, slots=nframes + 1, batch=batch)
     for i, f in enumerate(frames):
         dp.submit(100 + i, *f)
-    for i in (4, 0, 2, 1, 3):                                  # any order; frame 4 (or 3, 4) sits in an unfilled batch
+    for i in [nframes - 1] + [(7 * k) % (nframes - 1) for k in range(nframes - 1)]:   # any order; the last frame(s) sit in an unfilled batch
         v = dp.view(100 + i)
         for k in ("labels", "logits", "ctu_off", "pus", "satd", "cand"):
             assert (v[k] == want[i][k]).all(), (batch, i, k)
         dp.release(100 + i)
     st = dp.stats()
-    assert st["frames"] == 5
+    assert st["frames"] == nframes
     dp.close()
 
 
