@@ -137,6 +137,7 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
+  TL_BEGIN();
 
   if (tid == 0) {
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
@@ -159,6 +160,7 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
   const uint32_t idesc = idesc_bf16(128, 128);
   const int total = geo.nctu * fb.n;            // CTUs of all frames of this launch
   pdl_wait();                                   // prologue done; from here on global memory of the frame is touched
+  if (tid == 0) { TL_WAITED(); }
   const long long trace_t0 = clock64(); (void)trace_t0;
 
   if (warp > K1_MMA_WARP) {
@@ -378,6 +380,7 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
   fence_before_sync();
   __syncthreads();
   TRACE_TOTAL(16, trace_t0);
+  TL_END(1);
   if (warp == 8) tmem_dealloc(tbase, 512);
 }
 
@@ -406,6 +409,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
+  TL_BEGIN();
 
   if (tid == 0) {
     for (int i = 0; i < 4; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 16); }
@@ -425,6 +429,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
       mbar_expect_tx(bar_w, SZ_W2);
       for (int i = 0; i < 9; i++) bulk_g2s(sm + K2_W + i * 4096, blob + OFF_W2 + i * 4096, 4096, bar_w);
       pdl_wait();                               // the weights are on their way; cat is the predecessor's output
+      TL_WAITED();
       if ((int)blockIdx.x < geo.nctu) {
         mbar_expect_tx(&bar_cfull[0], CAT_BYTES);
         bulk_g2s(sm + K2_CAT, cat + (size_t)blockIdx.x * CAT_BYTES, CAT_BYTES, &bar_cfull[0]);
@@ -553,6 +558,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   fence_before_sync();
   __syncthreads();
   TRACE_TOTAL(17, trace_t0);
+  TL_END(2);
   if (warp == K2_MMA_WARP) tmem_dealloc(tbase, 512);
 }
 
@@ -577,6 +583,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
+  TL_BEGIN();
 
   if (tid == 0) {
     for (int i = 0; i < 2; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 8); }
@@ -596,6 +603,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
       mbar_expect_tx(bar_w, SZ_W3);
       for (int i = 0; i < 36; i++) bulk_g2s(sm + K3_W + i * 4096, blob + OFF_W3 + i * 4096, 4096, bar_w);
       pdl_wait();                               // a2 is the predecessor's output
+      TL_WAITED();
       if ((int)blockIdx.x < geo.nctu)
         for (int j = 0; j < 4; j++) {
           mbar_expect_tx(&bar_afull[j], 2 * A2_PLANE);
@@ -698,6 +706,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
   fence_before_sync();
   __syncthreads();
   TRACE_TOTAL(18, trace_t0);
+  TL_END(3);
   if (warp == 8) tmem_dealloc(tbase, 512);
 }
 
@@ -745,6 +754,7 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nt = blockIdx.x;   // sample tile
   pdl_launch_dependents();
+  TL_BEGIN();
 #ifdef HEVCDL_FC_TRACE
   long long tr[8];
 #define FC_TR(i) tr[i] = clock64()
@@ -782,6 +792,7 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
       for (int i = 0; i < 16; i++) bulk_g2s(sm + K4_FC2W + i * 4096, blob + OFF_FC2 + i * 4096, 4096, bar_w2);
       for (int kc = 0; kc < K4_NSTAGE; kc++) load_w(kc);
       pdl_wait();
+      TL_WAITED();
       for (int kc = 0; kc < K4_NSTAGE; kc++) load_f(kc);
 #pragma unroll 1
       for (int kc = 0; kc < 32; kc++) {
@@ -929,6 +940,7 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
     printf("fc trace blk %d: setup %lld loop %lld fc1epi %lld fc2 %lld fc2epi %lld fc3 %lld labels %lld total %lld clk\n", (int)blockIdx.x,
            tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[7] - tr[0]);
 #endif
+  TL_END(4);
   if (warp == 8) tmem_dealloc(tbase, 512);
 }
 

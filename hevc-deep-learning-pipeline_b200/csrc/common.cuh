@@ -34,6 +34,30 @@ struct Fp32Params {
 // (pdl_launch_dependents at entry) and runs its own prologue -- barrier init, TMEM allocation, weight loads --
 // before pdl_wait(), which returns once the predecessor grid has completed and its writes are visible.  Without
 // the launch attribute both are no-ops.
+// Tuning builds only (-DHEVCDL_TIMELINE): every CTA logs (kernel, block, entry, predecessor-wait passed, exit) in
+// %globaltimer nanoseconds; hevcdl_destroy writes the log to $HEVCDL_TIMELINE_OUT (tools/timeline.py reads it).
+#ifdef HEVCDL_TIMELINE
+constexpr unsigned TL_CAP = 1u << 18;
+__device__ unsigned long long g_tl[TL_CAP][4];
+__device__ unsigned g_tl_n;
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_BEGIN() __shared__ unsigned long long tl_s[2]; if (threadIdx.x == 0) tl_s[0] = tl_now()
+#define TL_WAITED() tl_s[1] = tl_now()
+#define TL_END(kid)                                                                   \
+  if (threadIdx.x == 0) {                                                              \
+    const unsigned i_ = atomicAdd(&g_tl_n, 1u);                                        \
+    if (i_ < TL_CAP) { g_tl[i_][0] = ((unsigned long long)(kid) << 32) | blockIdx.x; g_tl[i_][1] = tl_s[0]; g_tl[i_][2] = tl_s[1]; g_tl[i_][3] = tl_now(); } \
+  }
+#else
+#define TL_BEGIN()
+#define TL_WAITED()
+#define TL_END(kid)
+#endif
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -79,6 +79,7 @@ struct hevcdl_ctx {
   TcParams tc{};
   int numSMs = 0;
   int batch = 1;                       // frames per CNN launch (cfg.batch)
+  bool stageTimes = true;              // bracket the CNN / RMD stages of every launch with events (hevcdl_get_stats: ms_cnn, ms_rmd)
   std::vector<Slot *> pending;         // submitted frames waiting for their batch to fill
   int rmdBlocks = 0;                   // persistent grid of k_rmd_items: resident blocks per SM x SMs
   std::string err;
@@ -211,6 +212,14 @@ int ensure_host_pu_cap(hevcdl_ctx *ctx, Slot &s, size_t n) {
   return HEVCDL_OK;
 }
 
+// Order `st` behind `ev` -- unless the event has already completed: a wait node between two kernels costs front-end time
+// and keeps the next kernel's CTAs from starting in the shadow of its predecessor (programmatic dependent launch).
+static void wait_unless_done(cudaStream_t st, cudaEvent_t ev) {
+  if (cudaEventQuery(ev) == cudaSuccess) return;
+  cudaGetLastError();                             // cudaErrorNotReady is not an error
+  cudaStreamWaitEvent(st, ev, 0);
+}
+
 // Queue the device pipeline of n <= cfg.batch slots on ctx->stream: one CNN launch for all of them (tensor-core path),
 // then the RMD kernels per frame.  Returns kernels launched.
 int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
@@ -218,7 +227,7 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
   int launches = 0;
   Slot &head = *sl[0];
   if (ctx->rmd)
-    for (int i = 0; i < n; i++) cudaStreamWaitEvent(ctx->stream, sl[i]->evRmd, 0);   // a slot's earlier K6 (other stream) is done
+    for (int i = 0; i < n; i++) wait_unless_done(ctx->stream, sl[i]->evRmd);   // a slot's earlier K6 (other stream) is done
   if (timed) cudaEventRecord(head.evT0, ctx->stream);
   if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
     FrameBatch fb{};
@@ -271,13 +280,13 @@ int flush_pending(hevcdl_ctx *ctx) {
   const int n = (int)ctx->pending.size();
   if (n == 0) return HEVCDL_OK;
   const FrameGeom &g = ctx->geo;
-  for (Slot *s : ctx->pending) CK(cudaStreamWaitEvent(ctx->stream, s->evIn, 0));
-  ctx->stats.kernel_launches += launch_pipeline(ctx, ctx->pending.data(), n, true);
+  for (Slot *s : ctx->pending) wait_unless_done(ctx->stream, s->evIn);
+  ctx->stats.kernel_launches += launch_pipeline(ctx, ctx->pending.data(), n, ctx->stageTimes);
   CK(cudaGetLastError());
   for (int i = 0; i < n; i++) {
     Slot *s = ctx->pending[i];
     s->state = SLOT_QUEUED;
-    s->timed = i == 0;
+    s->timed = ctx->stageTimes && i == 0;
     CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
     CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->d2h));
     CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
@@ -420,6 +429,8 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   ctx->batch = cfg->batch < 1 ? 1 : (cfg->batch > MAX_BATCH ? MAX_BATCH : cfg->batch);
   if (ctx->batch > ctx->cfg.slots) ctx->batch = ctx->cfg.slots;
   if (cfg->precision != HEVCDL_PREC_BF16_TC) ctx->batch = 1;   // the fp32 parity path launches per frame
+  // throughput mode: no timing events between the launches of consecutive batches unless asked for
+  ctx->stageTimes = ctx->batch == 1 || getenv("HEVCDL_STAGE_TIMES") != nullptr;
   std::string wp = cfg->weights_path;
   auto fail = [&](int rc) { g_create_err = ctx->err; hevcdl_destroy(ctx); return rc; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(HEVCDL_E_CUDA); }
@@ -467,6 +478,20 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
 void hevcdl_destroy(hevcdl_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+#ifdef HEVCDL_TIMELINE
+  if (const char *out = getenv("HEVCDL_TIMELINE_OUT")) {
+    cudaDeviceSynchronize();
+    unsigned n = 0;
+    cudaMemcpyFromSymbol(&n, g_tl_n, sizeof n);
+    if (n > TL_CAP) n = TL_CAP;
+    std::vector<unsigned long long> rec((size_t)n * 4);
+    if (n && cudaMemcpyFromSymbol(rec.data(), g_tl, rec.size() * 8) == cudaSuccess) {
+      if (FILE *f = fopen(out, "wb")) { fwrite(rec.data(), 8, rec.size(), f); fclose(f); }
+    }
+    n = 0;
+    cudaMemcpyToSymbol(g_tl_n, &n, sizeof n);
+  }
+#endif
 #ifdef HEVCDL_TRACE
   {
     cudaDeviceSynchronize();

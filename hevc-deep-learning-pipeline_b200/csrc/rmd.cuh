@@ -373,7 +373,9 @@ __global__ void __launch_bounds__(256)
 k_rmd_plan(const RmdBatch rb, FrameGeom geo, int items_grid, RmdItem *__restrict__ items, int *__restrict__ ctrl) {
   const int lane = threadIdx.x & 31, gctu = blockIdx.x * 8 + (threadIdx.x >> 5);
   pdl_launch_dependents();
+  TL_BEGIN();
   pdl_wait();
+  if (threadIdx.x == 0) { TL_WAITED(); }
   if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = items_grid;
   const int total = geo.nctu * rb.n;
   if (gctu >= total) return;
@@ -462,6 +464,7 @@ k_rmd_plan(const RmdBatch rb, FrameGeom geo, int items_grid, RmdItem *__restrict
     it_big += __shfl_sync(0xffffffffu, sb, 31);
     it_small += __shfl_sync(0xffffffffu, ss, 31);
   }
+  TL_END(5);
 }
 
 // Test hook support: per-CTU counts for labels that did not come from the CNN kernels (which write them themselves).
@@ -879,7 +882,9 @@ k_rmd_items(const RmdBatch rb, FrameGeom geo, int pitch, const RmdItem *__restri
     a4 = on ? (((__popc((g & 3) & (c0 & 3)) & 1) ? neg : one) | (((__popc((g & 3) & (c1 & 3)) & 1) ? neg : one) << 16)) : 0u;
   }
   pdl_launch_dependents();
+  TL_BEGIN();
   pdl_wait();
+  if (threadIdx.x == 0) { TL_WAITED(); }
   const int nitems = ctrl[1];
   int it = blockIdx.x;                          // first round is static: k_rmd_plan started the counter at gridDim.x
   while (it < nitems) {
@@ -898,6 +903,7 @@ k_rmd_items(const RmdBatch rb, FrameGeom geo, int pitch, const RmdItem *__restri
     __syncthreads();                            // also: every warp is done with the item's shared memory
     it = S.next_item;
   }
+  TL_END(6);
 }
 
 // ---- exact mode: explicit original blocks, reference lines and mode bits ----------------------
