@@ -66,7 +66,8 @@ typedef struct {
 
 typedef struct {
   uint64_t frames, ctus, pus;
-  double ms_cnn, ms_rmd;   /* device time (CUDA events) accumulated over frames */
+  double ms_cnn, ms_rmd;   /* device time (CUDA events) accumulated over frames; recorded with batch == 1, or with any
+                              batch when HEVCDL_STAGE_TIMES is set in the environment (the events cost throughput) */
   uint64_t kernel_launches;
 } hevcdl_stats_t;
 
