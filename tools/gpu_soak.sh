@@ -13,26 +13,27 @@ want = []
 for i, f in enumerate(frames):
     ref.submit(i, *f); v = ref.view(i); want.append({k: v[k].copy() for k in v}); ref.release(i)
 ref.close()
-dp = host.DepthPredictor(w, h, precision=1, rmd=True, slots=8, batch=2)
-t0 = time.time(); n = 0; bad = 0
-inflight = []
-for it in range(600):
-    i = it % len(frames)
-    dp.submit(it, *frames[i]); inflight.append((it, i))
-    if len(inflight) >= 6:
-        fid, fi = inflight.pop(0)
+for batch, slots, depth in ((2, 8, 6), (4, 13, 11), (8, 25, 21)):     # depths that are no multiple of the batch: partial batches get flushed
+    dp = host.DepthPredictor(w, h, precision=1, rmd=True, slots=slots, batch=batch)
+    t0 = time.time(); n = 0; bad = 0
+    inflight = []
+    for it in range(600):
+        i = it % len(frames)
+        dp.submit(it, *frames[i]); inflight.append((it, i))
+        if len(inflight) >= depth:
+            fid, fi = inflight.pop(0)
+            v = dp.view(fid)
+            for k in ("labels", "ctu_off", "pus", "satd", "cand"):
+                if not (v[k] == want[fi][k]).all(): bad += 1
+            dp.release(fid); n += 1
+    for fid, fi in inflight:
         v = dp.view(fid)
         for k in ("labels", "ctu_off", "pus", "satd", "cand"):
             if not (v[k] == want[fi][k]).all(): bad += 1
         dp.release(fid); n += 1
-for fid, fi in inflight:
-    v = dp.view(fid)
-    for k in ("labels", "ctu_off", "pus", "satd", "cand"):
-        if not (v[k] == want[fi][k]).all(): bad += 1
-    dp.release(fid); n += 1
-print("soak: %d frames, %d mismatching arrays, %.1f s, stats %s" % (n, bad, time.time() - t0, dp.stats()))
-dp.close()
-assert bad == 0
+    print("soak batch %d: %d frames, %d mismatching arrays, %.1f s, stats %s" % (batch, n, bad, time.time() - t0, dp.stats()))
+    dp.close()
+    assert bad == 0
 PY
 python - <<'PY' 2>&1 | tee -a gpurun_out/soak.log
 import importlib, sys, os, tempfile
