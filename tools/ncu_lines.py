@@ -44,7 +44,9 @@ def main():
                     a["stall"][k[6:]] += int(v)
     ti = sum(a["inst"] for a in agg.values()) or 1
     ts = sum(a["samp"] for a in agg.values()) or 1
-    print("kernel %s: %d warp instructions, %d samples" % (kern, ti, ts))
+    # the source page lists an instruction under every line of its inline stack, so this total is inclusive (it exceeds
+    # smsp__inst_executed.sum); the per-line percentages are relative to it
+    print("kernel %s: %d warp instructions (inclusive over inlined lines), %d samples" % (kern, ti, ts))
     tot = defaultdict(int)
     for a in agg.values():
         for k, v in a["stall"].items():
