@@ -19,11 +19,11 @@ namespace hevcdl {
 
 constexpr int MAX_PU_CTU = 320;                 // 64 8x8 CUs x (1 + 4 NxN PUs)
 
-__device__ __forceinline__ int zidx4(int ux, int uy) {   // z-order of a 4x4 unit in a CTU (TComRom.cpp:284)
-  int z = 0;
-#pragma unroll
-  for (int b = 0; b < 4; b++) z |= (((ux >> b) & 1) << (2 * b)) | (((uy >> b) & 1) << (2 * b + 1));
-  return z;
+__device__ __forceinline__ int zidx4(int ux, int uy) {   // z-order of a 4x4 unit in a CTU (TComRom.cpp:284); ux, uy in [0,16)
+  uint32_t v = (uint32_t)ux | ((uint32_t)uy << 8);       // both coordinates spread at once, one per byte
+  v = (v | (v << 2)) & 0x3333u;
+  v = (v | (v << 1)) & 0x5555u;
+  return (int)((v | (v >> 7)) & 0xFFu);                  // x bits on even positions, y bits on odd ones
 }
 
 // Neighbour unit available iff inside the picture and earlier in coding order (CTU raster, then
@@ -276,6 +276,29 @@ __device__ __constant__ int8_t c_mode_angle[35] = {0, 0, 32, 26, 21, 17, 13, 9, 
                                                    -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
 __device__ __constant__ int16_t c_mode_inv[35] = {0, 0, 256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315,
                                                   256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+
+// What block_large needs to know about (PU size, mode), one word: bit 0 filtered references (TComPattern.cpp:545-570),
+// bit 1 horizontal class (modes 2..17), bit 2 not served by the table interpolation (planar, DC, pure H/V with the edge
+// filter), bit 3 negative angle; bits 8..15 the angle, bits 16..31 the inverse angle.  Index 0/1/2 = PU size 16/32/64.
+struct ModeInfoTab { uint32_t v[3][35]; };
+__host__ __device__ constexpr ModeInfoTab make_mode_info() {
+  ModeInfoTab t{};
+  constexpr int ang[35] = {0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26,
+                           -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
+  constexpr int inv[35] = {0, 0, 256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315,
+                           256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+  for (int si = 0; si < 3; si++) {
+    const int n = 16 << si;
+    const unsigned long long fm = mode_filter_mask(n);
+    for (int m = 0; m < 35; m++) {
+      const uint32_t flt = (uint32_t)((fm >> m) & 1ull), hor = (m >= 2 && m < 18) ? 1u : 0u;
+      const uint32_t slow = (m < 2 || (ang[m] == 0 && n <= 16)) ? 1u : 0u, neg = ang[m] < 0 ? 1u : 0u;
+      t.v[si][m] = flt | (hor << 1) | (slow << 2) | (neg << 3) | (((uint32_t)ang[m] & 0xFFu) << 8) | ((uint32_t)inv[m] << 16);
+    }
+  }
+  return t;
+}
+__device__ __constant__ ModeInfoTab c_mode_info = make_mode_info();
 
 // Everything about (PU, mode) that does not depend on the pixel: computed once per work item.
 struct ModeK {
@@ -589,7 +612,7 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
   constexpr int lgnb = rs == 32 ? 2 : 1;        // log2(8x8 blocks per region row)
   constexpr int spm = rs == 32 ? 8 : 2;         // slabs per mode; a reduction group is up to 8 slabs = 16 blocks
   constexpr int ngroups = rs == 32 ? 35 : 11;   // 32: one mode per group; 16: eight groups of 4 modes, then 32, 33, 34 alone
-  const unsigned long long fmask = n == 16 ? mode_filter_mask(16) : (n == 32 ? mode_filter_mask(32) : 0ull);
+  const uint32_t *__restrict__ minfo = c_mode_info.v[n == 16 ? 0 : (n == 32 ? 1 : 2)];
   const int rx0 = n == 64 ? (item.quad & 1) * 32 : 0, ry0 = n == 64 ? (item.quad >> 1) * 32 : 0;
   const int g = lane >> 2, t = lane & 3;
   const bool has_flt = n == 16 || n == 32;
@@ -646,15 +669,16 @@ __device__ __forceinline__ void block_large(RmdBlockS &S, const uint8_t *__restr
     const int nm = rs == 32 ? 1 : (q < 8 ? 4 : 1);
     for (int mi = 0; mi < nm; mi++) {
       const int mode = mfirst + mi;
-      const bool flt = (fmask >> mode) & 1ull, hor = mode >= 2 && mode < 18;
+      const uint32_t info = minfo[mode];
+      const bool flt = info & 1u, hor = info & 2u;
       const int16_t *c = S.line[flt ? 1 : 0] + 2 * n;
-      const int angle = c_mode_angle[mode], sg = hor ? -1 : 1;
+      const int angle = (int)(int8_t)(info >> 8), sg = hor ? -1 : 1;
       const uint8_t *o = (hor ? S.orgT : S.org) + g * ORG_P + 2 * t;
       const int i0 = (hor ? ry0 : rx0) + 2 * t, j0 = (hor ? rx0 : ry0) + g;
-      const bool slow = mode < 2 || (angle == 0 && n <= 16);
-      const uint32_t *tbase = S.ptab[(hor ? 2 : 0) + (flt ? 1 : 0)];
-      if (angle < 0) {                          // projected side samples in front of the main array
-        const int inv = c_mode_inv[mode];
+      const bool slow = info & 4u;
+      const uint32_t *tbase = S.ptab[((info >> 1) & 1u) * 2 + (info & 1u)];
+      if (info & 8u) {                          // negative angle: projected side samples in front of the main array
+        const int inv = (int)(info >> 16);
         const int kmin = ((n * angle) >> 5) + 1;
         __syncwarp();                           // readers of the previous table are done
         for (int k = kmin + lane; k <= n; k += 32) {
