@@ -482,6 +482,7 @@ k_tc_conv2(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
     }
     __syncwarp();
   } else {
+    pdl_wait();                                   // every warp that stores to global memory orders itself behind the predecessor grid (a2 is still read by the previous batch's K3)
     const int lq = warp & 3, cq = warp >> 2;      // TMEM lane quarter, group of 16 output channels
     const int m = lq * 32 + lane, yy = m >> 3, xi = m & 7;
     const float g2r = __ldg(fp + F_G2 + 16 * cq + (lane & 15)), b2r = __ldg(fp + F_B2 + 16 * cq + (lane & 15));
@@ -641,6 +642,7 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
     }
     __syncwarp();
   } else {
+    pdl_wait();                                   // feats is still read by the previous batch's K4: no store before the predecessor grid is complete
     const int lq = warp & 3, hy = warp >> 2;
     const int c = lq * 32 + lane;   // output channel
     uint32_t it = 0, rb = 0;
@@ -825,6 +827,7 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
     for (int f = tid; f < 16 * 64; f += 256)    // fc3 weights [16][64] -> [64][16]: conflict-free reads in the fc3 step
       reinterpret_cast<float *>(sm + K4_F3W)[(f & 63) * 16 + (f >> 6)] = __ldg(fp + F_F3W + f);
     FC_TR(1);
+    pdl_wait();                                   // labels / logits / ctu_cnt are read by the previous batch's K6 and copies: no store before the predecessor grid is complete
     mbar_wait(bar_done, 0);
     fence_after_sync();
     FC_TR(2);
@@ -998,21 +1001,24 @@ inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int threads
 }
 
 // Queue the four CNN kernels of one frame (programmatic dependent launch: each kernel's prologue overlaps its
-// predecessor's tail).  Returns the number of kernels launched.
-inline int tc_launch(const TcParams &p, const FrameBatch &fb, FrameGeom g, int pitch, int cpitch, int boundary_fix, int num_sms,
-                     cudaStream_t st) {
+// predecessor's tail).  *launches += kernels launched; returns the first launch error.
+inline cudaError_t tc_launch(const TcParams &p, const FrameBatch &fb, FrameGeom g, int pitch, int cpitch, int boundary_fix, int num_sms,
+                             cudaStream_t st, int *launches) {
   FrameGeom gt = g;                              // K2/K3 only loop over CTUs: give them the launch's total
   gt.nctu = g.nctu * fb.n;
   const int grid = gt.nctu < num_sms ? gt.nctu : num_sms;
   const int npad = ((4 * gt.nctu + 127) / 128) * 128;   // <= p.npad (sized for the largest batch); the feats layout follows the launch
-  tc_launch_pdl(k_tc_l1, grid, K1_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat);
-  tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2);
-  tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad);
+  cudaError_t e;
+  if ((e = tc_launch_pdl(k_tc_l1, grid, K1_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat)) != cudaSuccess) return e;
+  if ((e = tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2)) != cudaSuccess) return e;
+  if ((e = tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad)) != cudaSuccess) return e;
   if (npad / FcSmall::NT > num_sms)             // more 32-sample tiles than SMs: 64-sample tiles halve the weight traffic
-    tc_launch_pdl(k_tc_fc<FcLarge>, npad / FcLarge::NT, TC_THREADS, FcLarge::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
+    e = tc_launch_pdl(k_tc_fc<FcLarge>, npad / FcLarge::NT, TC_THREADS, FcLarge::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
   else
-    tc_launch_pdl(k_tc_fc<FcSmall>, npad / FcSmall::NT, TC_THREADS, FcSmall::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
-  return 4;
+    e = tc_launch_pdl(k_tc_fc<FcSmall>, npad / FcSmall::NT, TC_THREADS, FcSmall::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
+  if (e != cudaSuccess) return e;
+  *launches += 4;
+  return cudaSuccess;
 }
 
 }  // namespace hevcdl

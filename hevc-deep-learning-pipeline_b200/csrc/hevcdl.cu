@@ -2,6 +2,7 @@
 // Host side: frame slots, pinned staging, three streams (copies in, kernels, copies out) chained by CUDA events,
 // so the H2D copy of frame i+1 and the D2H copies of frame i-1 overlap the kernels of frame i.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <chrono>
 #include <cmath>
@@ -15,6 +16,7 @@
 #include "cnn_tc.cuh"
 #include "common.cuh"
 #include "rmd.cuh"
+#include "../../include/hevcdl_internal.h"
 
 using namespace hevcdl;
 
@@ -187,7 +189,7 @@ int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
   CK(cudaMalloc(&s.dCand, ctx->puCap * 8));
   CK(cudaMallocHost(&s.hPlanes, ybytes + 2 * cbytes));
   CK(cudaMallocHost(&s.hLabels, (size_t)g.nctu * 16));
-  CK(cudaMallocHost(&s.hLogits, (size_t)g.nctu * 64 * sizeof(float)));
+  if (ctx->cfg.outputs & HEVCDL_OUT_LOGITS) CK(cudaMallocHost(&s.hLogits, (size_t)g.nctu * 64 * sizeof(float)));
   CK(cudaMallocHost(&s.hCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
   CK(cudaEventCreateWithFlags(&s.evIn, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s.evCnn, cudaEventDisableTiming));
@@ -206,7 +208,7 @@ int ensure_host_pu_cap(hevcdl_ctx *ctx, Slot &s, size_t n) {
   if (s.hCand) cudaFreeHost(s.hCand);
   s.hPus = nullptr; s.hSatd = nullptr; s.hCand = nullptr; s.hPuCap = 0;
   CK(cudaMallocHost(&s.hPus, cap * sizeof(hevcdl_pu)));
-  CK(cudaMallocHost(&s.hSatd, cap * 35 * sizeof(uint32_t)));
+  if (ctx->cfg.outputs & HEVCDL_OUT_SATD) CK(cudaMallocHost(&s.hSatd, cap * 35 * sizeof(uint32_t)));
   CK(cudaMallocHost(&s.hCand, cap * 8));
   s.hPuCap = cap;
   return HEVCDL_OK;
@@ -221,14 +223,14 @@ static void wait_unless_done(cudaStream_t st, cudaEvent_t ev) {
 }
 
 // Queue the device pipeline of n <= cfg.batch slots on ctx->stream: one CNN launch for all of them (tensor-core path),
-// then the RMD kernels per frame.  Returns kernels launched.
-int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
+// then the RMD kernels per frame.  *launches += kernels launched; every launch / record return code is checked.
+int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed, int *launches_out) {
   const FrameGeom g = ctx->geo;
   int launches = 0;
   Slot &head = *sl[0];
   if (ctx->rmd)
     for (int i = 0; i < n; i++) wait_unless_done(ctx->stream, sl[i]->evRmd);   // a slot's earlier K6 (other stream) is done
-  if (timed) cudaEventRecord(head.evT0, ctx->stream);
+  if (timed) CK(cudaEventRecord(head.evT0, ctx->stream));
   if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
     FrameBatch fb{};
     fb.n = n;
@@ -237,24 +239,24 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
       fb.Y[i] = s.dY; fb.U[i] = s.dU; fb.V[i] = s.dV;
       fb.labels[i] = s.dLabels; fb.logits[i] = s.dLogits; fb.ctu_cnt[i] = ctx->cfg.rmd ? s.dCtuCnt : nullptr;
     }
-    launches += tc_launch(ctx->tc, fb, g, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, ctx->numSMs, ctx->stream);
+    CK(tc_launch(ctx->tc, fb, g, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, ctx->numSMs, ctx->stream, &launches));
   } else {
     const int grid = g.nctu < 4 * ctx->numSMs ? g.nctu : 4 * ctx->numSMs;
     for (int i = 0; i < n; i++) {
       Slot &s = *sl[i];
-      launch_pdl(k_cnn_fp32, grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream, (const uint8_t *)s.dY, (const uint8_t *)s.dU, (const uint8_t *)s.dV, g,
-                 ctx->pitch, ctx->cpitch, ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr);
+      CK(launch_pdl(k_cnn_fp32, grid, FP32_THREADS, FP32_SMEM_BYTES, ctx->stream, (const uint8_t *)s.dY, (const uint8_t *)s.dU, (const uint8_t *)s.dV, g,
+                    ctx->pitch, ctx->cpitch, ctx->fp, ctx->cfg.boundary_fix, s.dLabels, s.dLogits, ctx->cfg.rmd ? s.dCtuCnt : nullptr));
       launches++;
     }
   }
-  if (timed) cudaEventRecord(head.evT1, ctx->stream);
+  if (timed) CK(cudaEventRecord(head.evT1, ctx->stream));
   // K6 is CUDA-core work with small blocks, the CNN kernels are one big tensor-core CTA per SM: on its own stream the
   // RMD pass of this batch shares the SMs with K1/K2 of the next batch instead of waiting in line behind them.
   cudaStream_t rs = ctx->rmd ? ctx->rmd : ctx->stream;
   if (ctx->cfg.rmd) {                             // one plan + one items launch for the whole batch (queue in the head slot)
     if (rs != ctx->stream) {
-      cudaEventRecord(head.evCnn, ctx->stream);
-      cudaStreamWaitEvent(rs, head.evCnn, 0);
+      CK(cudaEventRecord(head.evCnn, ctx->stream));
+      CK(cudaStreamWaitEvent(rs, head.evCnn, 0));
     }
     RmdBatch rb{};
     rb.n = n;
@@ -263,15 +265,16 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed) {
       rb.Y[i] = s.dY; rb.labels[i] = s.dLabels; rb.ctu_cnt[i] = s.dCtuCnt; rb.ctu_off[i] = s.dCtuOff;
       rb.pus[i] = s.dPus; rb.satd[i] = s.dSatd; rb.cand[i] = s.dCand;
     }
-    launch_pdl(k_rmd_plan, (g.nctu * n + 7) / 8, 256, 0, rs, rb, g, ctx->rmdBlocks, head.dItems, head.dCtrl);
-    launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, rs, rb, g, ctx->pitch, (const RmdItem *)head.dItems, head.dCtrl);
+    CK(launch_pdl(k_rmd_plan, (g.nctu * n + 7) / 8, 256, 0, rs, rb, g, ctx->rmdBlocks, head.dItems, head.dCtrl));
+    CK(launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, rs, rb, g, ctx->pitch, (const RmdItem *)head.dItems, head.dCtrl));
     launches += 2;
   } else {
     rs = ctx->stream;
   }
-  for (int i = 0; i < n; i++) cudaEventRecord(sl[i]->evRmd, rs);   // every kernel of these frames is done
-  if (timed) cudaEventRecord(head.evT2, rs);
-  return launches;
+  for (int i = 0; i < n; i++) CK(cudaEventRecord(sl[i]->evRmd, rs));   // every kernel of these frames is done
+  if (timed) CK(cudaEventRecord(head.evT2, rs));
+  if (launches_out) *launches_out += launches;
+  return HEVCDL_OK;
 }
 
 // Launch the kernels of the frames submitted so far (a full batch, or fewer when somebody asks for a pending frame)
@@ -281,7 +284,12 @@ int flush_pending(hevcdl_ctx *ctx) {
   if (n == 0) return HEVCDL_OK;
   const FrameGeom &g = ctx->geo;
   for (Slot *s : ctx->pending) wait_unless_done(ctx->stream, s->evIn);
-  ctx->stats.kernel_launches += launch_pipeline(ctx, ctx->pending.data(), n, ctx->stageTimes);
+  {
+    int nl = 0;
+    const int rc = launch_pipeline(ctx, ctx->pending.data(), n, ctx->stageTimes, &nl);
+    ctx->stats.kernel_launches += nl;
+    if (rc) return rc;
+  }
   CK(cudaGetLastError());
   for (int i = 0; i < n; i++) {
     Slot *s = ctx->pending[i];
@@ -289,7 +297,8 @@ int flush_pending(hevcdl_ctx *ctx) {
     s->timed = ctx->stageTimes && i == 0;
     CK(cudaStreamWaitEvent(ctx->d2h, s->evRmd, 0));
     CK(cudaMemcpyAsync(s->hLabels, s->dLabels, (size_t)g.nctu * 16, cudaMemcpyDeviceToHost, ctx->d2h));
-    CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
+    if (ctx->cfg.outputs & HEVCDL_OUT_LOGITS)
+      CK(cudaMemcpyAsync(s->hLogits, s->dLogits, (size_t)g.nctu * 64 * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
     if (ctx->cfg.rmd)
       CK(cudaMemcpyAsync(s->hCtuOff, s->dCtuOff, ((size_t)g.nctu + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h));
     CK(cudaEventRecord(s->evLabels, ctx->d2h));
@@ -308,14 +317,10 @@ int submit_impl(hevcdl_ctx *ctx, int frame, const T *y, int sy, const T *u, cons
   const FrameGeom &g = ctx->geo;
   const int W = g.W, H = g.H, P = ctx->pitch, CP = ctx->cpitch;
   uint8_t *hy = s->hPlanes, *hu = hy + (size_t)P * H, *hv = hu + (size_t)CP * (H / 2);
-  const uint8_t *src_y = nullptr;
-  bool direct = false;
-  if (sizeof(T) == 1) {  // already-pinned 8-bit planes can be copied without staging
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, y) == cudaSuccess && at.type == cudaMemoryTypeHost) direct = true;
-    else cudaGetLastError();
-    src_y = reinterpret_cast<const uint8_t *>(y);
-  }
+  // hevcdl_cfg.pinned_input: the caller's 8-bit planes are page-locked and stay untouched until the frame has been
+  // waited for, so the copy engine may read them after this call returns (no staging copy, no pointer probing)
+  const bool direct = sizeof(T) == 1 && ctx->cfg.pinned_input;
+  const uint8_t *src_y = reinterpret_cast<const uint8_t *>(y);
   if (direct && sy == P && sc == CP && (const uint8_t *)u == src_y + (size_t)P * H && (const uint8_t *)v == (const uint8_t *)u + (size_t)CP * (H / 2)) {
     // one contiguous pinned I420 frame whose strides equal the device pitches: a single copy
     CK(cudaMemcpyAsync(s->dY, src_y, (size_t)P * H + 2 * (size_t)CP * (H / 2), cudaMemcpyHostToDevice, ctx->h2d));
@@ -373,7 +378,8 @@ int fetch_pus(hevcdl_ctx *ctx, Slot *s) {
   CK(cudaStreamWaitEvent(ctx->d2hPu, s->evRmd, 0));
   if (n) {
     CK(cudaMemcpyAsync(s->hPus, s->dPus, n * sizeof(hevcdl_pu), cudaMemcpyDeviceToHost, ctx->d2hPu));
-    CK(cudaMemcpyAsync(s->hSatd, s->dSatd, n * 35 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->d2hPu));
+    if (ctx->cfg.outputs & HEVCDL_OUT_SATD)
+      CK(cudaMemcpyAsync(s->hSatd, s->dSatd, n * 35 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->d2hPu));
     CK(cudaMemcpyAsync(s->hCand, s->dCand, n * 8, cudaMemcpyDeviceToHost, ctx->d2hPu));
   }
   CK(cudaStreamSynchronize(ctx->d2hPu));
@@ -401,10 +407,48 @@ const char *hevcdl_status_str(int st) {
 
 const char *hevcdl_last_error(const hevcdl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+// NUMA node of a CUDA device from sysfs; the calling thread is restricted to that node's CPUs, so that pinned
+// allocations (first touch) and staging memcpys made by it afterwards are local to the GPU's PCIe root complex.
+int hevcdl_numa_bind_thread(int device) {
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) { cudaGetLastError(); return HEVCDL_E_NODEVICE; }
+  for (char *c = bdf; *c; c++) if (*c >= 'A' && *c <= 'F') *c += 'a' - 'A';   // sysfs names are lower case
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+  int node = -1;
+  if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+  if (node < 0) return 0;                         // no NUMA information: single node
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  FILE *f = fopen(path, "r");
+  if (!f) return 0;
+  char list[4096] = {0};
+  const bool got = fgets(list, sizeof list, f) != nullptr;
+  fclose(f);
+  if (!got) return 0;
+  cpu_set_t set, cur;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof cur, &cur) != 0) return 0;
+  int nset = 0;
+  for (char *p = list; *p;) {                     // "0-31,64-95"
+    char *e;
+    const long a = strtol(p, &e, 10);
+    if (e == p) break;
+    long b = a;
+    if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+      if (CPU_ISSET(c, &cur)) { CPU_SET(c, &set); nset++; }     // never widen a mask the launcher (cgroup, taskset) gave us
+    p = (*e == ',') ? e + 1 : e;
+    if (*e != ',') break;
+  }
+  if (nset > 0) sched_setaffinity(0, sizeof set, &set);
+  return node;
+}
+
 int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   if (!cfg || !out || cfg->abi_version != HEVCDL_ABI_VERSION || cfg->width <= 0 || cfg->height <= 0 ||
       (cfg->width % 8) || (cfg->height % 8) || cfg->width > 8192 || cfg->height > 8192 || !cfg->weights_path ||
-      (cfg->precision != HEVCDL_PREC_FP32 && cfg->precision != HEVCDL_PREC_BF16_TC)) {
+      (cfg->precision != HEVCDL_PREC_FP32 && cfg->precision != HEVCDL_PREC_BF16_TC) ||
+      (cfg->outputs & ~(HEVCDL_OUT_LOGITS | HEVCDL_OUT_SATD))) {
     g_create_err = "invalid hevcdl_cfg";
     return HEVCDL_E_INVAL;
   }
@@ -434,6 +478,7 @@ int hevcdl_create(const hevcdl_cfg *cfg, hevcdl_ctx **out) {
   std::string wp = cfg->weights_path;
   auto fail = [&](int rc) { g_create_err = ctx->err; hevcdl_destroy(ctx); return rc; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(HEVCDL_E_CUDA); }
+  if (cfg->numa_bind) hevcdl_numa_bind_thread(cfg->device);   // best effort: a host without NUMA topology in sysfs is not an error
   ctx->numSMs = prop.multiProcessorCount;
   FrameGeom &g = ctx->geo;
   g.W = cfg->width; g.H = cfg->height;
@@ -569,6 +614,7 @@ int hevcdl_frame_labels(hevcdl_ctx *ctx, int frame, uint8_t *labels, float *logi
   if (!s) return HEVCDL_E_NOFRAME;
   int rc = finish_slot(ctx, s);
   if (rc) return rc;
+  if (logits && !(ctx->cfg.outputs & HEVCDL_OUT_LOGITS)) { ctx->err = "context created without HEVCDL_OUT_LOGITS"; return HEVCDL_E_INVAL; }
   if (labels) memcpy(labels, s->hLabels, (size_t)ctx->geo.nctu * 16);
   if (logits) memcpy(logits, s->hLogits, (size_t)ctx->geo.nctu * 64 * sizeof(float));
   return HEVCDL_OK;
@@ -589,6 +635,7 @@ int hevcdl_frame_pus(hevcdl_ctx *ctx, int frame, hevcdl_pu *pus, uint32_t *satd,
   if (!ctx) return HEVCDL_E_INVAL;
   Slot *s = find_slot(ctx, frame);
   if (!s) return HEVCDL_E_NOFRAME;
+  if (satd && !(ctx->cfg.outputs & HEVCDL_OUT_SATD)) { ctx->err = "context created without HEVCDL_OUT_SATD"; return HEVCDL_E_INVAL; }
   int rc = finish_slot(ctx, s);
   if (rc) return rc;
   if ((rc = fetch_pus(ctx, s))) return rc;
@@ -618,13 +665,13 @@ int hevcdl_frame_view_get(hevcdl_ctx *ctx, int frame, int want_pus, hevcdl_frame
   int rc = finish_slot(ctx, s);
   if (rc) return rc;
   memset(out, 0, sizeof *out);
-  out->labels = s->hLabels; out->logits = s->hLogits; out->nctu = ctx->geo.nctu;
+  out->labels = s->hLabels; out->logits = (ctx->cfg.outputs & HEVCDL_OUT_LOGITS) ? s->hLogits : nullptr; out->nctu = ctx->geo.nctu;
   if (ctx->cfg.rmd) {
     out->ctu_off = s->hCtuOff;
     if (want_pus) {
       if ((rc = fetch_pus(ctx, s))) return rc;
       out->npu = s->hCtuOff[ctx->geo.nctu];
-      out->pus = s->hPus; out->satd = s->hSatd; out->cand = s->hCand;
+      out->pus = s->hPus; out->satd = (ctx->cfg.outputs & HEVCDL_OUT_SATD) ? s->hSatd : nullptr; out->cand = s->hCand;
     }
   }
   return HEVCDL_OK;
@@ -724,7 +771,12 @@ int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int i
     return n;
   };
   Slot *last = nullptr;
-  for (int it = 0; it < iters;) { const int n = group(it); nl += launch_pipeline(ctx, grp.data(), n, false); it += n; last = grp[n - 1]; }
+  for (int it = 0; it < iters;) {
+    const int n = group(it);
+    const int rc = launch_pipeline(ctx, grp.data(), n, false, &nl);
+    if (rc) return rc;
+    it += n; last = grp[n - 1];
+  }
   if (ctx->rmd && last) CK(cudaStreamWaitEvent(ctx->stream, last->evRmd, 0));   // the RMD stream's last launch is part of the pass
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaEventSynchronize(e1));
@@ -736,7 +788,7 @@ int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int i
     const int n = group(it);
     it += n;
     Slot &s = *grp[0];
-    nl += launch_pipeline(ctx, grp.data(), n, true);
+    { const int rc = launch_pipeline(ctx, grp.data(), n, true, &nl); if (rc) return rc; }
     CK(cudaEventSynchronize(s.evT2));
     float a = 0, b = 0;
     CK(cudaEventElapsedTime(&a, s.evT0, s.evT1));
@@ -761,12 +813,12 @@ int hevcdl_bench_e2e(hevcdl_ctx *ctx, int first_id, int iters, int depth, int nb
     hevcdl_frame_view fv;
     int rc = hevcdl_frame_view_get(ctx, frame, ctx->cfg.rmd, &fv);
     if (rc) return rc;
-    bytes += (uint64_t)nctu * 16 + (uint64_t)nctu * 64 * sizeof(float);
+    bytes += (uint64_t)nctu * 16 + (fv.logits ? (uint64_t)nctu * 64 * sizeof(float) : 0);
     chk += fv.labels[(size_t)nctu * 16 - 1];
     if (fv.ctu_off) bytes += ((uint64_t)nctu + 1) * sizeof(int32_t);
     if (fv.npu > 0) {
-      bytes += (uint64_t)fv.npu * (sizeof(hevcdl_pu) + 35 * sizeof(uint32_t) + 8);
-      chk += fv.cand[(size_t)fv.npu * 8 - 8] + fv.satd[(size_t)fv.npu * 35 - 1];
+      bytes += (uint64_t)fv.npu * (sizeof(hevcdl_pu) + 8 + (fv.satd ? 35 * sizeof(uint32_t) : 0));
+      chk += fv.cand[(size_t)fv.npu * 8 - 8] + (fv.satd ? fv.satd[(size_t)fv.npu * 35 - 1] : 0);
     }
     return hevcdl_release_frame(ctx, frame);
   };
@@ -817,8 +869,8 @@ int hevcdl_debug_rerun_rmd(hevcdl_ctx *ctx, int frame, const uint8_t *labels) {
   rb.n = 1;
   rb.Y[0] = s->dY; rb.labels[0] = s->dLabels; rb.ctu_cnt[0] = s->dCtuCnt; rb.ctu_off[0] = s->dCtuOff;
   rb.pus[0] = s->dPus; rb.satd[0] = s->dSatd; rb.cand[0] = s->dCand;
-  launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, st, rb, g, ctx->rmdBlocks, s->dItems, s->dCtrl);
-  launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, st, rb, g, ctx->pitch, (const RmdItem *)s->dItems, s->dCtrl);
+  CK(launch_pdl(k_rmd_plan, (g.nctu + 7) / 8, 256, 0, st, rb, g, ctx->rmdBlocks, s->dItems, s->dCtrl));
+  CK(launch_pdl(k_rmd_items, ctx->rmdBlocks, RMD_BW * 32, 0, st, rb, g, ctx->pitch, (const RmdItem *)s->dItems, s->dCtrl));
   CK(cudaGetLastError());
   ctx->stats.kernel_launches += 3;
   CK(cudaEventRecord(s->evRmd, st));

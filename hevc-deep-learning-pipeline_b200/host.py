@@ -16,20 +16,25 @@ LIB_PATH = os.environ.get("HEVCDL_LIB") or os.path.join(_HERE, "csrc", "libhevcd
 DEFAULT_WEIGHTS = os.path.join(os.path.dirname(_HERE), "weights", "hevc_encoder_model.hdlw")
 
 PREC_FP32, PREC_BF16_TC = 0, 1
+OUT_LOGITS, OUT_SATD = 1, 2            # hevcdl_output_flags
+ABI_VERSION = 3
 
+# include/hevcdl.h: the drop-in boundary
 EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_get_stats",
-    "hevcdl_stream",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_get_stats", "hevcdl_numa_bind_thread",
 ]
+# include/hevcdl_internal.h: measurement and test hooks
+EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
 
 
 class Cfg(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("slots", C.c_int32), ("precision", C.c_int32), ("rmd", C.c_int32), ("boundary_fix", C.c_int32),
-                ("batch", C.c_int32), ("weights_path", C.c_char_p)]
+                ("batch", C.c_int32), ("outputs", C.c_int32), ("pinned_input", C.c_int32), ("numa_bind", C.c_int32),
+                ("weights_path", C.c_char_p)]
 
 
 class Stats(C.Structure):
@@ -87,6 +92,7 @@ def load_library():
     L.hevcdl_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.hevcdl_stream.argtypes = [vp]
     L.hevcdl_stream.restype = vp
+    L.hevcdl_numa_bind_thread.argtypes = [ip]
     _lib = L
     return L
 
@@ -100,14 +106,18 @@ class DepthPredictor:
     encoder_intra_main.cfg:20-22), so ranks shard frames f -> rank f % world with no exchange."""
 
     def __init__(self, width, height, device=0, slots=2, precision=PREC_FP32, rmd=True, boundary_fix=False,
-                 weights=DEFAULT_WEIGHTS, batch=1):
+                 weights=DEFAULT_WEIGHTS, batch=1, outputs=OUT_LOGITS | OUT_SATD, pinned_input=False, numa_bind=False):
+        """outputs: hevcdl_output_flags -- this mirror defaults to everything (logits for margin reports, SATD tables for
+        the parity tests); the C default, and what bench.py's end-to-end leg uses, is 0: labels + PU list + candidate modes.
+        pinned_input: planes handed to submit() are page-locked and stay untouched until the frame is waited for."""
         self.lib = load_library()
+        self.outputs = int(outputs)
         self.width, self.height = int(width), int(height)
         self.ctu_w, self.ctu_h = (self.width + 63) // 64, (self.height + 63) // 64
         self.nctu = self.ctu_w * self.ctu_h
         self.rmd = bool(rmd)
-        cfg = Cfg(2, device, self.width, self.height, slots, precision, int(rmd), int(boundary_fix), int(batch),
-                  os.fsencode(weights))
+        cfg = Cfg(ABI_VERSION, device, self.width, self.height, slots, precision, int(rmd), int(boundary_fix), int(batch),
+                  int(outputs), int(pinned_input), int(numa_bind), os.fsencode(weights))
         h = C.c_void_p()
         rc = self.lib.hevcdl_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -157,7 +167,7 @@ class DepthPredictor:
         n = C.c_int()
         self._ck(self.lib.hevcdl_frame_pu_count(self.h, frame, C.byref(n)), "frame_pu_count")
         pus = np.empty(n.value, PU_DTYPE)
-        satd = np.empty((n.value, 35), np.uint32)
+        satd = np.empty((n.value, 35), np.uint32) if self.outputs & OUT_SATD else None
         cand = np.empty((n.value, 8), np.uint8)
         self._ck(self.lib.hevcdl_frame_pus(self.h, frame, _ptr(pus), _ptr(satd), _ptr(cand)), "frame_pus")
         return pus, satd, cand
@@ -183,9 +193,11 @@ class DepthPredictor:
                 cache[key] = a
             return a
         n, m = v.nctu, v.npu
-        return {"labels": arr(v.labels, C.c_uint8, n * 16, (n, 16)), "logits": arr(v.logits, C.c_float, n * 64, (n, 4, 16)),
+        return {"labels": arr(v.labels, C.c_uint8, n * 16, (n, 16)),
+                "logits": arr(v.logits, C.c_float, n * 64 if v.logits else 0, (n if v.logits else 0, 4, 16)),
                 "ctu_off": arr(v.ctu_off, C.c_int32, n + 1 if v.ctu_off else 0, (n + 1 if v.ctu_off else 0,)),
-                "pus": arr(v.pus, C.c_uint8, m * 8, (m,), PU_DTYPE), "satd": arr(v.satd, C.c_uint32, m * 35, (m, 35)),
+                "pus": arr(v.pus, C.c_uint8, m * 8, (m,), PU_DTYPE),
+                "satd": arr(v.satd, C.c_uint32, m * 35 if v.satd else 0, (m if v.satd else 0, 35)),
                 "cand": arr(v.cand, C.c_uint8, m * 8, (m, 8))}
 
     def ctu_pu_range(self, frame, addr):
@@ -269,6 +281,11 @@ class DepthPredictor:
         s = Stats()
         self._ck(self.lib.hevcdl_get_stats(self.h, C.byref(s)), "get_stats")
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def numa_bind_thread(device):
+    """Pin the calling thread to the CPUs of the device's NUMA node (hevcdl_numa_bind_thread); returns the node."""
+    return load_library().hevcdl_numa_bind_thread(int(device))
 
 
 def frame_to_rank(frame, world_size):

@@ -32,7 +32,9 @@ def parse_bitstream_cfg(path="bitstream.cfg"):
             parts = line.split(":")
             val = ":".join(parts[1:]).strip(" ").strip("\n").strip()
             if i == 0:
-                out["input"] = val
+                # the reference's own bitstream.cfg names the file Windows-style (".\\Flowervase_...yuv"); the same file
+                # must open here: drop a leading ".\\" and turn the remaining separators round
+                out["input"] = val[2:].replace("\\", "/") if val.startswith(".\\") else val.replace("\\", "/")
             elif i == 3:
                 out["frame_rate"] = val
             elif i == 5:
@@ -54,12 +56,25 @@ def gen_frames(_args):
 def use_model(args):
     cfg = parse_bitstream_cfg()
     w, h = cfg["width"], cfg["height"]
+    if w <= 0 or h <= 0 or w % 2 or h % 2:
+        raise SystemExit("hevcdl sidecar: 4:2:0 needs even SourceWidth/SourceHeight, got %dx%d" % (w, h))
     fbytes = w * h * 3 // 2
+    if not os.path.exists(cfg["input"]):
+        # fail BEFORE the encoder starts polling ./pred (HM_dl TEncCu.cpp:245 never times out)
+        raise SystemExit("hevcdl sidecar: InputFile %r of bitstream.cfg not found" % cfg["input"])
     nfile = os.path.getsize(cfg["input"]) // fbytes
-    nframes = min(cfg["frames"], nfile)                    # use_model.py:73-76: stop at FramesToBeEncoded
+    if nfile < cfg["frames"]:
+        raise SystemExit("hevcdl sidecar: %s holds %d frames of %dx%d, bitstream.cfg asks for %d -- the encoder would wait "
+                         "for ./pred/%d forever" % (cfg["input"], nfile, w, h, cfg["frames"], nfile))
+    nframes = cfg["frames"]                                # use_model.py:73-76: stop at FramesToBeEncoded
     prec = host.PREC_BF16_TC if args.precision == "bf16" else host.PREC_FP32
     depth = max(2, 2 * args.batch)
-    dp = host.DepthPredictor(w, h, device=args.device, slots=depth, precision=prec, rmd=False, batch=args.batch)
+    # The library takes multiples of 8 (HM's minimum CU, TAppEncCfg.cpp:2176).  The reference sidecar accepts any size:
+    # it crops the UNPADDED picture and PIL pads with black (use_model.py:92-93).  Video black (Y=16, Cb=Cr=128) converts
+    # to RGB (0,0,0) exactly (csrc/common.cuh yuv2rgb), so padding the planes with it up to the next multiple of 8 gives
+    # the CNN the very tensor the reference would see; the CTU count ceil(W/64) x ceil(H/64) does not change.
+    w8, h8 = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+    dp = host.DepthPredictor(w8, h8, device=args.device, slots=depth, precision=prec, rmd=False, batch=args.batch, outputs=0)
     yuv = np.memmap(cfg["input"], np.uint8, "r")
     inflight = []
 
@@ -75,6 +90,10 @@ def use_model(args):
         Y = fr[:w * h].reshape(h, w)
         U = fr[w * h:w * h * 5 // 4].reshape(h // 2, w // 2)
         V = fr[w * h * 5 // 4:].reshape(h // 2, w // 2)
+        if (w8, h8) != (w, h):
+            Y = np.pad(Y, ((0, h8 - h), (0, w8 - w)), constant_values=16)
+            U = np.pad(U, ((0, (h8 - h) // 2), (0, (w8 - w) // 2)), constant_values=128)
+            V = np.pad(V, ((0, (h8 - h) // 2), (0, (w8 - w) // 2)), constant_values=128)
         dp.submit(f, Y, U, V)
         inflight.append(f)
         if len(inflight) >= depth:

@@ -21,16 +21,33 @@
 //   HEVCDL_DEVICE     CUDA ordinal (default 0)
 //   HEVCDL_PRECISION  fp32 (default: tightest parity with the torch sidecar) | bf16 (tcgen05 tensor cores)
 //   HEVCDL_BOUNDARY_FIX 1 = raise labels of picture-edge CTUs so partial CTUs tile (default 0 = reference)
+//   HEVCDL_LOOKAHEAD  frames submitted ahead of the one being encoded (default 3; 0 = off).  A reader thread preads frames
+//                     n+1 .. n+k of the encoder's own input file (all-intra pictures are independent and the file offset of
+//                     frame f is f * W * H * 3/2) while HM encodes frame n, so only the first frame ever waits
+//                     for the device.  The file is found from HEVCDL_INPUT or the encoder's own command line / -c files
+//                     (InputFile, FrameSkip, FramesToBeEncoded); every prefetched frame is checked against the planes HM
+//                     hands over for that frame id (hash of all three planes) -- on a mismatch the prefetch is dropped
+//                     and the frame is uploaded from HM's planes as without lookahead.  8-bit 4:2:0 input without padding only.
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
 //                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
 //                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
 //                     2 = exact mode: per PU, HM's reconstructed reference samples go to hevcdl_rmd_exact (bit-exact,
 //                     byte-identical bitstream, one synchronous call per PU) (default 0: HM's own pass)
 // There is no fallback: any library failure aborts the encoder with the library's error text.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <unistd.h>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "TLibEncoder/TEncCu.h"
 #include "TLibEncoder/TEncTop.h"
@@ -39,6 +56,165 @@
 #include "rmd_hook.h"
 
 namespace {
+
+// ---- frame lookahead (replaces the overlap the reference gets from running use_model.py as a
+// detached process ahead of the encoder, encmain.cpp:107-108) ---------------------------------------------------------
+uint64_t hash_bytes(uint64_t h, const uint8_t *p, size_t n) {
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, p + i, 8); h = (h ^ w) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; }
+  for (; i < n; i++) { h = (h ^ p[i]) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; }
+  return h;
+}
+uint64_t hash_u8_plane(uint64_t h, const uint8_t *p, int w, int hgt) {          // row by row, like hash_pel_plane
+  for (int y = 0; y < hgt; y++) h = hash_bytes(h, p + (size_t)y * w, w);
+  return h;
+}
+uint64_t hash_pel_plane(uint64_t h, const Pel *p, int stride, int w, int hgt, std::vector<uint8_t> &row) {
+  row.resize(w);
+  for (int y = 0; y < hgt; y++) {
+    const Pel *r = p + (size_t)y * stride;
+    for (int x = 0; x < w; x++) row[x] = (uint8_t)r[x];
+    h = hash_bytes(h, row.data(), w);
+  }
+  return h;
+}
+
+// What the encoder was told about its input, recovered from its own command line (/proc/self/cmdline) and -c files.
+struct InputSpec {
+  std::string file;
+  long skip = 0, frames = -1, tsr = 1;
+  bool eight_bit = true;
+  static std::string value_of(const std::string &line, const char *key) {      // "Key : value   # comment"
+    size_t i = 0;
+    while (i < line.size() && isspace((unsigned char)line[i])) i++;
+    const size_t kl = strlen(key);
+    if (line.compare(i, kl, key) != 0) return "";
+    i += kl;
+    while (i < line.size() && isspace((unsigned char)line[i])) i++;
+    if (i >= line.size() || line[i] != ':') return "";
+    std::string v = line.substr(i + 1);
+    const size_t hsh = v.find('#');
+    if (hsh != std::string::npos) v.erase(hsh);
+    const size_t a = v.find_first_not_of(" \t\r\n"), b = v.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : v.substr(a, b - a + 1);
+  }
+  void take(const char *key, const std::string &v) {
+    if (v.empty()) return;
+    if (!strcmp(key, "InputFile")) file = v;
+    else if (!strcmp(key, "FrameSkip")) skip = atol(v.c_str());
+    else if (!strcmp(key, "FramesToBeEncoded")) frames = atol(v.c_str());
+    else if (!strcmp(key, "TemporalSubsampleRatio")) tsr = atol(v.c_str());
+    else if (!strcmp(key, "InputBitDepth")) eight_bit = atol(v.c_str()) == 8 || atol(v.c_str()) == 0;
+  }
+  void parse_cfg(const std::string &path) {
+    std::ifstream f(path);
+    std::string line;
+    static const char *keys[] = {"InputFile", "FrameSkip", "FramesToBeEncoded", "TemporalSubsampleRatio", "InputBitDepth"};
+    while (std::getline(f, line))
+      for (const char *k : keys) take(k, value_of(line, k));
+  }
+  void parse_cmdline() {
+    std::ifstream f("/proc/self/cmdline", std::ios::binary);
+    std::vector<std::string> av;
+    std::string a;
+    while (std::getline(f, a, '\0')) av.push_back(a);
+    static const struct { const char *sh, *lg; } opt[] = {{"-i", "InputFile"}, {"-fs", "FrameSkip"}, {"-f", "FramesToBeEncoded"},
+                                                           {"-ts", "TemporalSubsampleRatio"}, {nullptr, "InputBitDepth"}};
+    for (size_t i = 1; i < av.size(); i++) {       // later options override earlier ones, as in the reference's parser
+      if (av[i] == "-c" && i + 1 < av.size()) { parse_cfg(av[++i]); continue; }
+      for (const auto &o : opt) {
+        const std::string lg = std::string("--") + o.lg;
+        if (o.sh && av[i] == o.sh && i + 1 < av.size()) { take(o.lg, av[++i]); break; }
+        if (av[i] == lg && i + 1 < av.size()) { take(o.lg, av[++i]); break; }
+        if (av[i].compare(0, lg.size() + 1, lg + "=") == 0) { take(o.lg, av[i].substr(lg.size() + 1)); break; }
+      }
+    }
+    if (const char *e = getenv("HEVCDL_INPUT")) file = e;
+  }
+};
+
+// Reader thread: keeps frames (next .. next + ring) of the input file in host buffers.  Only this thread touches the
+// file; only the encoder thread touches the hevcdl context.
+struct FrameReader {
+  int fd = -1, w = 0, h = 0;
+  long skip = 0, tsr = 1, nframes = 0;             // encoder frame id f lives at file frame skip + f * tsr
+  size_t fbytes = 0;
+  std::vector<std::vector<uint8_t>> ring;
+  std::vector<long> held;                          // encoder frame id held by each ring buffer (-1: none)
+  long want_lo = 0, want_hi = -1;                  // ids the encoder thread still wants buffered: [want_lo, want_hi]
+  bool stop = false;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::thread th;
+
+  bool open(const InputSpec &in, int width, int height, int depth) {
+    if (in.file.empty() || !in.eight_bit || in.tsr < 1) return false;
+    fd = ::open(in.file.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    w = width; h = height; fbytes = (size_t)w * h * 3 / 2;
+    if (fstat(fd, &st) != 0 || st.st_size < (off_t)fbytes || st.st_size % (off_t)fbytes) { ::close(fd); fd = -1; return false; }
+    skip = in.skip; tsr = in.tsr;
+    nframes = ((long)(st.st_size / (off_t)fbytes) - skip + tsr - 1) / tsr;
+    if (in.frames >= 0 && in.frames < nframes) nframes = in.frames;
+    ring.assign(depth + 1, std::vector<uint8_t>());
+    for (auto &b : ring) b.resize(fbytes);
+    held.assign(ring.size(), -1);
+    th = std::thread([this] { run(); });
+    return true;
+  }
+  void run() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      long f = -1;
+      int slot = -1;
+      cv.wait(lk, [&] {
+        if (stop) return true;
+        for (long c = want_lo; c <= want_hi && c < nframes; c++) {
+          bool have = false;
+          for (long hId : held) have |= hId == c;
+          if (have) continue;
+          for (size_t i = 0; i < held.size(); i++)
+            if (held[i] < want_lo) { f = c; slot = (int)i; return true; }   // a buffer whose frame is no longer wanted
+          return false;
+        }
+        return false;
+      });
+      if (stop) return;
+      held[slot] = -2;                             // being filled
+      lk.unlock();
+      const off_t off = (off_t)(skip + f * tsr) * (off_t)fbytes;
+      size_t got = 0;
+      while (got < fbytes) {
+        const ssize_t r = pread(fd, ring[slot].data() + got, fbytes - got, off + (off_t)got);
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      lk.lock();
+      held[slot] = got == fbytes ? f : -1;
+      if (got != fbytes) nframes = f;              // short file: nothing beyond this frame
+      cv.notify_all();
+    }
+  }
+  // encoder thread: ask for [lo, hi]; returns the buffer of frame f if it is ready (no waiting)
+  void want(long lo, long hi) { std::lock_guard<std::mutex> lk(mu); want_lo = lo; want_hi = hi; cv.notify_all(); }
+  const uint8_t *ready(long f, int wait_ms = 0) {
+    std::unique_lock<std::mutex> lk(mu);
+    const uint8_t *buf = nullptr;
+    auto have = [&] {
+      for (size_t i = 0; i < held.size(); i++) if (held[i] == f) { buf = ring[i].data(); return true; }
+      return f >= nframes;                         // past the end of the file: never comes
+    };
+    if (wait_ms > 0) cv.wait_for(lk, std::chrono::milliseconds(wait_ms), have);
+    else have();
+    return buf;
+  }
+  void close() {
+    if (th.joinable()) { { std::lock_guard<std::mutex> lk(mu); stop = true; cv.notify_all(); } th.join(); }
+    if (fd >= 0) ::close(fd);
+    fd = -1;
+  }
+};
 
 struct HevcdlSession {
   hevcdl_ctx *ctx = nullptr;
@@ -53,6 +229,13 @@ struct HevcdlSession {
   bool have_view = false;
   int ctu_first = 0, ctu_count = 0, cursor = 0;   // PU range of the CTU being compressed + last hit
   unsigned long long hook_hits = 0, hook_misses = 0;
+  // lookahead
+  FrameReader reader;
+  int lookahead = 0;            // frames submitted ahead (0: off)
+  long submitted_hi = -1;       // highest frame id handed to the device from the file
+  std::vector<std::pair<long, uint64_t>> ahead;   // (frame id, hash of the file's planes) of frames submitted from the file
+  unsigned long long la_hits = 0, la_direct = 0, la_mismatch = 0;
+  std::vector<uint8_t> rowbuf;
 
   static void die(const char *what, int rc, hevcdl_ctx *c) {
     fprintf(stderr, "hevcdl: %s failed: %s (%s)\n", what, hevcdl_status_str(rc), hevcdl_last_error(c));
@@ -66,10 +249,20 @@ struct HevcdlSession {
     const char *e;
     cfg.device = (e = getenv("HEVCDL_DEVICE")) ? atoi(e) : 0;
     cfg.width = w; cfg.height = h;
-    cfg.slots = 2;
+    lookahead = (e = getenv("HEVCDL_LOOKAHEAD")) ? atoi(e) : 3;
+    if (lookahead < 0) lookahead = 0;
+    if (lookahead > 16) lookahead = 16;
+    if (lookahead) {
+      InputSpec in;
+      in.parse_cmdline();
+      if (!reader.open(in, w, h, lookahead + 1)) lookahead = 0;    // no usable input file: behave as without lookahead
+    }
+    cfg.slots = 2 + lookahead;
+    cfg.batch = 1;
     cfg.precision = ((e = getenv("HEVCDL_PRECISION")) && !strcmp(e, "bf16")) ? HEVCDL_PREC_BF16_TC : HEVCDL_PREC_FP32;
     const int rmd_mode = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
     cfg.rmd = rmd_mode == 1;
+    cfg.outputs = rmd_mode == 1 ? HEVCDL_OUT_SATD : 0;   // the first-pass hook re-ranks with HM's own mode bits: it needs the SATD table
     gpu_rmd = rmd_mode == 1;
     exact_rmd = rmd_mode == 2;
     cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
@@ -91,16 +284,68 @@ struct HevcdlSession {
 
   // Hand the picture's ORIGINAL planes (the same ones xCompressCU reads at TEncCu.cpp:484) to the device.
   // This replaces gen_frames.py:21 (ffmpeg dump) and the sidecar's whole per-frame loop (use_model.py:74-127).
-  void begin_frame(int id, TComPicYuv *org) {
+  void begin_frame(int id, TComPicYuv *org, const TComSPS *sps) {
     const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
+    // the CNN and the SATD pass are defined on 8-bit samples (the reference sidecar reads the 8-bit input file,
+    // gen_frames.py:21); with a higher internal bit depth HM's Pel planes hold scaled values that must not be truncated
+    if (sps->getBitDepth(CHANNEL_TYPE_LUMA) != 8 || sps->getBitDepth(CHANNEL_TYPE_CHROMA) != 8 || org->getChromaFormat() != CHROMA_420) {
+      fprintf(stderr, "hevcdl: only 8-bit 4:2:0 encodes are supported (internal bit depth %d/%d)\n",
+              sps->getBitDepth(CHANNEL_TYPE_LUMA), sps->getBitDepth(CHANNEL_TYPE_CHROMA));
+      exit(EXIT_FAILURE);
+    }
     if (!ctx) open(w, h);
     if (w != width || h != height) { fprintf(stderr, "hevcdl: picture size changed mid-sequence\n"); exit(EXIT_FAILURE); }
     if (frame >= 0) { const int rc = hevcdl_release_frame(ctx, frame); if (rc) die("hevcdl_release_frame", rc, ctx); }
-    const int rc = hevcdl_submit_frame_pel16(ctx, id, org->getAddr(COMPONENT_Y), org->getStride(COMPONENT_Y),
-                                             org->getAddr(COMPONENT_Cb), org->getAddr(COMPONENT_Cr), org->getStride(COMPONENT_Cb));
-    if (rc) die("hevcdl_submit_frame_pel16", rc, ctx);
+    bool on_device = false;
+    if (lookahead) {
+      for (size_t i = 0; i < ahead.size(); i++) {
+        if (ahead[i].first != id) continue;
+        uint64_t hs = 0;
+        hs = hash_pel_plane(hs, org->getAddr(COMPONENT_Y), org->getStride(COMPONENT_Y), w, h, rowbuf);
+        hs = hash_pel_plane(hs, org->getAddr(COMPONENT_Cb), org->getStride(COMPONENT_Cb), w / 2, h / 2, rowbuf);
+        hs = hash_pel_plane(hs, org->getAddr(COMPONENT_Cr), org->getStride(COMPONENT_Cr), w / 2, h / 2, rowbuf);
+        if (hs == ahead[i].second) { on_device = true; la_hits++; ahead.erase(ahead.begin() + i); }
+        else {   // the file is not what HM is encoding (pre-processing, another skip): drop everything read ahead
+          la_mismatch++;
+          fprintf(stderr, "hevcdl: lookahead frame %d differs from the encoder's picture; lookahead disabled\n", id);
+          for (auto &a : ahead) { const int rc = hevcdl_release_frame(ctx, (int)a.first); if (rc) die("hevcdl_release_frame", rc, ctx); }
+          ahead.clear();
+          lookahead = 0;
+          reader.close();
+        }
+        break;
+      }
+    }
+    if (!on_device) {
+      const int rc = hevcdl_submit_frame_pel16(ctx, id, org->getAddr(COMPONENT_Y), org->getStride(COMPONENT_Y),
+                                               org->getAddr(COMPONENT_Cb), org->getAddr(COMPONENT_Cr), org->getStride(COMPONENT_Cb));
+      if (rc) die("hevcdl_submit_frame_pel16", rc, ctx);
+      la_direct++;
+    }
     frame = id;
     have_view = false;
+    if (lookahead) {
+      // top up: every frame of (id, id + lookahead] the reader already holds goes to the device now (non-blocking: a staging
+      // copy and queued work), the rest next time; the reader is told what to fetch meanwhile
+      if (submitted_hi < id) submitted_hi = id;
+      reader.want(submitted_hi + 1, (long)id + lookahead + 1);   // one frame further than the submit window: the next top-up finds it read
+      while (submitted_hi < (long)id + lookahead) {
+        // nothing ahead yet (first frame, or the reader fell behind): the next frame is worth a bounded wait -- the device
+        // is busy with the current frame for about as long as a page-cache read takes, and HM blocks on its labels next
+        const uint8_t *buf = reader.ready(submitted_hi + 1, ahead.empty() ? 25 : 0);
+        if (!buf) break;
+        const long f = submitted_hi + 1;
+        const uint8_t *y = buf, *u = y + (size_t)w * h, *v = u + (size_t)(w / 2) * (h / 2);
+        const int rc = hevcdl_submit_frame_u8(ctx, (int)f, y, w, u, v, w / 2);
+        if (rc) die("hevcdl_submit_frame_u8", rc, ctx);
+        uint64_t hs = hash_u8_plane(0, y, w, h);
+        hs = hash_u8_plane(hs, u, w / 2, h / 2);
+        hs = hash_u8_plane(hs, v, w / 2, h / 2);
+        ahead.push_back(std::make_pair(f, hs));
+        submitted_hi = f;
+        reader.want(submitted_hi + 1, (long)id + lookahead + 1);   // one frame further than the submit window: the next top-up finds it read
+      }
+    }
   }
 
   // PU range of one CTU in the frame's device results (fetched once per frame, zero-copy)
@@ -133,8 +378,11 @@ struct HevcdlSession {
   }
 
   ~HevcdlSession() {
+    reader.close();
     if (ctx) {
       if (getenv("HEVCDL_VERBOSE")) {
+        fprintf(stderr, "hevcdl: lookahead %d: %llu frames were on the device before HM asked, %llu uploaded from HM's planes, %llu mismatches\n",
+                lookahead, la_hits, la_direct, la_mismatch);
         hevcdl_stats_t st;
         if (!hevcdl_get_stats(ctx, &st))
           fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches, "
@@ -161,7 +409,7 @@ Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
   // behind the copy and the labels of all CTUs come back in one transfer.
   if ( g_session.frame != m_iFrame )
   {
-    g_session.begin_frame( m_iFrame, pCtu->getPic()->getPicYuvOrg() );
+    g_session.begin_frame( m_iFrame, pCtu->getPic()->getPicYuvOrg(), pCtu->getSlice()->getSPS() );
   }
 
   uint8_t depth8[16];

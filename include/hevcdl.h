@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define HEVCDL_ABI_VERSION 2
+#define HEVCDL_ABI_VERSION 3
 
 typedef enum {
   HEVCDL_OK = 0,
@@ -35,6 +35,15 @@ typedef enum {
   HEVCDL_PREC_FP32 = 0,    /* CUDA-core fp32 CNN (tightest parity with the torch fp32 oracle) */
   HEVCDL_PREC_BF16_TC = 1  /* tcgen05 tensor-core CNN, bf16 operands, fp32 accumulate + fp32 BN */
 } hevcdl_precision;
+
+/* hevcdl_cfg.outputs: what besides the 16 labels per CTU (and, with rmd=1, the PU list and the ranked candidate
+ * modes) is copied back to the host for every frame.  The 35 x u32 SATD table is 82 % of a frame's device-to-host
+ * bytes and only a consumer that re-ranks with its own mode bits (the HM first-pass hook, hm_plugin/rmd_hook.h)
+ * needs it; the logits are a diagnostic (argmax margins). */
+typedef enum {
+  HEVCDL_OUT_LOGITS = 1,   /* CNN outputs before argmax (use_model.py:100) */
+  HEVCDL_OUT_SATD = 2      /* per-PU 35-entry SATD table of the RMD pass */
+} hevcdl_output_flags;
 
 typedef struct hevcdl_ctx hevcdl_ctx;
 
@@ -53,6 +62,17 @@ typedef struct {
   int32_t batch;           /* frames per CNN launch, 1..8 (0 = 1).  All-intra frames are independent; with batch > 1 the
                               kernels of a frame start once `batch` frames have been submitted or when a pending frame is
                               asked for, whichever comes first.  Results do not depend on it.  Tensor-core path only. */
+  int32_t outputs;         /* hevcdl_output_flags: optional per-frame results copied to the host (0: labels, PU list and
+                              candidate modes only).  Getters of an output that was not asked for return NULL / E_INVAL. */
+  int32_t pinned_input;    /* 1: the caller promises that the planes handed to hevcdl_submit_frame_u8 live in page-locked
+                              host memory and stay UNTOUCHED until hevcdl_wait_frame / hevcdl_ctu_labels / any getter has
+                              returned for that frame: they are read by the copy engine after submit returns (no staging
+                              copy).  0 (default): submit copies the planes into the context's own pinned staging buffer
+                              before it returns; the caller may reuse its buffers at once. */
+  int32_t numa_bind;       /* 1: before allocating, pin the CALLING thread to the CPUs of the device's NUMA node
+                              (/sys/bus/pci/devices/<bdf>/numa_node), so that the context's pinned buffers and the staging
+                              copies of that thread are local to the GPU's PCIe root (8 ranks copying through one socket's
+                              memory is what bounds multi-GPU end-to-end throughput).  The affinity stays in force. */
   const char *weights_path;/* HDLW blob made by tools/convert_weights.py */
 } hevcdl_cfg;
 
@@ -137,37 +157,12 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
                      const uint8_t *mpm_add, double sqrt_lambda, uint32_t *satd, uint8_t *cand,
                      uint8_t *ncand);
 
-/* Measurement: run the device pipeline `iters` times over planes already resident in the slots of
- * frames[0..nframes) (round-robin; no H2D/D2H), timed with CUDA events on the context's stream.
- * ms[0] = total of one pass timed by a single event pair; ms[1], ms[2] = CNN (K0-K5) and RMD
- * (enumeration + K6) stage totals from a second pass with per-stage events.  launches: kernels
- * launched per pass. */
-int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int iters, float ms[3],
-                          int *launches);
-
-/* Measurement, end to end: `iters` frames through the public calls above -- hevcdl_submit_frame_u8 from the HOST
- * planes y/u/v[i % nbuf] (pinned or pageable, caller-owned), hevcdl_frame_view_get(want_pus) on the oldest frame
- * once `depth` frames are in flight, hevcdl_release_frame -- timed with the host's steady clock from the first
- * submit to the last view.  Frame ids first_id .. first_id+iters-1.  seconds: wall time; d2h_bytes: bytes of the
- * views read; checksum: a value folded from every view so the reads cannot be elided. */
-int hevcdl_bench_e2e(hevcdl_ctx *ctx, int first_id, int iters, int depth, int nbuf, const uint8_t *const *y,
-                     const uint8_t *const *u, const uint8_t *const *v, int stride_y, int stride_c, double *seconds,
-                     uint64_t *d2h_bytes, uint64_t *checksum);
-
-/* Test hook (tensor-core path only): copy one L2-resident intermediate of the most recent frame to
- * the host -- which = 0: conv1/conv64 output planes ("cat"), 1: conv2 output planes, 2: conv3
- * features in the fc1 operand layout.  *size receives the byte size; dst may be NULL to query it. */
-int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size_t *size);
-
-/* Test hook: run the RMD pass (K6) of a finished frame again with caller-supplied labels [nctu*16] instead of the CNN's --
- * the reference's own interface hands labels over as files (use_model.py:121-125), and the CNN never predicts some
- * cases (64x64 CUs on ordinary content) that K6 must still handle.  Synchronous; afterwards the frame's label and PU
- * getters return the new labels and their PU lists. */
-int hevcdl_debug_rerun_rmd(hevcdl_ctx *ctx, int frame, const uint8_t *labels);
+/* Pin the calling thread to the CPUs of `device`'s NUMA node (what hevcdl_cfg.numa_bind does inside hevcdl_create),
+ * for callers that allocate their own pinned frame buffers before creating a context.  Returns the node (>= 0), or a
+ * negative hevcdl_status when the topology cannot be read (single-node hosts report node 0 or -1 in sysfs: no-op, 0). */
+int hevcdl_numa_bind_thread(int device);
 
 int hevcdl_get_stats(hevcdl_ctx *ctx, hevcdl_stats_t *out);
-/* CUDA stream handle (cudaStream_t) of the context, for callers that time with their own events */
-void *hevcdl_stream(hevcdl_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -169,3 +169,31 @@ def frame_rmd(pic, labels, ctu_begin=0, ctu_end=None):
     k = lib().oracle_frame_rmd(np.ascontiguousarray(pic), W, H, np.ascontiguousarray(labels, np.uint8),
                                ctu_begin, ctu_end, pu, satd)
     return pu[:k].copy(), satd[:k].copy()
+
+
+def label_parity(labels, ref_labels, margins, eps, logits=None, ref_logits=None):
+    """Parity statistics of device labels against the oracle's (checker side of tests/ and of bench.py's `parity` key).
+    margins [nctu,16]: the oracle's argmax margins (top logit minus runner-up, per 16x16 block).  The reference's fix-up
+    rules (use_model.py:102-119) couple the 16 labels of a CTU, so a CTU must match whenever ALL its margins exceed eps.
+    With both logit arrays the argmax decisions themselves are compared: `argmax_flips` and the largest oracle margin
+    among the flipped ones (`max_flipped_margin`) -- the evidence eps is set from."""
+    labels, ref_labels = np.asarray(labels), np.asarray(ref_labels)
+    n = len(labels)
+    mar = np.asarray(margins).reshape(n, -1)
+    diff_ctu = (labels != ref_labels).any(axis=1)
+    safe = mar.min(axis=1) > eps
+    out = {"ctus": int(n), "labels": int(labels.size), "labels_differing": int((labels != ref_labels).sum()),
+           "ctus_differing": int(diff_ctu.sum()), "eps": float(eps), "ctus_all_margins_above_eps": int(safe.sum()),
+           "ctus_differing_above_eps": int((diff_ctu & safe).sum()),
+           "max_min_margin_of_differing_ctu": float(mar.min(axis=1)[diff_ctu].max()) if diff_ctu.any() else 0.0}
+    if logits is not None and ref_logits is not None:
+        a = np.asarray(logits).reshape(n, 16, 4).argmax(axis=2)          # [ctu][quadrant*4 + group] -> digit (first maximum)
+        b = np.asarray(ref_logits).reshape(n, 16, 4).argmax(axis=2)
+        flip = a != b
+        # margins are stored per label position (4x4 raster); group g of quadrant q sits at SCATTER[q][g]
+        scatter = np.array([0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15])
+        mg = mar[:, scatter]
+        out["argmax_flips"] = int(flip.sum())
+        out["max_flipped_margin"] = float(mg[flip].max()) if flip.any() else 0.0
+        out["max_abs_dlogit"] = float(np.abs(np.asarray(logits) - np.asarray(ref_logits)).max())
+    return out

@@ -9,18 +9,26 @@ import pytest
 from conftest import ROOT
 
 
-def test_library_exports_every_declared_symbol(built, host):
-    hdr = open(os.path.join(ROOT, "include", "hevcdl.h")).read()
+def _declared(header):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(hevcdl_[a-z0-9_]+)\s*\(", hdr))
-    assert declared == set(host.EXPORTS), declared ^ set(host.EXPORTS)
+    return set(re.findall(r"\b(hevcdl_[a-z0-9_]+)\s*\(", hdr))
+
+
+def test_library_exports_every_declared_symbol(built, host):
+    public, internal = _declared("hevcdl.h"), _declared("hevcdl_internal.h")
+    assert public == set(host.EXPORTS), public ^ set(host.EXPORTS)
+    assert internal == set(host.EXPORTS_INTERNAL), internal ^ set(host.EXPORTS_INTERNAL)
+    assert not any("bench" in n or "debug" in n for n in public)      # measurement / test hooks stay out of the boundary
     lib = C.CDLL(built)
-    for name in declared:
+    for name in public | internal:
         assert getattr(lib, name) is not None
 
 
 def test_struct_layouts_match_header(host):
-    assert C.sizeof(host.Cfg) == 9 * 4 + 4 + 8              # 9 int32, padding, the weights pointer
+    assert C.sizeof(host.Cfg) == 12 * 4 + 8                 # 12 int32, the weights pointer
+    hdr = open(os.path.join(ROOT, "include", "hevcdl.h")).read()
+    assert int(re.search(r"#define HEVCDL_ABI_VERSION (\d+)", hdr).group(1)) == host.ABI_VERSION
     assert host.PU_DTYPE.itemsize == 8
     assert C.sizeof(host.Stats) == 48
 
@@ -37,9 +45,11 @@ def test_create_fails_loudly_without_gpu(built, host):
 def test_create_rejects_bad_cfg(built, host):
     lib = host.load_library()
     h = C.c_void_p()
-    cfg = host.Cfg(2, 0, 417, 240, 1, 0, 1, 0, 1, b"x")       # width not a multiple of 8
+    cfg = host.Cfg(host.ABI_VERSION, 0, 417, 240, 1, 0, 1, 0, 1, 0, 0, 0, b"x")       # width not a multiple of 8
     assert lib.hevcdl_create(C.byref(cfg), C.byref(h)) == -1
-    cfg = host.Cfg(99, 0, 416, 240, 1, 0, 1, 0, 1, b"x")      # wrong ABI version
+    cfg = host.Cfg(99, 0, 416, 240, 1, 0, 1, 0, 1, 0, 0, 0, b"x")      # wrong ABI version
+    assert lib.hevcdl_create(C.byref(cfg), C.byref(h)) == -1
+    cfg = host.Cfg(host.ABI_VERSION, 0, 416, 240, 1, 0, 1, 0, 1, 8, 0, 0, b"x")       # unknown output flag
     assert lib.hevcdl_create(C.byref(cfg), C.byref(h)) == -1
     assert lib.hevcdl_status_str(-2).decode().startswith("no usable CUDA device")
 

@@ -10,8 +10,14 @@ from conftest import GOLDEN, unsafe_label_mismatches
 
 pytestmark = pytest.mark.gpu
 
-# label parity is demanded wherever the oracle's argmax margin exceeds eps (logit units)
-EPS = {0: 1e-3, 1: 0.25}
+# Label parity is demanded in every CTU whose 16 oracle argmax margins all exceed eps (logit units).  eps is set from
+# evidence: over 8 mixed 1080p frames + noise + flat (profiles/r01_label_parity_1080p.json) and the 100-frame 1080p
+# sequence of the BD-rate sweep the largest oracle margin of an argmax the bf16 tensor-core path flipped is 0.044; fp32
+# flips nothing above 1e-3.  On top of the margin rule the tests bound HOW MANY labels / CTUs may differ at all.
+EPS = {0: 1e-3, 1: 0.1}
+# measured on the 1080p frame below: bf16 0.19 % of labels / 1.1 % of CTUs; fp32 none
+MAX_LABEL_FRAC = {0: 0.0, 1: 0.005}
+MAX_CTU_FRAC = {0: 0.0, 1: 0.025}
 
 
 def _precisions(host):
@@ -28,32 +34,37 @@ def _mk(host, w, h, prec, **kw):
 
 
 @pytest.mark.parametrize("prec", [0, 1])
-def test_labels_vs_unmodified_use_model_golden(built, host, prec):
+def test_labels_vs_unmodified_use_model_golden(built, host, oracle, weights, prec):
+    """Labels written by the UNMODIFIED use_model.py for this picture (tools/gen_golden.py).  fp32: identical.  bf16: the
+    28 CTUs of this picture come out identical too (measured); should an operand rounding ever move one, it may only be a
+    CTU holding an argmax margin <= eps."""
     g = np.load(os.path.join(GOLDEN, "cnn_labels_416x240.npz"))
     dp = _mk(host, 416, 240, prec, rmd=False)
     lab = dp.predict_frame(g["Y"], g["U"], g["V"])
+    dp.close()
     if prec == 0:
         assert (lab == g["labels"]).all()
     else:
-        assert (lab != g["labels"]).any(axis=1).mean() < 0.1      # CTUs whose labels moved (bf16 operands)
-    dp.close()
+        _, _, mar = oracle.frame_labels(weights, g["Y"], g["U"], g["V"], want_logits=True)
+        rep = oracle.label_parity(lab, g["labels"], mar, EPS[1])
+        assert rep["ctus_differing_above_eps"] == 0 and rep["ctus_differing"] <= 1, rep
 
 
 @pytest.mark.parametrize("prec", [0, 1])
 def test_logits_and_labels_vs_oracle_1080p(built, host, oracle, weights, pkg, prec):
+    """BASELINE configs[1]: ALL 510 CTUs of the 1080p frame against the oracle (OpenMP C: seconds), both precisions."""
     Y, U, V = pkg.synth.synth_frame(1920, 1080, 0)
     dp = _mk(host, 1920, 1080, prec, rmd=False)
     lab, lg = dp.predict_frame(Y, U, V, want_logits=True)
     dp.close()
-    # oracle on a bounded sample of CTUs (3 rows incl. the partial bottom row) -- seconds on CPU
-    rows = (0, 8, 16)
-    for r in rows:
-        a, b = r * 30, r * 30 + 30
-        olab, olg, mar = oracle.frame_labels(weights, Y, U, V, a, b, want_logits=True)
-        d = np.abs(lg[a:b] - olg[a:b]).max()
-        assert d < (2e-3 if prec == 0 else 1.0), d
-        nbad, nsafe = unsafe_label_mismatches(lab[a:b], olab[a:b], mar[a:b], EPS[prec])
-        assert nbad == 0 and nsafe > 0, (r, nbad, nsafe)
+    olab, olg, mar = oracle.frame_labels(weights, Y, U, V, want_logits=True)
+    rep = oracle.label_parity(lab, olab, mar, EPS[prec], lg, olg)
+    print("1080p label parity prec=%d: %s" % (prec, rep))
+    assert rep["max_abs_dlogit"] < (2e-3 if prec == 0 else 0.25), rep
+    assert rep["ctus_differing_above_eps"] == 0 and rep["ctus_all_margins_above_eps"] > 400, rep
+    assert rep["max_flipped_margin"] <= EPS[prec], rep
+    assert rep["labels_differing"] <= MAX_LABEL_FRAC[prec] * rep["labels"], rep
+    assert rep["ctus_differing"] <= MAX_CTU_FRAC[prec] * rep["ctus"], rep
 
 
 @pytest.mark.parametrize("kind", ["noise", "flat"])
@@ -268,12 +279,13 @@ def test_full_size_properties_4k(built, host, pkg):
 
 
 @pytest.mark.parametrize("w,h", [(3840, 2160), (7680, 4320)])
-def test_tensor_core_path_and_k6_at_full_sizes(built, host, oracle, weights, pkg, w, h):
-    """BASELINE configs[3]/[4] picture sizes (2040 / 8160 CTUs) through the tensor-core CNN and K6: labels against
-    the oracle on sampled CTU rows (incl. the partial bottom row), K6 PU lists + SATDs bit-exact against the oracle on
-    the same rows, per-CTU offsets consistent over the whole frame, and every PU ranked."""
+@pytest.mark.parametrize("prec", [0, 1])
+def test_cnn_and_k6_at_full_sizes(built, host, oracle, weights, pkg, w, h, prec):
+    """BASELINE configs[3]/[4] picture sizes (2040 / 8160 CTUs) through the CNN (fp32 CUDA-core and bf16 tensor-core) and
+    K6: labels against the oracle on sampled CTU rows (incl. the partial bottom row), K6 PU lists + SATDs bit-exact against
+    the oracle on the same rows, per-CTU offsets consistent over the whole frame, and every PU ranked."""
     Y, U, V = pkg.synth.synth_frame(w, h, 1)
-    dp = _mk(host, w, h, 1, rmd=True, slots=1)
+    dp = _mk(host, w, h, prec, rmd=True, slots=1)
     dp.submit(0, Y, U, V)
     v = dp.view(0)
     lab, lg, off, pus, satd, cand = v["labels"], v["logits"], v["ctu_off"], v["pus"], v["satd"], v["cand"]
@@ -287,9 +299,12 @@ def test_tensor_core_path_and_k6_at_full_sizes(built, host, oracle, weights, pkg
     for r in (0, ch // 2, ch - 1):
         a, b = r * cw, r * cw + min(cw, 24)
         olab, olg, mar = oracle.frame_labels(weights, Y, U, V, a, b, want_logits=True)
-        assert np.abs(lg[a:b] - olg[a:b]).max() < 1.0
-        nbad, nsafe = unsafe_label_mismatches(lab[a:b], olab[a:b], mar[a:b], EPS[1])
-        assert nbad == 0 and nsafe > 0, (r, nbad, nsafe)
+        rep = oracle.label_parity(lab[a:b], olab[a:b], mar[a:b], EPS[prec], lg[a:b], olg[a:b])
+        assert rep["max_abs_dlogit"] < (2e-3 if prec == 0 else 0.25), rep
+        assert rep["ctus_differing_above_eps"] == 0 and rep["ctus_all_margins_above_eps"] > 0, (r, rep)
+        assert rep["max_flipped_margin"] <= EPS[prec], (r, rep)
+        if prec == 0:
+            assert rep["labels_differing"] == 0, (r, rep)
         opu, osatd = oracle.frame_rmd(Y, lab, a, b)
         sl = slice(off[a], off[b])
         assert len(opu) == off[b] - off[a]
@@ -354,7 +369,7 @@ def test_odd_geometries_vs_oracle(built, host, oracle, weights, pkg, w, h, prec)
         dp.release(0); dp.close()
         if not fix:
             olab, olg, mar = oracle.frame_labels(weights, Y, U, V, want_logits=True)
-            assert np.abs(lg - olg).max() < (2e-3 if prec == 0 else 1.0)
+            assert np.abs(lg - olg).max() < (2e-3 if prec == 0 else 0.25)
             assert unsafe_label_mismatches(lab, olab, mar, EPS[prec])[0] == 0
         opu, osatd = oracle.frame_rmd(Y, lab)
         assert len(opu) == len(pus)

@@ -143,9 +143,11 @@ def test_sidecar_parses_bitstream_cfg_by_line_index_and_resets_pred(tmp_path, mo
     import importlib
     sidecar = importlib.import_module("hevc-deep-learning-pipeline_b200.sidecar")
     monkeypatch.chdir(tmp_path)
-    (tmp_path / "bitstream.cfg").write_text(BITSTREAM_CFG.format(yuv="C:\\\\seq\\\\a.yuv", w=416, h=240, n=6))
+    (tmp_path / "bitstream.cfg").write_text(BITSTREAM_CFG.format(yuv="C:\\seq\\a.yuv", w=416, h=240, n=6))
     cfg = sidecar.parse_bitstream_cfg()
-    assert cfg == {"input": "C:\\\\seq\\\\a.yuv", "frame_rate": "30", "width": 416, "height": 240, "frames": 6}
+    assert cfg == {"input": "C:/seq/a.yuv", "frame_rate": "30", "width": 416, "height": 240, "frames": 6}   # separators turned round
+    (tmp_path / "bitstream.cfg").write_text(BITSTREAM_CFG.format(yuv=".\\Flowervase_416x240_30.yuv", w=416, h=240, n=6))
+    assert sidecar.parse_bitstream_cfg()["input"] == "Flowervase_416x240_30.yuv"                          # the reference's own bitstream.cfg:1
     (tmp_path / "pred").mkdir(); (tmp_path / "pred" / "stale").mkdir()
     sidecar.main(["gen_frames"])
     assert os.path.isdir("pred") and os.listdir("pred") == []
@@ -171,3 +173,35 @@ def test_unmodified_reference_encoder_with_the_b200_sidecar(tmp_path, built, pkg
     assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-600:], rb["stderr"][-400:])
     assert sorted(os.listdir(a / "pred")) == ["0", "1", "2"] and len(os.listdir(a / "pred" / "0")) == 6
     assert ra["sha1"] == rb["sha1"]
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_dropin_lookahead_prefetches_frames_and_keeps_the_bitstream(tmp_path, built, host, pkg):
+    """a reader thread in the binding preads frames n+1.. of the encoder's input file and submits them
+    while HM encodes frame n, so only frame 0 waits for the device.  The stream must stay byte-identical to the reference's
+    (fp32 labels), with and without lookahead; a wrong HEVCDL_INPUT must be detected (hash mismatch) and ignored."""
+    import re
+    w, h, n = 256, 192, 6
+    frames = [pkg.synth.synth_frame(w, h, 80 + i) for i in range(n)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    hm_util.write_yuv(str(b / "other.yuv"), frames[::-1])
+    dp = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=False)
+    for f, (Y, U, V) in enumerate(frames):
+        hm_util.write_pred(str(a / "pred"), f, dp.predict_frame(Y, U, V, frame=f))
+    dp.close()
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, n, 32)
+    assert ra["rc"] == 0
+    r1 = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, n, 32, out="la.bin", env={"HEVCDL_VERBOSE": "1"})
+    r0 = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, n, 32, out="nola.bin", env={"HEVCDL_VERBOSE": "1", "HEVCDL_LOOKAHEAD": "0"})
+    r2 = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, n, 32, out="bad.bin", env={"HEVCDL_VERBOSE": "1", "HEVCDL_INPUT": "other.yuv"})
+    for r in (r0, r1, r2):
+        assert r["rc"] == 0 and r["sha1"] == ra["sha1"], r["stderr"][-400:]
+    m = re.search(r"lookahead (\d+): (\d+) frames were on the device before HM asked, (\d+) uploaded from HM's planes, (\d+) mismatches", r1["stderr"])
+    assert m and int(m.group(1)) == 3 and int(m.group(2)) == n - 1 and int(m.group(3)) == 1 and int(m.group(4)) == 0, r1["stderr"][-300:]
+    m = re.search(r"lookahead (\d+): (\d+) frames were on the device", r0["stderr"])
+    assert m and int(m.group(1)) == 0 and int(m.group(2)) == 0
+    assert "lookahead disabled" in r2["stderr"]
