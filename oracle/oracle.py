@@ -59,6 +59,12 @@ def lib():
     return _LIB
 
 
+def set_threads(n):
+    """Threads of the OpenMP loops (0 = all cores)."""
+    lib().oracle_set_threads.argtypes = [C.c_int]
+    lib().oracle_set_threads(int(n))
+
+
 def load_weights(path):
     raw = open(path, "rb").read()
     assert raw[:8] == b"HDLW0001", "bad weight blob"

@@ -48,7 +48,17 @@ class TorchConvNet2:
         return F.linear(out, p["f3w"], p["f3b"])
 
     @torch.no_grad()
-    def frame_labels(self, Y, U, V, ctu_begin, ctu_end):
+    def sidecar_ctus(self, Y, U, V, ctu_begin, ctu_end, pred_dir, frame=0):
+        """The sidecar's whole per-CTU job (use_model.py:86-127) for CTUs [ctu_begin, ctu_end): crop, ToTensor, four
+        batch-1 forwards, label rules AND the per-CTU handshake file (written under a temporary name, then renamed)."""
+        import os
+        d = os.path.join(pred_dir, str(frame))
+        os.makedirs(d, exist_ok=True)
+        lab = self.frame_labels(Y, U, V, ctu_begin, ctu_end, _write_dir=d)
+        return lab
+
+    @torch.no_grad()
+    def frame_labels(self, Y, U, V, ctu_begin, ctu_end, _write_dir=None):
         """use_model.py:86-119 for CTUs [ctu_begin, ctu_end): stage RGB (oracle K0 definition), four
         batch-1 forwards per CTU, argmax + fix-ups (C oracle for the integer rules)."""
         H, W = Y.shape
@@ -62,4 +72,10 @@ class TorchConvNet2:
                 oy, ox = (q // 2) * 32, (q % 2) * 32
                 lg[q] = self.forward(x64[:, :, oy:oy + 32, ox:ox + 32].contiguous(), x64)[0].numpy()
             labels[a - ctu_begin], _ = _o.ctu_labels(lg)
+            if _write_dir is not None:                                  # use_model.py:121-125
+                import os
+                tmp = os.path.join(_write_dir, "ctu.txt")
+                with open(tmp, "w") as f:
+                    f.write("".join("%d " % v for v in labels[a - ctu_begin]))
+                os.rename(tmp, os.path.join(_write_dir, "ctu%d.txt" % a))
         return labels
