@@ -111,8 +111,11 @@ __device__ __forceinline__ uint4 pack8_bf16(const float *y) {
 // ================================================================================================
 constexpr int P64_PITCH = 68, P64_BYTES = 68 * 68 * 4;   // (R,G) or (B,0) bf16 pairs, 2-pixel zero halo
 constexpr int P1_PITCH = 36, P1_BYTES = 36 * 36 * 4;
+// raw CTU tiles as the TMA engine delivers them, double-buffered: Y 64x64, Cb 32x32, Cr 32x32 (u8)
+constexpr int RAW_Y = 0, RAW_U = 4096, RAW_V = 5120, RAW_BYTES = 6144;
 constexpr int K1_W = 0, K1_P64 = K1_W + SZ_L1W, K1_P1 = K1_P64 + 2 * P64_BYTES, K1_RED = K1_P1 + 8 * P1_BYTES,
-              K1_BAR = K1_RED + 2 * 8 * 16 * 4, K1_SMEM = K1_BAR + 128;
+              K1_BAR = K1_RED + 2 * 8 * 16 * 4, K1_RAW = (K1_BAR + 128 + 127) / 128 * 128, K1_SMEM = K1_RAW + 2 * RAW_BYTES;
+#define STAGE_BAR_SYNC() asm volatile("bar.sync 2, 96;" ::: "memory")   // the three staging warps of K1
 
 // 8 epilogue warps (warp = TMEM lane quarter + 4 * channel half) + 1 TMA/MMA warp + 3 staging warps.  A 16-epilogue-warp
 // variant (4 channels per thread) was measured slower (40.9 vs 37 us per 1080p frame): twice the TMEM load instructions and
@@ -124,7 +127,8 @@ constexpr int K1_W = 0, K1_P64 = K1_W + SZ_L1W, K1_P1 = K1_P64 + 2 * P64_BYTES, 
 constexpr int K1_THREADS = 12 * 32, K1_MMA_WARP = 8, K1_STAGE_THREADS = 96, K1_STAGE_ITERS = (1024 + K1_STAGE_THREADS - 1) / K1_STAGE_THREADS;
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
-k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t *__restrict__ blob, uint8_t *__restrict__ cat) {
+k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo, int pitch, int cpitch, const uint8_t *__restrict__ blob,
+        uint8_t *__restrict__ cat) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
@@ -133,6 +137,7 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
   uint64_t *bar_w = bar_full + 4;
   uint64_t *bar_pfull = bar_full + 5;                               // [2] conv64 planes / quadrant planes staged (3 staging warps)
   uint64_t *bar_pfree = bar_full + 7;                               // [2] ... no longer read by the tensor core
+  uint64_t *bar_raw = bar_full + 9;                                 // [2] raw Y / Cb / Cr tiles of a CTU landed (TMA)
   float *red = reinterpret_cast<float *>(sm + K1_RED);              // [2][8 warps][16]
   const float *fp = reinterpret_cast<const float *>(blob + OFF_F32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -145,6 +150,7 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
     mbar_init(bar_w, 1);
     mbar_init(&bar_pfull[0], K1_STAGE_THREADS / 32); mbar_init(&bar_pfull[1], K1_STAGE_THREADS / 32);
     mbar_init(&bar_pfree[0], 1); mbar_init(&bar_pfree[1], 1);
+    mbar_init(&bar_raw[0], 1); mbar_init(&bar_raw[1], 1);
     mbar_init_fence();
   }
   if (warp == K1_MMA_WARP) tmem_alloc(&tmem_slot, 512);
@@ -165,14 +171,45 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
 
   if (warp > K1_MMA_WARP) {
     // ---- staging: (R,G) and (B,0) planes of the CTU and of its four zero-padded quadrants ----------
+    // The raw tiles come in by TMA (cp.async.bulk.tensor, one 64x64 Y box and two 32x32 chroma boxes per CTU, zeros
+    // outside the picture), one CTU ahead of the conversion: replaces the frame dump + PIL crops of the reference
+    // (gen_frames.py:21, use_model.py:78-95).  -DHEVCDL_K1_LDG: the former __ldg staging, kept for the A/B measurement.
     const int stid = tid - (K1_MMA_WARP + 1) * 32;
     uint32_t j = 0;                               // CTUs done by this CTA
+#ifndef HEVCDL_K1_LDG
+    auto issue_raw = [&](int ctu, uint32_t buf) {   // one elected thread: the three boxes of a CTU
+      const int f = ctu / geo.nctu, ctu_l = ctu - f * geo.nctu;
+      const int cx = ctu_l % geo.ctu_w, cy = ctu_l / geo.ctu_w;
+      uint8_t *raw = sm + K1_RAW + buf * RAW_BYTES;
+      mbar_expect_tx(&bar_raw[buf], RAW_BYTES);
+      tma_load_2d(raw + RAW_Y, &tm.y[f], cx * 64, cy * 64, &bar_raw[buf]);
+      tma_load_2d(raw + RAW_U, &tm.u[f], cx * 32, cy * 32, &bar_raw[buf]);
+      tma_load_2d(raw + RAW_V, &tm.v[f], cx * 32, cy * 32, &bar_raw[buf]);
+    };
+    if (stid == 0 && (int)blockIdx.x < total) issue_raw(blockIdx.x, 0);
+#endif
 #pragma unroll 1
     for (int ctu = blockIdx.x; ctu < total; ctu += gridDim.x, j++) {
       const int f = ctu / geo.nctu, ctu_l = ctu - f * geo.nctu;
-      const uint8_t *__restrict__ Y = fb.Y[f], *__restrict__ U = fb.U[f], *__restrict__ V = fb.V[f];
       const int ctu_x = ctu_l % geo.ctu_w, ctu_y = ctu_l / geo.ctu_w;
       uint32_t yv[K1_STAGE_ITERS], uv[K1_STAGE_ITERS], vv[K1_STAGE_ITERS];
+#ifndef HEVCDL_K1_LDG
+      STAGE_BAR_SYNC();                           // every staging thread has read the other raw buffer (CTU j-1)
+      if (stid == 0 && ctu + (int)gridDim.x < total) issue_raw(ctu + gridDim.x, (j + 1) & 1);
+      MBAR_WAIT(&bar_raw[j & 1], (j >> 1) & 1, 13);
+      const uint8_t *raw = sm + K1_RAW + (j & 1) * RAW_BYTES;
+#pragma unroll
+      for (int k = 0; k < K1_STAGE_ITERS; k++) {
+        const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
+        yv[k] = 0; uv[k] = 0; vv[k] = 0;
+        if (it < 1024) {
+          yv[k] = *reinterpret_cast<const uint32_t *>(raw + RAW_Y + y * 64 + x4);
+          uv[k] = *reinterpret_cast<const uint16_t *>(raw + RAW_U + (y >> 1) * 32 + (x4 >> 1));
+          vv[k] = *reinterpret_cast<const uint16_t *>(raw + RAW_V + (y >> 1) * 32 + (x4 >> 1));
+        }
+      }
+#else
+      const uint8_t *__restrict__ Y = fb.Y[f], *__restrict__ U = fb.U[f], *__restrict__ V = fb.V[f];
 #pragma unroll
       for (int k = 0; k < K1_STAGE_ITERS; k++) {  // raw samples first: the loads fly while the planes are still being read
         const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
@@ -184,6 +221,7 @@ k_tc_l1(const FrameBatch fb, FrameGeom geo, int pitch, int cpitch, const uint8_t
           vv[k] = __ldg(reinterpret_cast<const uint16_t *>(V + (size_t)(gy >> 1) * cpitch + (gx >> 1)));
         }
       }
+#endif
       uint32_t rg[K1_STAGE_ITERS][4], b0[K1_STAGE_ITERS][4];
 #pragma unroll
       for (int k = 0; k < K1_STAGE_ITERS; k++) {
@@ -1002,14 +1040,14 @@ inline cudaError_t tc_launch_pdl(void (*kernel)(KArgs...), int grid, int threads
 
 // Queue the four CNN kernels of one frame (programmatic dependent launch: each kernel's prologue overlaps its
 // predecessor's tail).  *launches += kernels launched; returns the first launch error.
-inline cudaError_t tc_launch(const TcParams &p, const FrameBatch &fb, FrameGeom g, int pitch, int cpitch, int boundary_fix, int num_sms,
+inline cudaError_t tc_launch(const TcParams &p, const FrameBatch &fb, const TmapBatch &tm, FrameGeom g, int pitch, int cpitch, int boundary_fix, int num_sms,
                              cudaStream_t st, int *launches) {
   FrameGeom gt = g;                              // K2/K3 only loop over CTUs: give them the launch's total
   gt.nctu = g.nctu * fb.n;
   const int grid = gt.nctu < num_sms ? gt.nctu : num_sms;
   const int npad = ((4 * gt.nctu + 127) / 128) * 128;   // <= p.npad (sized for the largest batch); the feats layout follows the launch
   cudaError_t e;
-  if ((e = tc_launch_pdl(k_tc_l1, grid, K1_THREADS, K1_SMEM, st, fb, g, pitch, cpitch, p.blob, p.cat)) != cudaSuccess) return e;
+  if ((e = tc_launch_pdl(k_tc_l1, grid, K1_THREADS, K1_SMEM, st, fb, tm, g, pitch, cpitch, p.blob, p.cat)) != cudaSuccess) return e;
   if ((e = tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2)) != cudaSuccess) return e;
   if ((e = tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad)) != cudaSuccess) return e;
   if (npad / FcSmall::NT > num_sms)             // more 32-sample tiles than SMs: 64-sample tiles halve the weight traffic

@@ -1,5 +1,6 @@
 // common.cuh -- shared definitions for libhevcdl.so (sm_100a only).
 #pragma once
+#include <cuda.h>           // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -86,6 +87,12 @@ struct FrameBatch {
   float *logits[MAX_BATCH];
   uint32_t *ctu_cnt[MAX_BATCH];   // may be null (rmd = 0)
   int n;
+};
+
+// TMA descriptors of the frames of a launch (K1 stages every CTU's 64x64 Y tile and 32x32 Cb / Cr tiles with
+// cp.async.bulk.tensor; samples outside the picture arrive as zeros).  Passed as a __grid_constant__ kernel parameter.
+struct TmapBatch {
+  CUtensorMap y[MAX_BATCH], u[MAX_BATCH], v[MAX_BATCH];
 };
 
 // The same for the RMD kernels: one plan + one items launch serve all frames of a batch (one work-item queue).

@@ -60,6 +60,7 @@ struct Slot {
   uint8_t *hCand = nullptr;
   size_t hPuCap = 0;
   bool pusFetched = false;
+  CUtensorMap tmY, tmU, tmV;           // TMA descriptors of the three device planes (tensor-core path: K1 stages by cp.async.bulk.tensor)
   bool timed = false;                  // head of a launch batch: its evT0..evT2 bracket the batch's stages
   cudaEvent_t evCnn = nullptr, evIn = nullptr, evLabels = nullptr, evRmd = nullptr, evT0 = nullptr, evT1 = nullptr, evT2 = nullptr;
 };
@@ -170,12 +171,48 @@ int load_weights(hevcdl_ctx *ctx) {
   return HEVCDL_OK;
 }
 
+// 2-D u8 tensor map of one plane: dims (w, h), row pitch `pitch` bytes, box bw x bh, no swizzle, zero fill outside.
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so that libcuda is not a link
+// dependency of this library.
+int make_plane_tmap(hevcdl_ctx *ctx, CUtensorMap *tm, const uint8_t *base, int w, int h, int pitch, int bw, int bh) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled enc = nullptr;
+  if (!enc) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { ctx->err = "cuTensorMapEncodeTiled not available in this driver"; return HEVCDL_E_CUDA; }
+    enc = (EncodeTiled)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh}, estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[128];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (CUresult %d) for a %dx%d plane, pitch %d", (int)r, w, h, pitch);
+    ctx->err = b;
+    return HEVCDL_E_CUDA;
+  }
+  return HEVCDL_OK;
+}
+
 int alloc_slot(hevcdl_ctx *ctx, Slot &s) {
   const FrameGeom &g = ctx->geo;
   const size_t ybytes = (size_t)ctx->pitch * g.H, cbytes = (size_t)ctx->cpitch * (g.H / 2);
   CK(cudaMalloc(&s.dY, ybytes + 2 * cbytes));
   CK(cudaMemset(s.dY, 0, ybytes + 2 * cbytes));
   s.dU = s.dY + ybytes; s.dV = s.dU + cbytes;
+  if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
+    int rc;
+    if ((rc = make_plane_tmap(ctx, &s.tmY, s.dY, g.W, g.H, ctx->pitch, 64, 64)) ||
+        (rc = make_plane_tmap(ctx, &s.tmU, s.dU, g.W / 2, g.H / 2, ctx->cpitch, 32, 32)) ||
+        (rc = make_plane_tmap(ctx, &s.tmV, s.dV, g.W / 2, g.H / 2, ctx->cpitch, 32, 32)))
+      return rc;
+  }
   CK(cudaMalloc(&s.dLabels, (size_t)g.nctu * 16));
   CK(cudaMalloc(&s.dLogits, (size_t)g.nctu * 64 * sizeof(float)));
   CK(cudaMalloc(&s.dCtuOff, ((size_t)g.nctu + 1) * sizeof(int)));
@@ -233,13 +270,18 @@ int launch_pipeline(hevcdl_ctx *ctx, Slot *const *sl, int n, bool timed, int *la
   if (timed) CK(cudaEventRecord(head.evT0, ctx->stream));
   if (ctx->cfg.precision == HEVCDL_PREC_BF16_TC) {
     FrameBatch fb{};
+    TmapBatch tm;
     fb.n = n;
+    for (int i = 0; i < MAX_BATCH; i++) {         // unused entries repeat the head's descriptors (never dereferenced)
+      const Slot &s = *sl[i < n ? i : 0];
+      tm.y[i] = s.tmY; tm.u[i] = s.tmU; tm.v[i] = s.tmV;
+    }
     for (int i = 0; i < n; i++) {
       Slot &s = *sl[i];
       fb.Y[i] = s.dY; fb.U[i] = s.dU; fb.V[i] = s.dV;
       fb.labels[i] = s.dLabels; fb.logits[i] = s.dLogits; fb.ctu_cnt[i] = ctx->cfg.rmd ? s.dCtuCnt : nullptr;
     }
-    CK(tc_launch(ctx->tc, fb, g, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, ctx->numSMs, ctx->stream, &launches));
+    CK(tc_launch(ctx->tc, fb, tm, g, ctx->pitch, ctx->cpitch, ctx->cfg.boundary_fix, ctx->numSMs, ctx->stream, &launches));
   } else {
     const int grid = g.nctu < 4 * ctx->numSMs ? g.nctu : 4 * ctx->numSMs;
     for (int i = 0; i < n; i++) {

@@ -153,6 +153,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
+// ---- 2-D tiled TMA load (cp.async.bulk.tensor): box at element coordinates (x, y) of the tensor described by `tmap`
+// (a CUtensorMap in kernel-parameter space, __grid_constant__) -> shared memory; elements outside the tensor arrive as
+// zeros and still count towards the barrier's transaction bytes (= the full box).
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&v);
