@@ -23,7 +23,7 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def build():
     """Compile the C restatement (gcc, seconds)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c")]
+    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c")]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so] + srcs + ["-lm"])
     return so
@@ -55,6 +55,12 @@ def lib():
         L.oracle_enum_ctu_pus.restype = C.c_int
         L.oracle_frame_rmd.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int, i32p, u32p]
         L.oracle_frame_rmd.restype = C.c_int
+        L.oracle_tq_matrix.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.oracle_tq_matrix.restype = C.c_int
+        L.oracle_tq_forward.argtypes = [i16p, C.c_int, C.c_int, i32p]
+        L.oracle_tq_inverse.argtypes = [i32p, C.c_int, C.c_int, i16p]
+        L.oracle_tq_tu.argtypes = [i16p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i16p]
+        L.oracle_tq_tu.restype = C.c_uint32
         _LIB = L
     return _LIB
 
@@ -203,3 +209,35 @@ def label_parity(labels, ref_labels, margins, eps, logits=None, ref_logits=None)
         out["max_flipped_margin"] = float(mg[flip].max()) if flip.any() else 0.0
         out["max_abs_dlogit"] = float(np.abs(np.asarray(logits) - np.asarray(ref_logits)).max())
     return out
+
+
+# ---- transform / quantisation core (oracle/tq_oracle.c) -------------------------------------------------------------
+TQ_FLAG_DST, TQ_FLAG_TSKIP, TQ_FLAG_INTER = 1, 2, 4
+
+
+def tq_matrix(n):
+    """The n-point HEVC core transform matrix [k][x]."""
+    return np.array([[lib().oracle_tq_matrix(n, k, x) for x in range(n)] for k in range(n)], np.int32)
+
+
+def tq_forward(resi, dst=False):
+    n = resi.shape[0]
+    out = np.zeros((n, n), np.int32)
+    lib().oracle_tq_forward(np.ascontiguousarray(resi, np.int16), n, int(dst), out)
+    return out
+
+
+def tq_inverse(coeff, dst=False):
+    n = coeff.shape[0]
+    out = np.zeros((n, n), np.int16)
+    lib().oracle_tq_inverse(np.ascontiguousarray(coeff, np.int32), n, int(dst), out)
+    return out
+
+
+def tq_tu(resi, qp, flags=0):
+    """One TU through transform, flat quantiser, dequantiser and inverse transform: (coeff, level, deq, rec, abs_sum)."""
+    n = resi.shape[0]
+    c, q, d = (np.zeros((n, n), np.int32) for _ in range(3))
+    r = np.zeros((n, n), np.int16)
+    s = lib().oracle_tq_tu(np.ascontiguousarray(resi, np.int16), int(n).bit_length() - 1, int(qp), int(flags), c, q, d, r)
+    return c, q, d, r, int(s)

@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Golden vectors of the transform / quantisation core, made by RUNNING THE REFERENCE in this
+container (needs /root/reference and `make -C oracle ref`); the fixtures travel, the reference does not.
+
+  tests/golden/tq_transform_ref.npz   random and extreme blocks through the reference's OWN xTrMxN / xITrMxN
+                                      (oracle/_ref/libtqref.so = tq_ref_harness.cpp linked with libhmref.a), every size + DST
+  tests/golden/tq_trace_192x128_qp32.npz   per-TU dumps printed by oracle/_ref/TAppEncoder_tqtrace (the reference built with
+                                      its own DEBUG_TRANSFORM_AND_QUANTISE switch, TComTrQuant.cpp:1496-1662) while encoding
+                                      the 192x128 fixture frame at QP 32 with --RDOQ=0 --RDOQTS=0 --SignHideFlag=0 (the flat
+                                      quantiser xQuant, :1126-1249): residual, transform output, levels and, where the
+                                      reference ran the inverse path, dequantised coefficients and reconstructed residual.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import hm_util  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def transform_vectors():
+    ref = C.CDLL(os.path.join(REFDIR, "libtqref.so"))
+    ref.tqref_init()
+    ip = np.ctypeslib.ndpointer(np.int32, flags="C")
+    ref.tqref_forward.argtypes = [ip, ip, C.c_int, C.c_int]
+    ref.tqref_inverse.argtypes = [ip, ip, C.c_int, C.c_int]
+    rng = np.random.default_rng(20261017)
+    sizes, dsts, resi, coeff, icoeff, iresi = [], [], [], [], [], []
+    for N, cnt in ((4, 24), (8, 20), (16, 12), (32, 8)):
+        for dst in ((0, 1) if N == 4 else (0,)):
+            for t in range(cnt):
+                kind = t % 4
+                if kind == 0:
+                    blk = rng.integers(-255, 256, (N, N))
+                elif kind == 1:
+                    blk = rng.integers(-12, 13, (N, N))
+                elif kind == 2:
+                    blk = np.full((N, N), 255 if t % 8 < 4 else -255)
+                else:
+                    blk = rng.integers(0, 2, (N, N)) * 510 - 255
+                b = np.ascontiguousarray(blk, np.int32)
+                c = np.zeros((N, N), np.int32)
+                ref.tqref_forward(b.copy(), c, N, dst)
+                ci = np.ascontiguousarray(rng.integers(-32768, 32768, (N, N)) if kind != 1 else rng.integers(-400, 400, (N, N)), np.int32)
+                r = np.zeros((N, N), np.int32)
+                ref.tqref_inverse(ci.copy(), r, N, dst)
+                assert np.abs(r).max() <= 32768
+                sizes.append(N); dsts.append(dst)
+                resi.append(b.astype(np.int16).ravel()); coeff.append(c.ravel())
+                icoeff.append(ci.ravel()); iresi.append(r.astype(np.int16).ravel())
+    off = np.concatenate([[0], np.cumsum([s * s for s in sizes])]).astype(np.int64)
+    np.savez_compressed(os.path.join(GOLD, "tq_transform_ref.npz"), sizes=np.array(sizes, np.uint8), dst=np.array(dsts, np.uint8), off=off,
+                        resi=np.concatenate(resi), coeff=np.concatenate(coeff), icoeff=np.concatenate(icoeff), iresi=np.concatenate(iresi))
+    print("tq_transform_ref.npz:", len(sizes), "blocks")
+
+
+HDR = re.compile(r"^\d+: (\d+)x(\d+) channel (\d) TU (at input to transform|between transform and quantiser|at output of quantiser|"
+                 r"at input to dequantiser|between dequantiser and inverse-transform|at output of inverse-transform)$")
+STAGE = {"at input to transform": "resi", "between transform and quantiser": "coeff", "at output of quantiser": "level",
+         "at input to dequantiser": "level2", "between dequantiser and inverse-transform": "deq", "at output of inverse-transform": "rec"}
+
+
+def parse_trace(path):
+    recs, cur = [], None
+    with open(path) as f:
+        lines = f.read().split("\n")
+    i = 0
+    while i < len(lines):
+        m = HDR.match(lines[i])
+        if not m:
+            i += 1
+            continue
+        n, ch, st = int(m.group(1)), int(m.group(3)), STAGE[m.group(4)]
+        blk = np.array([[int(v) for v in lines[i + 1 + r].split()] for r in range(n)], np.int64)
+        assert blk.shape == (n, n), (i, blk.shape)
+        i += 1 + n
+        if st == "resi":
+            cur = {"n": n, "ch": ch, "resi": blk}
+            recs.append(cur)
+        else:
+            assert cur is not None and cur["n"] == n and cur["ch"] == ch, (i, st)
+            cur[st] = blk
+    return recs
+
+
+def trace_vectors(per_class=14):
+    g = np.load(os.path.join(GOLD, "rmd_trace_192x128_qp32.npz"))
+    Y, U, V = g["Y"], g["U"], g["V"]
+    H, W = Y.shape
+    qp = int(g["qp"])
+    with tempfile.TemporaryDirectory() as td:
+        hm_util.write_yuv(os.path.join(td, "in.yuv"), [(Y, U, V)])
+        hm_util.write_pred(os.path.join(td, "pred"), 0, g["labels"])
+        cmd = [os.path.join(REFDIR, "TAppEncoder_tqtrace"), "-c", hm_util.CFG, "-i", "in.yuv", "-wdt", str(W), "-hgt", str(H), "-fr", "30",
+               "-f", "1", "-q", str(qp), "-b", "t.bin", "--InputBitDepth=8", "--InputChromaFormat=420", "--Level=6.2", "--RDOQ=0",
+               "--RDOQTS=0", "--SignHideFlag=0"]
+        with open(os.path.join(td, "trace.txt"), "w") as f:
+            subprocess.check_call(cmd, cwd=td, stdout=f, stderr=subprocess.DEVNULL)
+        recs = parse_trace(os.path.join(td, "trace.txt"))
+    print("trace:", len(recs), "TUs")
+    # chroma QP of the reference for luma QP 32, ChromaQpOffset 0, 4:2:0 (TComRom.cpp g_aucChromaScale): 31
+    qpc = {32: 31}[qp]
+    rng = np.random.default_rng(7)
+    pick = []
+    classes = {}
+    for k, r in enumerate(recs):
+        if "level" not in r:
+            continue
+        tskip = r["n"] == 4 and (r["coeff"] == r["resi"] * 32).all() and r["resi"].any()
+        key = (r["n"], r["ch"], "rec" in r, bool(tskip))
+        classes.setdefault(key, []).append(k)
+    for key, idx in sorted(classes.items()):
+        sel = rng.permutation(idx)[:per_class if key[2] else 4]
+        pick += [(int(k), key) for k in sel]
+        print(key, len(idx), "->", len(sel))
+    sizes, chans, qps, flags, has_inv = [], [], [], [], []
+    resi, coeff, level, deq, rec = [], [], [], [], []
+    for k, key in pick:
+        r = recs[k]
+        n, ch = r["n"], r["ch"]
+        sizes.append(n); chans.append(ch); qps.append(qp if ch == 0 else qpc)
+        flags.append((2 if key[3] else (1 if (n == 4 and ch == 0) else 0)))      # oracle/tq_oracle.c TQ_FLAG_*: DST for 4x4 luma, TSKIP
+        has_inv.append(1 if "rec" in r else 0)
+        resi.append(r["resi"].astype(np.int16).ravel()); coeff.append(r["coeff"].astype(np.int32).ravel())
+        level.append(r["level"].astype(np.int32).ravel())
+        if "rec" in r:
+            assert (r["level2"] == r["level"]).all()
+            deq.append(r["deq"].astype(np.int32).ravel()); rec.append(r["rec"].astype(np.int16).ravel())
+        else:
+            deq.append(np.zeros(n * n, np.int32)); rec.append(np.zeros(n * n, np.int16))
+    off = np.concatenate([[0], np.cumsum([s * s for s in sizes])]).astype(np.int64)
+    np.savez_compressed(os.path.join(GOLD, "tq_trace_192x128_qp32.npz"), sizes=np.array(sizes, np.uint8), chan=np.array(chans, np.uint8),
+                        qp=np.array(qps, np.uint8), flags=np.array(flags, np.uint8), has_inv=np.array(has_inv, np.uint8), off=off,
+                        resi=np.concatenate(resi), coeff=np.concatenate(coeff), level=np.concatenate(level), deq=np.concatenate(deq),
+                        rec=np.concatenate(rec))
+    print("tq_trace_192x128_qp32.npz:", len(sizes), "TUs,", os.path.getsize(os.path.join(GOLD, "tq_trace_192x128_qp32.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    transform_vectors()
+    trace_vectors()
