@@ -16,6 +16,7 @@
 #include "cnn_tc.cuh"
 #include "common.cuh"
 #include "rmd.cuh"
+#include "tq.cuh"
 #include "../../include/hevcdl_internal.h"
 
 using namespace hevcdl;
@@ -87,6 +88,10 @@ struct hevcdl_ctx {
   int rmdBlocks = 0;                   // persistent grid of k_rmd_items: resident blocks per SM x SMs
   std::string err;
   hevcdl_stats_t stats{};
+  // scratch for hevcdl_tu_code
+  void *dTq = nullptr;
+  void *hTq = nullptr;                 // pinned mirror of dTq
+  size_t tqCap = 0;
   // scratch for hevcdl_rmd_exact
   void *dExact = nullptr;
   void *hExact = nullptr;              // pinned mirror of dExact
@@ -612,8 +617,9 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     if (s.evT1) cudaEventDestroy(s.evT1);
     if (s.evT2) cudaEventDestroy(s.evT2);
   }
-  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact);
+  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact); cudaFree(ctx->dTq);
   if (ctx->hExact) cudaFreeHost(ctx->hExact);
+  if (ctx->hTq) cudaFreeHost(ctx->hTq);
   tc_release(&ctx->tc);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
@@ -787,6 +793,57 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
   if (satd) memcpy(satd, hp + o_satd, (size_t)n * 35 * 4);
   if (cand) memcpy(cand, hp + o_cand, (size_t)n * 10);
   if (ncand) memcpy(ncand, hp + o_nc, n);
+  return HEVCDL_OK;
+}
+
+int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level,
+                   int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd) {
+  if (!ctx || n < 0 || (n && (!tus || !resi || !level || !rec || !abs_sum))) return HEVCDL_E_INVAL;
+  if (n == 0) return HEVCDL_OK;
+  cudaSetDevice(ctx->cfg.device);
+  for (int i = 0; i < n; i++) {
+    const hevcdl_tu &t = tus[i];
+    if (t.log2_size < 2 || t.log2_size > 5 || t.qp > 51 || (size_t)t.offset + ((size_t)1 << (2 * t.log2_size)) > nelem ||
+        ((t.flags & HEVCDL_TU_TSKIP) && t.log2_size != 2) || (t.offset & 1)) {
+      ctx->err = "hevcdl_tu: log2_size 2..5, qp 0..51, even offset inside nelem, transform skip only for 4x4";
+      return HEVCDL_E_INVAL;
+    }
+  }
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_tus = al((size_t)n * sizeof(hevcdl_tu)), b_resi = al(nelem * 2), b_coeff = coeff ? al(nelem * 4) : 0, b_level = al(nelem * 2),
+               b_deq = deq ? al(nelem * 4) : 0, b_rec = al(nelem * 2), b_asum = al((size_t)n * 4), b_ssd = ssd ? al((size_t)n * 8) : 0;
+  const size_t o_tus = 0, o_resi = o_tus + b_tus, o_coeff = o_resi + b_resi, o_level = o_coeff + b_coeff, o_deq = o_level + b_level,
+               o_rec = o_deq + b_deq, o_asum = o_rec + b_rec, o_ssd = o_asum + b_asum, total = o_ssd + b_ssd;
+  if (total > ctx->tqCap) {
+    cudaFree(ctx->dTq); ctx->dTq = nullptr; ctx->tqCap = 0;
+    if (ctx->hTq) { cudaFreeHost(ctx->hTq); ctx->hTq = nullptr; }
+    const size_t cap = total < (1u << 20) ? (1u << 20) : total + total / 2;
+    CK(cudaMalloc(&ctx->dTq, cap));
+    CK(cudaMallocHost(&ctx->hTq, cap));
+    ctx->tqCap = cap;
+  }
+  uint8_t *hp = (uint8_t *)ctx->hTq, *dp = (uint8_t *)ctx->dTq;
+  memcpy(hp + o_tus, tus, (size_t)n * sizeof(hevcdl_tu));
+  memcpy(hp + o_resi, resi, nelem * 2);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dp, hp, o_coeff, cudaMemcpyHostToDevice, st));
+  // gaps between TU blocks (if the caller's offsets leave any) come back as zeros, not as stale bytes
+  CK(cudaMemsetAsync(dp + o_coeff, 0, total - o_coeff, st));
+  const int grid = (n + TQ_WARPS - 1) / TQ_WARPS < 8 * ctx->numSMs ? (n + TQ_WARPS - 1) / TQ_WARPS : 8 * ctx->numSMs;
+  k_tu_code<<<grid, TQ_WARPS * 32, sizeof(TqBlockS), st>>>(n, (const hevcdl_tu *)(dp + o_tus), (const int16_t *)(dp + o_resi),
+                                                            coeff ? (int32_t *)(dp + o_coeff) : nullptr, (int16_t *)(dp + o_level),
+                                                            deq ? (int32_t *)(dp + o_deq) : nullptr, (int16_t *)(dp + o_rec),
+                                                            (uint32_t *)(dp + o_asum), ssd ? (uint64_t *)(dp + o_ssd) : nullptr);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(hp + o_coeff, dp + o_coeff, total - o_coeff, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (coeff) memcpy(coeff, hp + o_coeff, nelem * 4);
+  memcpy(level, hp + o_level, nelem * 2);
+  if (deq) memcpy(deq, hp + o_deq, nelem * 4);
+  memcpy(rec, hp + o_rec, nelem * 2);
+  memcpy(abs_sum, hp + o_asum, (size_t)n * 4);
+  if (ssd) memcpy(ssd, hp + o_ssd, (size_t)n * 8);
   return HEVCDL_OK;
 }
 

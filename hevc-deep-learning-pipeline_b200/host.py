@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_get_stats", "hevcdl_numa_bind_thread",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_get_stats", "hevcdl_numa_bind_thread",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
@@ -47,6 +47,8 @@ class FrameView(C.Structure):
                 ("satd", C.c_void_p), ("cand", C.c_void_p), ("nctu", C.c_int32), ("npu", C.c_int32)]
 
 
+TU_DTYPE = np.dtype([("log2_size", "u1"), ("qp", "u1"), ("flags", "u1"), ("reserved", "u1"), ("offset", "<u4")])
+TU_DST, TU_TSKIP, TU_INTER = 1, 2, 4
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("part", "u1"), ("ctu", "<u2")])
 
 
@@ -93,6 +95,7 @@ def load_library():
     L.hevcdl_stream.argtypes = [vp]
     L.hevcdl_stream.restype = vp
     L.hevcdl_numa_bind_thread.argtypes = [ip]
+    L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -243,6 +246,34 @@ class DepthPredictor:
                                            _ptr(mpm_add), float(sqrt_lambda), _ptr(satd), _ptr(cand), _ptr(ncand)),
                  "rmd_exact")
         return satd, cand, ncand
+
+    # -- transform-unit coding core --------------------------------------------------------------
+    def tu_code(self, blocks, qps, flags=None, want_coeff=True, want_deq=True):
+        """blocks: list of (N,N) int16 residual blocks (N = 4, 8, 16, 32); qps, flags: per block.  Forward transform, flat
+        quantiser, dequantiser, inverse transform (hevcdl_tu_code).  Returns dict of per-block lists coeff / level / deq /
+        rec plus arrays abs_sum, ssd."""
+        n = len(blocks)
+        tus = np.zeros(n, TU_DTYPE)
+        sizes = np.array([b.shape[0] for b in blocks], np.int64)
+        off = np.concatenate([[0], np.cumsum(sizes * sizes)])
+        tus["log2_size"] = [int(s).bit_length() - 1 for s in sizes]
+        tus["qp"] = qps
+        tus["flags"] = 0 if flags is None else flags
+        tus["offset"] = off[:-1]
+        nelem = int(off[-1])
+        resi = np.concatenate([np.asarray(b, np.int16).ravel() for b in blocks]) if n else np.zeros(0, np.int16)
+        coeff = np.zeros(nelem, np.int32) if want_coeff else None
+        level = np.zeros(nelem, np.int16)
+        deq = np.zeros(nelem, np.int32) if want_deq else None
+        rec = np.zeros(nelem, np.int16)
+        asum = np.zeros(n, np.uint32)
+        ssd = np.zeros(n, np.uint64)
+        self._ck(self.lib.hevcdl_tu_code(self.h, n, _ptr(tus), _ptr(resi), nelem, _ptr(coeff), _ptr(level), _ptr(deq), _ptr(rec),
+                                         _ptr(asum), _ptr(ssd)), "tu_code")
+
+        def split(a):
+            return None if a is None else [a[off[i]:off[i + 1]].reshape(sizes[i], sizes[i]) for i in range(n)]
+        return {"coeff": split(coeff), "level": split(level), "deq": split(deq), "rec": split(rec), "abs_sum": asum, "ssd": ssd}
 
     # -- measurement -------------------------------------------------------------------------
     def bench_resident(self, frames, iters):

@@ -157,6 +157,29 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
                      const uint8_t *mpm_add, double sqrt_lambda, uint32_t *satd, uint8_t *cand,
                      uint8_t *ncand);
 
+/* Transform-unit coding core (first slice of the RD pass): for a batch of TUs the arithmetic of
+ * TComTrQuant::transformNxN + invTransformNxN as TEncSearch::xIntraCodingTUBlock calls them
+ * (HM TLibEncoder/TEncSearch.cpp:1129-1424; TLibCommon/TComTrQuant.cpp:1450-1666): forward core transform (DCT 4..32, DST for
+ * 4x4 intra luma, or transform skip) -> xQuant's flat quantiser (:1126-1249 without RDOQ and sign-bit hiding) -> xDeQuant
+ * (:1308-1423, no scaling lists) -> inverse transform, bit-exact at the reference's operating point (8-bit video, |residual|
+ * <= 2047 accepted).  tus[i].offset: element offset of TU i's (1 << log2_size)^2 block, row-major, in resi and in every
+ * output array (nelem elements each).  coeff (transform output) and deq (dequantised) may be NULL.  level: quantised
+ * coefficients (TCoeff clipped to 16 bits by xQuant); rec: reconstructed residual; abs_sum[i]: uiAbsSum (0 = cbf 0);
+ * ssd[i] (may be NULL): sum (resi - rec)^2, the SSE of xIntraCodingTUBlock when prediction + residual does not clip.
+ * Synchronous. */
+typedef struct {
+  uint8_t log2_size;       /* 2..5 */
+  uint8_t qp;              /* 0..51: luma QP, or the mapped chroma QP */
+  uint8_t flags;           /* HEVCDL_TU_* */
+  uint8_t reserved;
+  uint32_t offset;
+} hevcdl_tu;
+#define HEVCDL_TU_DST 1    /* 4x4 intra luma: DST-VII (TComTU::useDST) */
+#define HEVCDL_TU_TSKIP 2  /* transform skip */
+#define HEVCDL_TU_INTER 4  /* rounding offset 85/512 instead of 171/512 (non-I slices) */
+int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff,
+                   int16_t *level, int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd);
+
 /* Pin the calling thread to the CPUs of `device`'s NUMA node (what hevcdl_cfg.numa_bind does inside hevcdl_create),
  * for callers that allocate their own pinned frame buffers before creating a context.  Returns the node (>= 0), or a
  * negative hevcdl_status when the topology cannot be read (single-node hosts report node 0 or -1 in sysfs: no-op, 0). */

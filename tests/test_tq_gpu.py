@@ -1,0 +1,88 @@
+"""Transform-unit coding core on the device (hevcdl_tu_code, csrc/tq.cuh) through the C-ABI: bit-exact against the
+reference's own functions / encoder dumps (tests/golden/tq_*.npz, tools/gen_golden_tq.py) and against the oracle on random
+TUs of every size, QP and flag."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dp(built, host):
+    d = host.DepthPredictor(64, 64, precision=host.PREC_FP32, rmd=False, outputs=0)
+    yield d
+    d.close()
+
+
+def test_tu_core_vs_reference_encoder_dump(dp, host):
+    """Every TU of the fixture (sizes 4..32, luma + chroma QP, DST, transform skip) equals what the reference encoder printed."""
+    g = np.load(os.path.join(GOLDEN, "tq_trace_192x128_qp32.npz"))
+    n = len(g["sizes"])
+    blocks = [g["resi"][g["off"][i]:g["off"][i + 1]].reshape(int(g["sizes"][i]), int(g["sizes"][i])) for i in range(n)]
+    out = dp.tu_code(blocks, g["qp"], g["flags"])
+    for i in range(n):
+        a, b = int(g["off"][i]), int(g["off"][i + 1])
+        assert (out["coeff"][i].ravel() == g["coeff"][a:b]).all(), ("coeff", i, g["sizes"][i], g["flags"][i])
+        assert (out["level"][i].ravel() == g["level"][a:b]).all(), ("level", i)
+        assert out["abs_sum"][i] == np.abs(g["level"][a:b]).sum()
+        if g["has_inv"][i]:
+            assert (out["deq"][i].ravel() == g["deq"][a:b]).all(), ("deq", i)
+            assert (out["rec"][i].ravel() == g["rec"][a:b]).all(), ("rec", i)
+            assert out["ssd"][i] == ((blocks[i].astype(np.int64) - g["rec"][a:b].reshape(blocks[i].shape)) ** 2).sum()
+
+
+def test_forward_transform_vs_the_references_own_function(dp):
+    """Transform output on the reference's xTrMxN vectors (random, small, +-255 checkerboards), DCT 4..32 and DST."""
+    g = np.load(os.path.join(GOLDEN, "tq_transform_ref.npz"))
+    n = len(g["sizes"])
+    blocks = [g["resi"][g["off"][i]:g["off"][i + 1]].reshape(int(g["sizes"][i]), int(g["sizes"][i])) for i in range(n)]
+    out = dp.tu_code(blocks, np.full(n, 32), g["dst"].astype(np.uint8))
+    for i in range(n):
+        assert (out["coeff"][i].ravel() == g["coeff"][g["off"][i]:g["off"][i + 1]]).all(), (i, g["sizes"][i], g["dst"][i])
+
+
+def test_tu_core_vs_oracle_random(dp, oracle, host):
+    """2000 random TUs: every size, QP 0..51, DST / transform-skip / inter rounding, residuals up to +-255 and sparse ones;
+    coeff, level, deq, rec, abs_sum and ssd all equal the oracle's."""
+    rng = np.random.default_rng(11)
+    blocks, qps, flags = [], [], []
+    for k in range(2000):
+        n = int(rng.choice([4, 8, 16, 32], p=[0.4, 0.3, 0.2, 0.1]))
+        kind = k % 5
+        if kind == 0:
+            b = rng.integers(-255, 256, (n, n))
+        elif kind == 1:
+            b = rng.integers(-6, 7, (n, n))
+        elif kind == 2:
+            b = np.zeros((n, n), np.int64); b[rng.integers(0, n), rng.integers(0, n)] = rng.integers(-255, 256)
+        elif kind == 3:
+            b = (rng.integers(0, 2, (n, n)) * 2 - 1) * 255
+        else:
+            b = np.add.outer(np.arange(n), np.arange(n)) * rng.integers(-7, 8) + rng.integers(-40, 41)
+            b = np.clip(b, -255, 255)
+        f = 0
+        if n == 4:
+            f = int(rng.choice([0, host.TU_DST, host.TU_TSKIP]))
+        if rng.random() < 0.2:
+            f |= host.TU_INTER
+        blocks.append(b.astype(np.int16)); qps.append(int(rng.integers(0, 52))); flags.append(f)
+    out = dp.tu_code(blocks, qps, flags)
+    for i, b in enumerate(blocks):
+        c, q, d, r, s = oracle.tq_tu(b, qps[i], flags[i])
+        assert (out["coeff"][i] == c).all(), ("coeff", i, b.shape, qps[i], flags[i])
+        assert (out["level"][i] == q).all(), ("level", i, b.shape, qps[i], flags[i])
+        assert (out["deq"][i] == d).all(), ("deq", i, b.shape, qps[i], flags[i])
+        assert (out["rec"][i] == r).all(), ("rec", i, b.shape, qps[i], flags[i])
+        assert out["abs_sum"][i] == s and out["ssd"][i] == ((b.astype(np.int64) - r) ** 2).sum()
+
+
+def test_tu_core_rejects_bad_descriptors(dp, host):
+    with pytest.raises(host.HevcdlError):
+        dp.tu_code([np.zeros((8, 8), np.int16)], [32], [host.TU_TSKIP])      # transform skip is 4x4 only
+    with pytest.raises(host.HevcdlError):
+        dp.tu_code([np.zeros((4, 4), np.int16)], [52])                       # QP out of range
+    assert dp.tu_code([], [])["abs_sum"].size == 0
