@@ -269,8 +269,8 @@ def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed
     # ---- e2e: pinned host planes -> labels + PU lists + candidates back on the host, pipelined ------------
     pinned = []
     for (Y, U, V) in pool[:min(pool_n, 8)]:
-        buf = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
-        a = buf.numpy()
+        buf = host.PinnedBuffer(frame_bytes, write_combined=args.wc)      # page-locked by the library's own allocator
+        a = buf.a
         a[:w * h] = Y.ravel(); a[w * h:w * h * 5 // 4] = U.ravel(); a[w * h * 5 // 4:] = V.ravel()
         pinned.append((buf, a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2),
                        a[w * h * 5 // 4:].reshape(h // 2, w // 2)))
@@ -317,12 +317,16 @@ def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed
             "pus_per_frame": npu_total / pool_n, "stats": st}
 
 
-def copy_probe(torch, dist, world, frame_bytes, reps=64):
-    """All ranks copy at once (the situation of the e2e leg): per-rank H2D and D2H GB/s from / to pinned host memory."""
+def copy_probe(host, torch, dist, world, frame_bytes, reps=64):
+    """All ranks copy at once (the situation of the e2e leg): per-rank H2D and D2H GB/s from / to pinned host memory
+    (h2d_wc: from write-combined pinned memory)."""
     src = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
     dst = torch.empty(frame_bytes, dtype=torch.uint8, device="cuda")
+    wcb = host.PinnedBuffer(frame_bytes, write_combined=True)
+    wcb.a[:] = 7
+    wc = torch.from_numpy(wcb.a)
     out = {}
-    for name, (a, b) in (("h2d", (dst, src)), ("d2h", (src, dst))):
+    for name, (a, b) in (("h2d", (dst, src)), ("d2h", (src, dst)), ("h2d_wc", (dst, wc))):
         for _ in range(4):
             a.copy_(b, non_blocking=True)
         if world > 1:
@@ -341,6 +345,8 @@ def copy_probe(torch, dist, world, frame_bytes, reps=64):
             out[name + "_gbs_per_rank_min"], out[name + "_gbs_per_rank_max"] = float(t[0]), float(-t[1])
         else:
             out[name + "_gbs_per_rank_min"] = out[name + "_gbs_per_rank_max"] = gbs
+    del wc
+    wcb.close()
     return out
 
 
@@ -411,7 +417,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": r["e2e_value"], "unit": "CTU/s", "h2d_bytes_per_step": r["h2d_per_frame"],
                 "d2h_bytes_per_step": r["d2h_per_frame"], "pipeline_depth": r["depth"], "frames_timed": frames_timed,
-                "python_value": r["e2e_py_value"], "outputs": "labels + PU list + ranked candidate modes (hevcdl_cfg.outputs = 0)"},
+                "python_value": r["e2e_py_value"], "host_planes": "page-locked (hevcdl_host_alloc%s), hevcdl_cfg.pinned_input = 1" % (", write-combined" if args.wc else ""), "outputs": "labels + PU list + ranked candidate modes (hevcdl_cfg.outputs = 0)"},
         "gpu_launches": r["launches"],
         "roofline": {"bound": "tensor", "achieved": ach_cnn, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
                      "frac": ach_cnn / pk["tensor_burst"], "frac_sustained": ach_cnn / pk["tensor_sustained"],
@@ -427,7 +433,7 @@ def run_b200(args, rank, world, local_rank):
                                  "peak_tiops": 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12}},
     }
     if world > 1 or args.probe:
-        out["copy_probe"] = copy_probe(torch, dist, world, frame_bytes)
+        out["copy_probe"] = copy_probe(host, torch, dist, world, frame_bytes)
         out["copy_probe"]["what"] = "all %d ranks copying one frame's planes at once from / to pinned host memory, per-rank GB/s" % world
     if (world > 1 or args.config4k) and not args.no_config4k:
         # BASELINE configs[3]: 3840x2160, 240 frames, frame f -> rank f mod N
@@ -481,6 +487,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-binaries", action="store_true", help="skip timing oracle/_ref/TAppEncoder_{ref,anchor} (about 15 s)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--wc", action="store_true", help="write-combined pinned frame buffers in the e2e leg")
     ap.add_argument("--probe", action="store_true", help="add the host<->device copy probe at N=1 too")
     ap.add_argument("--config4k", action="store_true", help="add the 3840x2160 x 240 frames block at N=1 too (always on for N>1)")
     ap.add_argument("--no-config4k", action="store_true")

@@ -454,6 +454,16 @@ const char *hevcdl_status_str(int st) {
 
 const char *hevcdl_last_error(const hevcdl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+void *hevcdl_host_alloc(size_t bytes, int write_combined) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void hevcdl_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 // NUMA node of a CUDA device from sysfs; the calling thread is restricted to that node's CPUs, so that pinned
 // allocations (first touch) and staging memcpys made by it afterwards are local to the GPU's PCIe root complex.
 int hevcdl_numa_bind_thread(int device) {

@@ -385,7 +385,10 @@ struct RmdItem {
   uint16_t frame;       // frame of the launch batch
 };
 constexpr int MAX_ITEMS_CTU = 64;
-constexpr int RMD_BW = 4;                       // warps per block of k_rmd_items
+#ifndef HEVCDL_RMD_BW
+#define HEVCDL_RMD_BW 4
+#endif
+constexpr int RMD_BW = HEVCDL_RMD_BW;           // warps per block of k_rmd_items (tuning builds: -DHEVCDL_RMD_BW=1|2)
 constexpr int ORG_P = 40;                       // row pitch of the staged block: 10 words -> conflict-free 16-bit reads
 constexpr int RED_P = 36;                       // 16-byte aligned rows, conflict-free column writes and float4 row reads
 constexpr int PTAB_P = 132;
@@ -818,13 +821,23 @@ __device__ __forceinline__ void block_small(RmdBlockS &S, const uint8_t *__restr
     *reinterpret_cast<uint32_t *>(&S.org[r * ORG_P + 4 * cw]) =
         __ldg(reinterpret_cast<const uint32_t *>(Y + (size_t)(py + r) * pitch + px + 4 * cw));
   }
-  {
+  if constexpr (RMD_BW == 4) {
     int16_t *l4 = L + 68 + 20 * wid;            // warp k: the line of 4x4 PU k, then a quarter of the 8x8 line
     build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px + (wid & 1) * 4, py + (wid >> 1) * 4, 4, l4, 0, 17, lane);
     build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, 8, L, wid * 9, min(33, wid * 9 + 9), lane);
     __syncwarp();
     const int dc = line_dc_warp(l4, 4, lane);
     if (lane == 0) S.dcs[1 + wid] = (int16_t)dc;
+  } else {                                      // tuning builds with fewer warps per block
+    for (int k = wid; k < 4; k += RMD_BW) {
+      int16_t *l4 = L + 68 + 20 * k;
+      build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px + (k & 1) * 4, py + (k >> 1) * 4, 4, l4, 0, 17, lane);
+      __syncwarp();
+      const int dc = line_dc_warp(l4, 4, lane);
+      if (lane == 0) S.dcs[1 + k] = (int16_t)dc;
+    }
+    constexpr int q8 = (33 + RMD_BW - 1) / RMD_BW;
+    build_line_part(Y, pitch, geo.W, geo.H, geo.ctu_w, px, py, 8, L, wid * q8, min(33, wid * q8 + q8), lane);
   }
   __syncthreads();
   if (wid == 0) {
@@ -891,7 +904,7 @@ __device__ __forceinline__ void block_small(RmdBlockS &S, const uint8_t *__restr
     rank35_warp(S.satd[k][lane], lane < 3 ? S.satd[k][32 + lane] : 0xFFFFFFFFu, 8, cand_out + (p + k) * 8, lane);
 }
 
-__global__ void __launch_bounds__(RMD_BW * 32, 8)
+__global__ void __launch_bounds__(RMD_BW * 32, 32 / RMD_BW)
 k_rmd_items(const RmdBatch rb, FrameGeom geo, int pitch, const RmdItem *__restrict__ items, int *__restrict__ ctrl) {
   __shared__ __align__(16) RmdBlockS S;
   const int lane = threadIdx.x & 31;

@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_get_stats", "hevcdl_numa_bind_thread",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
@@ -95,6 +95,10 @@ def load_library():
     L.hevcdl_stream.argtypes = [vp]
     L.hevcdl_stream.restype = vp
     L.hevcdl_numa_bind_thread.argtypes = [ip]
+    L.hevcdl_host_alloc.argtypes = [C.c_size_t, ip]
+    L.hevcdl_host_alloc.restype = vp
+    L.hevcdl_host_free.argtypes = [vp]
+    L.hevcdl_host_free.restype = None
     L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
@@ -312,6 +316,25 @@ class DepthPredictor:
         s = Stats()
         self._ck(self.lib.hevcdl_get_stats(self.h, C.byref(s)), "get_stats")
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+class PinnedBuffer:
+    """Page-locked host bytes from hevcdl_host_alloc as a numpy uint8 array (`.a`); freed with the object."""
+
+    def __init__(self, nbytes, write_combined=False):
+        self.lib = load_library()
+        self.p = self.lib.hevcdl_host_alloc(int(nbytes), int(write_combined))
+        if not self.p:
+            raise HevcdlError("hevcdl_host_alloc(%d) failed" % nbytes)
+        self.a = np.ctypeslib.as_array(C.cast(self.p, C.POINTER(C.c_uint8)), shape=(int(nbytes),))
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.a = None
+            self.lib.hevcdl_host_free(self.p)
+            self.p = None
+
+    __del__ = close
 
 
 def numa_bind_thread(device):

@@ -220,6 +220,7 @@ struct HevcdlSession {
   hevcdl_ctx *ctx = nullptr;
   int width = 0, height = 0;
   int frame = -1;               // frame currently resident on the device (-1: none)
+  int labels_frame = -1;        // frame whose labels were last asked for (timing statistics)
   bool gpu_rmd = false;         // HEVCDL_RMD=1: first-pass SATDs come from the device (batched, original-pixel references)
   bool exact_rmd = false;       // HEVCDL_RMD=2: ... from hevcdl_rmd_exact fed HM's reconstructed references, PU by PU
   unsigned ex_x = ~0u, ex_y = ~0u, ex_n = 0;      // PU whose 35 SATDs are cached in ex_satd
@@ -235,6 +236,8 @@ struct HevcdlSession {
   long submitted_hi = -1;       // highest frame id handed to the device from the file
   std::vector<std::pair<long, uint64_t>> ahead;   // (frame id, hash of the file's planes) of frames submitted from the file
   unsigned long long la_hits = 0, la_direct = 0, la_mismatch = 0;
+  double t_create = 0, t_wait_first = 0, t_wait_later = 0;   // seconds: hevcdl_create; blocked in the first label query of frame 0 / of later frames
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   std::vector<uint8_t> rowbuf;
 
   static void die(const char *what, int rc, hevcdl_ctx *c) {
@@ -277,7 +280,9 @@ struct HevcdlSession {
         if (slash) { strcpy(slash, "/../../weights/hevc_encoder_model.hdlw"); cfg.weights_path = relpath; }
       }
     }
+    const double t0 = now();
     const int rc = hevcdl_create(&cfg, &ctx);
+    t_create = now() - t0;
     if (rc) die("hevcdl_create", rc, nullptr);
     width = w; height = h;
   }
@@ -383,6 +388,8 @@ struct HevcdlSession {
       if (getenv("HEVCDL_VERBOSE")) {
         fprintf(stderr, "hevcdl: lookahead %d: %llu frames were on the device before HM asked, %llu uploaded from HM's planes, %llu mismatches\n",
                 lookahead, la_hits, la_direct, la_mismatch);
+        fprintf(stderr, "hevcdl: encoder thread blocked %.3f s in hevcdl_create (CUDA context + weights + buffers), %.4f s waiting for the "
+                        "labels of the first frame, %.4f s for all later frames together\n", t_create, t_wait_first, t_wait_later);
         hevcdl_stats_t st;
         if (!hevcdl_get_stats(ctx, &st))
           fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches, "
@@ -413,7 +420,14 @@ Void TEncCu::compressCtu( Int m_iFrame, TComDataCU* pCtu )
   }
 
   uint8_t depth8[16];
+  const bool firstQuery = g_session.labels_frame != m_iFrame;
+  const double tq0 = firstQuery ? HevcdlSession::now() : 0.0;
   const int rc = hevcdl_ctu_labels( g_session.ctx, m_iFrame, (int)ctuRsAddr, depth8 );   // blocks on the frame's event
+  if ( firstQuery )
+  {
+    ( g_session.labels_frame < 0 ? g_session.t_wait_first : g_session.t_wait_later ) += HevcdlSession::now() - tq0;
+    g_session.labels_frame = m_iFrame;
+  }
   if ( rc ) HevcdlSession::die( "hevcdl_ctu_labels", rc, g_session.ctx );
   UInt label[16];                                   // same lifetime as the reference's stack array (TEncCu.cpp:247)
   for ( Int i = 0; i < 16; i++ ) label[i] = depth8[i];

@@ -180,6 +180,13 @@ typedef struct {
 int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff,
                    int16_t *level, int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd);
 
+/* Page-locked host memory for frame planes handed over with hevcdl_cfg.pinned_input = 1 (any page-locked memory will do;
+ * this is the allocator for callers without a CUDA runtime of their own).  write_combined != 0: cudaHostAllocWriteCombined --
+ * not snooped during the transfer, which some hosts move faster over PCIe; the CPU should only WRITE such memory (reads
+ * are uncached).  Returns NULL on failure. */
+void *hevcdl_host_alloc(size_t bytes, int write_combined);
+void hevcdl_host_free(void *p);
+
 /* Pin the calling thread to the CPUs of `device`'s NUMA node (what hevcdl_cfg.numa_bind does inside hevcdl_create),
  * for callers that allocate their own pinned frame buffers before creating a context.  Returns the node (>= 0), or a
  * negative hevcdl_status when the topology cannot be read (single-node hosts report node 0 or -1 in sysfs: no-op, 0). */
