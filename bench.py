@@ -422,6 +422,8 @@ def run_b200(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "achieved": ach_cnn, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
                      "frac": ach_cnn / pk["tensor_burst"], "frac_sustained": ach_cnn / pk["tensor_sustained"],
                      "peak_sustained": pk["tensor_sustained"], "traffic": traffic,
+                     "traffic_over_algorithmic": (traffic / (BYTES_PER_CTU * nctu)) if traffic else None,
+                     "traffic_note": "DRAM bytes of the CNN kernels per frame in the pipeline's natural cache state (ncu --cache-control none, profiles/traffic.json): the bf16 intermediates of a 4-frame launch exceed L2",
                      "peak_source": pk["src"] + " bf16: burst (a %.0f ms region at full clocks); frac_sustained is against the long-run figure" % r["ms_total"],
                      "kernel": "CNN stage = k_tc_l1 + k_tc_conv2 + k_tc_conv3 + k_tc_fc (tcgen05)" if prec else "k_cnn_fp32", "kernel_ms": ms_cnn,
                      "fused_path": {"achieved": ach_fused, "frac": ach_fused / pk["tensor_burst"], "frac_sustained": ach_fused / pk["tensor_sustained"],
@@ -432,6 +434,17 @@ def run_b200(args, rank, world, local_rank):
                      "rmd_alu": {"achieved_tiops": INTOP_PER_CTU * nctu / (ms_rmd / 1000.0) / 1e12,
                                  "peak_tiops": 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12}},
     }
+    bp = os.path.join(ROOT, "profiles", "r02_bdrate_1080p_100f.json")
+    if os.path.exists(bp):        # the other half of BASELINE.json's metric: NOT measured in this run (hours of encoder time), read from the committed sweep
+        bd = json.load(open(bp))
+        pick = {"hm_dl_vs_anchor": "reference_hm_dl_vs_anchor", "dropin_bf16_gpu_rmd_fix0_vs_hm_dl": "dropin_bf16_labels_gpu_rmd_vs_reference_hm_dl",
+                "dropin_bf16_gpu_rmd_fix0_vs_anchor": "dropin_bf16_labels_gpu_rmd_vs_anchor", "hm_dl_labels_bf16_fix0_vs_hm_dl": "bf16_labels_in_reference_encoder_vs_reference_hm_dl",
+                "dropin_bf16_gpu_rmd_fix1_vs_anchor": "dropin_boundary_fix_vs_anchor"}
+        out["bd_rate"] = {"source": "profiles/r02_bdrate_1080p_100f.json (tools/bdrate_100f.py): BASELINE configs[2], %dx%d, %d frames, QP %s; committed sweep, not re-run by bench.py" % (bd["width"], bd["height"], bd["frames"], bd["qps"]),
+                          "tolerance": "north_star: within +-1 % BD-rate / +-0.05 dB BD-PSNR of the reference HM_dl"}
+        for k, name in pick.items():
+            if k in bd.get("bd", {}):
+                out["bd_rate"][name] = {"bd_rate_y_pct": round(bd["bd"][k]["bd_rate_y_pct"], 3), "bd_psnr_y_db": round(bd["bd"][k]["bd_psnr_y_db"], 4)}
     if world > 1 or args.probe:
         out["copy_probe"] = copy_probe(host, torch, dist, world, frame_bytes)
         out["copy_probe"]["what"] = "all %d ranks copying one frame's planes at once from / to pinned host memory, per-rank GB/s" % world
