@@ -18,5 +18,11 @@ for i in range(2):
     v = dp.view(i)
     tot += int(v["labels"].sum()) + int(v["satd"][:, 0].sum() & 0xFFFF) + len(v["pus"])
     dp.release(i)
+# the transform-unit coding core (hevcdl_tu_code) on a few hundred TUs of every size
+import numpy as np
+rng = np.random.default_rng(1)
+blocks = [rng.integers(-255, 256, (n, n)).astype(np.int16) for n in (4, 8, 16, 32) * 64]
+out = dp.tu_code(blocks, rng.integers(0, 52, len(blocks)), [host.TU_DST if b.shape[0] == 4 and i % 3 == 0 else (host.TU_TSKIP if b.shape[0] == 4 and i % 3 == 1 else 0) for i, b in enumerate(blocks)])
+tot += int(out["abs_sum"].sum() & 0xFFFF)
 dp.close()
 print("sanitize_frame ok: checksum", tot)
