@@ -28,6 +28,10 @@
 //                     (InputFile, FrameSkip, FramesToBeEncoded); every prefetched frame is checked against the planes HM
 //                     hands over for that frame id (hash of all three planes) -- on a mismatch the prefetch is dropped
 //                     and the frame is uploaded from HM's planes as without lookahead.  8-bit 4:2:0 input without padding only.
+//   HEVCDL_TQ         1 = transform + flat quantiser + dequantiser + inverse transform of every TU of xIntraCodingTUBlock on the
+//                     device (hevcdl_tu_code, one synchronous call per TU): byte-identical bitstreams when the encoder runs
+//                     with --RDOQ=0 --RDOQTS=0 --SignHideFlag=0 (RDOQ and sign-bit hiding are not on the device); TUs the
+//                     core does not cover stay HM's (hm_plugin/rmd_hook.h)
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
 //                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
 //                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
@@ -49,6 +53,7 @@
 #include <thread>
 #include <vector>
 
+#include "TLibCommon/TComTU.h"
 #include "TLibEncoder/TEncCu.h"
 #include "TLibEncoder/TEncTop.h"
 
@@ -226,6 +231,8 @@ struct HevcdlSession {
   unsigned ex_x = ~0u, ex_y = ~0u, ex_n = 0;      // PU whose 35 SATDs are cached in ex_satd
   uint32_t ex_satd[35];
   unsigned long long exact_calls = 0;
+  bool gpu_tq = false;          // HEVCDL_TQ=1: TU transform / quantisation / inverse transform on the device
+  unsigned long long tq_calls = 0, tq_declined = 0;
   hevcdl_frame_view view;       // results of `frame` (pinned host memory owned by the library)
   bool have_view = false;
   int ctu_first = 0, ctu_count = 0, cursor = 0;   // PU range of the CTU being compressed + last hit
@@ -268,6 +275,7 @@ struct HevcdlSession {
     cfg.outputs = rmd_mode == 1 ? HEVCDL_OUT_SATD : 0;   // the first-pass hook re-ranks with HM's own mode bits: it needs the SATD table
     gpu_rmd = rmd_mode == 1;
     exact_rmd = rmd_mode == 2;
+    gpu_tq = (e = getenv("HEVCDL_TQ")) && atoi(e) == 1;
     cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
     // weights: HEVCDL_WEIGHTS, else the path baked in at build time, else <dir of this executable>/../../weights/
     static char relpath[4096];
@@ -393,9 +401,9 @@ struct HevcdlSession {
         hevcdl_stats_t st;
         if (!hevcdl_get_stats(ctx, &st))
           fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches, "
-                          "first-pass SATDs served %llu / missed %llu, exact PU calls %llu\n",
+                          "first-pass SATDs served %llu / missed %llu, exact PU calls %llu, TUs coded on the device %llu / left to HM %llu\n",
                   (unsigned long long)st.frames, (unsigned long long)st.ctus, st.ms_cnn, st.ms_rmd,
-                  (unsigned long long)st.kernel_launches, hook_hits, hook_misses, exact_calls);
+                  (unsigned long long)st.kernel_launches, hook_hits, hook_misses, exact_calls, tq_calls, tq_declined);
       }
       hevcdl_destroy(ctx);
     }
@@ -479,4 +487,45 @@ bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu
   }
   if ( !S.gpu_rmd || !S.have_view ) return false;
   return S.lookup( x, y, width, mode, sad );
+}
+
+// TU-coding hook (rmd_hook.h): called from the reference's xIntraCodingTUBlock in place of transformNxN + invTransformNxN.
+bool hevcdl_hm_tu_code( TComDataCU* pcCU, TComTU& rTu, int compIDi, short* piResi, unsigned uiStride, int* pcCoeff, int* puiAbsSum,
+                        int qp, bool useTransformSkip, bool rdoqOn )
+{
+  HevcdlSession &S = g_session;
+  if ( !S.gpu_tq || !S.ctx ) return false;
+  const ComponentID compID = ComponentID( compIDi );
+  const UInt uiAbsPartIdx = rTu.GetAbsPartIdxTU();
+  const TComRectangle &rect = rTu.getRect( compID );
+  const UInt n = rect.width;
+  // what the device core covers (csrc/tq.cuh): square 4..32 TUs, flat quantiser, no bypass, no scaling lists, 8-bit
+  if ( rdoqOn || rect.width != rect.height || n < 4 || n > 32 || pcCU->getCUTransquantBypass( uiAbsPartIdx ) ||
+       pcCU->getSlice()->getPPS()->getSignDataHidingEnabledFlag() || pcCU->getSlice()->getSPS()->getScalingListFlag() ||
+       qp < 0 || qp > 51 || ( useTransformSkip && n != 4 ) )
+  {
+    S.tq_declined++;
+    return false;
+  }
+  int16_t resi[32 * 32], level[32 * 32], rec[32 * 32];
+  for ( UInt y = 0; y < n; y++ )
+    for ( UInt x = 0; x < n; x++ ) resi[y * n + x] = piResi[y * uiStride + x];
+  hevcdl_tu tu;
+  tu.log2_size = (uint8_t)( n == 4 ? 2 : n == 8 ? 3 : n == 16 ? 4 : 5 );
+  tu.qp = (uint8_t)qp;
+  tu.flags = (uint8_t)( ( useTransformSkip ? HEVCDL_TU_TSKIP : ( rTu.useDST( compID ) ? HEVCDL_TU_DST : 0 ) ) |
+                        ( pcCU->getSlice()->getSliceType() == I_SLICE ? 0 : HEVCDL_TU_INTER ) );
+  tu.reserved = 0;
+  tu.offset = 0;
+  uint32_t absSum = 0;
+  const int rc = hevcdl_tu_code( S.ctx, 1, &tu, resi, (size_t)n * n, NULL, level, NULL, rec, &absSum, NULL );
+  if ( rc ) HevcdlSession::die( "hevcdl_tu_code", rc, S.ctx );
+  S.tq_calls++;
+  // exactly what transformNxN (TComTrQuant.cpp:1450-1534) and the inverse-transform if/else (TEncSearch.cpp:1310-1328) leave behind
+  *puiAbsSum = (int)absSum;
+  pcCU->setCbfPartRange( ( ( absSum > 0 ? 1 : 0 ) << rTu.GetTransformDepthRel() ), compID, uiAbsPartIdx, rTu.GetAbsPartIdxNumParts( compID ) );
+  for ( UInt i = 0; i < n * n; i++ ) pcCoeff[i] = absSum > 0 ? (int)level[i] : 0;
+  for ( UInt y = 0; y < n; y++ )
+    for ( UInt x = 0; x < n; x++ ) piResi[y * uiStride + x] = absSum > 0 ? rec[y * n + x] : 0;
+  return true;
 }

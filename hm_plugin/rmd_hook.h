@@ -15,5 +15,16 @@
 #pragma once
 class TComDataCU;
 class TComPrediction;
+class TComTU;
+/* Second hook (HEVCDL_TQ=1): the transform / quantisation / inverse-transform of one TU inside
+ * TEncSearch::xIntraCodingTUBlock (TEncSearch.cpp:1301 m_pcTrQuant->transformNxN(...) through the inverse-transform
+ * if/else ending before :1330 "//===== reconstruction =====") is wrapped in `if ( !hevcdl_hm_tu_code(...) ) { ... }` by a third
+ * sed rule of hm_plugin/Makefile.  When the TU is one the device core covers -- flat quantiser, i.e. the encoder runs with
+ * --RDOQ=0 --RDOQTS=0 --SignHideFlag=0, no transquant bypass -- the hook sends the residual block through hevcdl_tu_code
+ * (one synchronous call per TU: a parity demonstration like HEVCDL_RMD=2, not a speed-up), writes levels, cbf, uiAbsSum and
+ * the reconstructed residual exactly where the reference code would, and the bitstream stays byte-identical to the
+ * reference run with the same options.  Otherwise it returns false and the reference code runs. */
+bool hevcdl_hm_tu_code( TComDataCU* pcCU, TComTU& rTu, int compID, short* piResi, unsigned uiStride, int* pcCoeff, int* puiAbsSum,
+                        int qp, bool useTransformSkip, bool rdoqOn );
 bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode,
                          const short* org, unsigned orgStride, unsigned* sad );

@@ -205,3 +205,35 @@ def test_dropin_lookahead_prefetches_frames_and_keeps_the_bitstream(tmp_path, bu
     m = re.search(r"lookahead (\d+): (\d+) frames were on the device", r0["stderr"])
     assert m and int(m.group(1)) == 0 and int(m.group(2)) == 0
     assert "lookahead disabled" in r2["stderr"]
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,qp", [(192, 128, 32), (256, 192, 22)])
+def test_dropin_tu_core_on_the_device_keeps_the_bitstream(tmp_path, built, host, pkg, w, h, qp):
+    """HEVCDL_TQ=1: transform, flat quantiser, dequantiser and inverse transform of EVERY luma and chroma TU the reference's
+    xIntraCodingTUBlock codes (all RD trials included) come from hevcdl_tu_code.  With the encoder options the device core
+    covers (--RDOQ=0 --RDOQTS=0 --SignHideFlag=0) the bitstream must be byte-identical to the unmodified reference run with
+    the same options, and no TU may be left to HM."""
+    import re
+    frames = [pkg.synth.synth_frame(w, h, 90 + i) for i in range(2)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    dp = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=False)
+    for f, (Y, U, V) in enumerate(frames):
+        hm_util.write_pred(str(a / "pred"), f, dp.predict_frame(Y, U, V, frame=f))
+    dp.close()
+    flat = ("--RDOQ=0", "--RDOQTS=0", "--SignHideFlag=0")
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp, extra=flat)
+    rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, extra=flat, env={"HEVCDL_TQ": "1", "HEVCDL_VERBOSE": "1"})
+    assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-400:])
+    m = re.search(r"TUs coded on the device (\d+) / left to HM (\d+)", rb["stderr"])
+    assert m and int(m.group(1)) > 1000 and int(m.group(2)) == 0, rb["stderr"][-300:]
+    assert ra["sha1"] == rb["sha1"] and (ra["kbps"], ra["psnr_y"]) == (rb["kbps"], rb["psnr_y"])
+    # with RDOQ on (the reference's operating point) the hook must step aside and the stream still equals the reference's
+    rc = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, out="rdoq.bin", env={"HEVCDL_TQ": "1", "HEVCDL_VERBOSE": "1"})
+    rd = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp, out="rdoq.bin")
+    m = re.search(r"TUs coded on the device (\d+) / left to HM (\d+)", rc["stderr"])
+    assert m and int(m.group(1)) == 0 and int(m.group(2)) > 1000 and rc["sha1"] == rd["sha1"]
