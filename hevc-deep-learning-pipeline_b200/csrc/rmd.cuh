@@ -904,7 +904,10 @@ __device__ __forceinline__ void block_small(RmdBlockS &S, const uint8_t *__restr
     rank35_warp(S.satd[k][lane], lane < 3 ? S.satd[k][32 + lane] : 0xFFFFFFFFu, 8, cand_out + (p + k) * 8, lane);
 }
 
-__global__ void __launch_bounds__(RMD_BW * 32, 32 / RMD_BW)
+#ifndef HEVCDL_RMD_MINB
+#define HEVCDL_RMD_MINB (HEVCDL_RMD_BW == 4 ? 9 : 32 / HEVCDL_RMD_BW)   // 9 blocks of 4 warps (54 registers, no spill): 64.9 vs 65.6 us per 1080p frame with 8; 10 / 11 blocks spill and are slower (69.2 / 72.2 us), profiles/r02j_k6_blocks_per_sm.log
+#endif
+__global__ void __launch_bounds__(RMD_BW * 32, HEVCDL_RMD_MINB)
 k_rmd_items(const RmdBatch rb, FrameGeom geo, int pitch, const RmdItem *__restrict__ items, int *__restrict__ ctrl) {
   __shared__ __align__(16) RmdBlockS S;
   const int lane = threadIdx.x & 31;
