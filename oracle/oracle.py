@@ -23,7 +23,7 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def build():
     """Compile the C restatement (gcc, seconds)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c")]
+    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c", "rdoq_oracle.c")]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so] + srcs + ["-lm"])
     return so
@@ -61,6 +61,8 @@ def lib():
         L.oracle_tq_inverse.argtypes = [i32p, C.c_int, C.c_int, i16p]
         L.oracle_tq_tu.argtypes = [i16p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i16p]
         L.oracle_tq_tu.restype = C.c_uint32
+        L.oracle_rdoq.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+        L.oracle_rdoq.restype = C.c_uint32
         _LIB = L
     return _LIB
 
@@ -241,3 +243,14 @@ def tq_tu(resi, qp, flags=0):
     r = np.zeros((n, n), np.int16)
     s = lib().oracle_tq_tu(np.ascontiguousarray(resi, np.int16), int(n).bit_length() - 1, int(qp), int(flags), c, q, d, r)
     return c, q, d, r, int(s)
+
+
+def rdoq(coeff, ch, scan_type, qp, tskip, lam, est, ctx_cbf, is_intra=1, tr_idx_zero=0, sdh=1):
+    """Rate-distortion optimised quantisation of one TU (oracle/rdoq_oracle.c): coeff (n,n) int32 transform output, ch 0 luma /
+    1 chroma, scan_type 0 diag / 1 hor / 2 ver, lam = the encoder's lambda for the component, est = the 224 int32 of the
+    reference's estBitsSbacStruct.  Returns (levels (n,n) int32, abs_sum)."""
+    n = coeff.shape[0]
+    out = np.zeros((n, n), np.int32)
+    s = lib().oracle_rdoq(np.ascontiguousarray(coeff, np.int32), int(n).bit_length() - 1, int(ch), int(scan_type), int(qp), int(tskip),
+                          float(lam), np.ascontiguousarray(est, np.int32), int(ctx_cbf), int(is_intra), int(tr_idx_zero), int(sdh), out)
+    return out, int(s)

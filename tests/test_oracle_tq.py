@@ -45,3 +45,18 @@ def test_tu_pipeline_equals_the_reference_encoder_dump(oracle):
             assert s == 0                          # the reference skips the inverse path only for all-zero levels
         seen.add((n, int(g["chan"][i]), int(g["flags"][i])))
     assert {(4, 0, 1), (4, 0, 2), (8, 0, 0), (16, 0, 0), (32, 0, 0), (4, 1, 0), (8, 2, 0), (16, 1, 0)} <= seen
+
+
+def test_rdoq_equals_the_reference_encoder_calls(oracle):
+    """oracle/rdoq_oracle.c against calls of the reference's own xRateDistOptQuant (RDOQ + sign-bit hiding, every TU size,
+    luma and chroma, the three scan types, transform skip), inputs and outputs dumped by the reference encoder itself."""
+    g = np.load(os.path.join(GOLDEN, "tq_rdoq_192x128_qp32.npz"))
+    seen = set()
+    for i, h in enumerate(g["hdr"]):
+        n = int(h[1])
+        a, b = int(g["off"][i]), int(g["off"][i + 1])
+        lev, s = oracle.rdoq(g["src"][a:b].reshape(n, n), 0 if h[2] == 0 else 1, int(h[6]), int(h[3]), int(h[7]), float(g["lam"][i]),
+                             g["est"][i], int(h[8]), int(h[9]), int(h[13]), int(h[10]))
+        assert s == int(g["abs_sum"][i]) and (lev.ravel() == g["dst"][a:b]).all(), (i, n, h[2], h[6], h[7])
+        seen.add((n, int(h[2] != 0), int(h[6]), int(h[7])))
+    assert {(4, 0, 0, 0), (4, 0, 1, 1), (4, 0, 2, 0), (8, 0, 1, 0), (8, 0, 2, 0), (8, 1, 0, 0), (16, 0, 0, 0), (16, 1, 0, 0), (32, 0, 0, 0)} <= seen

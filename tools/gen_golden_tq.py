@@ -4,6 +4,8 @@ container (needs /root/reference and `make -C oracle ref`); the fixtures travel,
 
   tests/golden/tq_transform_ref.npz   random and extreme blocks through the reference's OWN xTrMxN / xITrMxN
                                       (oracle/_ref/libtqref.so = tq_ref_harness.cpp linked with libhmref.a), every size + DST
+  tests/golden/tq_rdoq_192x128_qp32.npz    calls of the reference's xRateDistOptQuant (inputs incl. the CABAC bit-estimate
+                                      tables, outputs) dumped by oracle/_ref/TAppEncoder_rdoqtrace at the default options
   tests/golden/tq_trace_192x128_qp32.npz   per-TU dumps printed by oracle/_ref/TAppEncoder_tqtrace (the reference built with
                                       its own DEBUG_TRANSFORM_AND_QUANTISE switch, TComTrQuant.cpp:1496-1662) while encoding
                                       the 192x128 fixture frame at QP 32 with --RDOQ=0 --RDOQTS=0 --SignHideFlag=0 (the flat
@@ -146,6 +148,51 @@ def trace_vectors(per_class=14):
     print("tq_trace_192x128_qp32.npz:", len(sizes), "TUs,", os.path.getsize(os.path.join(GOLD, "tq_trace_192x128_qp32.npz")), "bytes")
 
 
+def rdoq_vectors(per_class=7):
+    """tests/golden/tq_rdoq_192x128_qp32.npz: inputs and outputs of calls of the reference's xRateDistOptQuant, dumped by
+    oracle/_ref/TAppEncoder_rdoqtrace (oracle/rdoq_dump.h) while encoding the fixture frame at the reference's operating
+    point (RDOQ, RDOQTS, sign-bit hiding on): a sample of every (size, component, scan type, transform skip) class."""
+    import struct
+    g = np.load(os.path.join(GOLD, "rmd_trace_192x128_qp32.npz"))
+    Y, U, V = g["Y"], g["U"], g["V"]
+    H, W = Y.shape
+    qp = int(g["qp"])
+    with tempfile.TemporaryDirectory() as td:
+        hm_util.write_yuv(os.path.join(td, "in.yuv"), [(Y, U, V)])
+        hm_util.write_pred(os.path.join(td, "pred"), 0, g["labels"])
+        cmd = [os.path.join(REFDIR, "TAppEncoder_rdoqtrace"), "-c", hm_util.CFG, "-i", "in.yuv", "-wdt", str(W), "-hgt", str(H), "-fr", "30",
+               "-f", "1", "-q", str(qp), "-b", "t.bin", "--InputBitDepth=8", "--InputChromaFormat=420", "--Level=6.2"]
+        env = dict(os.environ, HEVCDL_RDOQ_DUMP=os.path.join(td, "rdoq.bin"))
+        subprocess.check_call(cmd, cwd=td, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        raw = open(os.path.join(td, "rdoq.bin"), "rb").read()
+    off, recs = 0, []
+    while off < len(raw):
+        hdr = np.frombuffer(raw, np.int32, 16, off).copy(); off += 64
+        assert hdr[0] == 0x52444F51
+        lam, es = struct.unpack_from("dd", raw, off); off += 16
+        est = np.frombuffer(raw, np.int32, hdr[12] // 4, off).copy(); off += int(hdr[12])
+        n2 = int(hdr[1]) ** 2
+        src = np.frombuffer(raw, np.int32, n2, off).copy(); off += 4 * n2
+        dst = np.frombuffer(raw, np.int32, n2, off).copy(); off += 4 * n2
+        a = int(np.frombuffer(raw, np.int32, 1, off)[0]); off += 4
+        recs.append((hdr, lam, es, est, src, dst, a))
+    print("rdoq trace:", len(recs), "calls")
+    rng = np.random.default_rng(9)
+    classes = {}
+    for k, r in enumerate(recs):
+        classes.setdefault((int(r[0][1]), int(r[0][2]), int(r[0][6]), int(r[0][7]), r[6] > 0), []).append(k)
+    pick = []
+    for key, idx in sorted(classes.items()):
+        pick += [int(k) for k in rng.permutation(idx)[:per_class if key[4] else 2]]
+    rs = [recs[k] for k in pick]
+    off = np.concatenate([[0], np.cumsum([int(r[0][1]) ** 2 for r in rs])]).astype(np.int64)
+    np.savez_compressed(os.path.join(GOLD, "tq_rdoq_192x128_qp32.npz"), hdr=np.stack([r[0] for r in rs]), lam=np.array([r[1] for r in rs]),
+                        err_scale=np.array([r[2] for r in rs]), est=np.stack([r[3] for r in rs]), off=off, src=np.concatenate([r[4] for r in rs]),
+                        dst=np.concatenate([r[5] for r in rs]), abs_sum=np.array([r[6] for r in rs], np.int64))
+    print("tq_rdoq_192x128_qp32.npz:", len(rs), "calls,", os.path.getsize(os.path.join(GOLD, "tq_rdoq_192x128_qp32.npz")), "bytes")
+
+
 if __name__ == "__main__":
     transform_vectors()
     trace_vectors()
+    rdoq_vectors()
