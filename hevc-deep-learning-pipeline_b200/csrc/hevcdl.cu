@@ -89,6 +89,8 @@ struct hevcdl_ctx {
   std::string err;
   hevcdl_stats_t stats{};
   // scratch for hevcdl_tu_code
+  void *dRdoq = nullptr;               // RdoqScratch per resident warp of k_tu_code (RDOQ launches only)
+  int rdoqWarps = 0;
   void *dTq = nullptr;
   void *hTq = nullptr;                 // pinned mirror of dTq
   size_t tqCap = 0;
@@ -627,7 +629,7 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     if (s.evT1) cudaEventDestroy(s.evT1);
     if (s.evT2) cudaEventDestroy(s.evT2);
   }
-  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact); cudaFree(ctx->dTq);
+  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact); cudaFree(ctx->dTq); cudaFree(ctx->dRdoq);
   if (ctx->hExact) cudaFreeHost(ctx->hExact);
   if (ctx->hTq) cudaFreeHost(ctx->hTq);
   tc_release(&ctx->tc);
@@ -806,24 +808,32 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
   return HEVCDL_OK;
 }
 
-int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level,
-                   int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd) {
-  if (!ctx || n < 0 || (n && (!tus || !resi || !level || !rec || !abs_sum))) return HEVCDL_E_INVAL;
+int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevcdl_tu_rdoq *rdoq, const int32_t *est, int n_est,
+                        const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level, int32_t *deq, int16_t *rec, uint32_t *abs_sum,
+                        uint64_t *ssd) {
+  if (!ctx || n < 0 || (n && (!tus || !resi || !level || !rec || !abs_sum)) || (rdoq && (!est || n_est <= 0))) return HEVCDL_E_INVAL;
   if (n == 0) return HEVCDL_OK;
   cudaSetDevice(ctx->cfg.device);
   for (int i = 0; i < n; i++) {
     const hevcdl_tu &t = tus[i];
     if (t.log2_size < 2 || t.log2_size > 5 || t.qp > 51 || (size_t)t.offset + ((size_t)1 << (2 * t.log2_size)) > nelem ||
-        ((t.flags & HEVCDL_TU_TSKIP) && t.log2_size != 2) || (t.offset & 1)) {
-      ctx->err = "hevcdl_tu: log2_size 2..5, qp 0..51, even offset inside nelem, transform skip only for 4x4";
+        ((t.flags & HEVCDL_TU_TSKIP) && t.log2_size != 2) || (t.offset & 1) || ((t.flags & HEVCDL_TU_RDOQ) && !rdoq)) {
+      ctx->err = "hevcdl_tu: log2_size 2..5, qp 0..51, even offset inside nelem, transform skip only for 4x4, HEVCDL_TU_RDOQ only with rdoq parameters";
+      return HEVCDL_E_INVAL;
+    }
+    if (rdoq && (t.flags & HEVCDL_TU_RDOQ) &&
+        (rdoq[i].est_index >= (uint32_t)n_est || rdoq[i].channel > 1 || rdoq[i].scan_type > 2 || rdoq[i].ctx_cbf >= 10 || !(rdoq[i].lambda > 0) ||
+         (rdoq[i].scan_type != 0 && t.log2_size > 3))) {
+      ctx->err = "hevcdl_tu_rdoq: est_index < n_est, channel 0/1, scan_type 0..2 (non-diagonal only for 4x4 / 8x8), ctx_cbf < 10, lambda > 0";
       return HEVCDL_E_INVAL;
     }
   }
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t b_tus = al((size_t)n * sizeof(hevcdl_tu)), b_resi = al(nelem * 2), b_coeff = coeff ? al(nelem * 4) : 0, b_level = al(nelem * 2),
+  const size_t b_tus = al((size_t)n * sizeof(hevcdl_tu)), b_resi = al(nelem * 2), b_rq = rdoq ? al((size_t)n * sizeof(hevcdl_tu_rdoq)) : 0,
+               b_est = rdoq ? al((size_t)n_est * HEVCDL_EST_INTS * 4) : 0, b_coeff = coeff ? al(nelem * 4) : 0, b_level = al(nelem * 2),
                b_deq = deq ? al(nelem * 4) : 0, b_rec = al(nelem * 2), b_asum = al((size_t)n * 4), b_ssd = ssd ? al((size_t)n * 8) : 0;
-  const size_t o_tus = 0, o_resi = o_tus + b_tus, o_coeff = o_resi + b_resi, o_level = o_coeff + b_coeff, o_deq = o_level + b_level,
-               o_rec = o_deq + b_deq, o_asum = o_rec + b_rec, o_ssd = o_asum + b_asum, total = o_ssd + b_ssd;
+  const size_t o_tus = 0, o_resi = o_tus + b_tus, o_rq = o_resi + b_resi, o_est = o_rq + b_rq, o_coeff = o_est + b_est, o_level = o_coeff + b_coeff,
+               o_deq = o_level + b_level, o_rec = o_deq + b_deq, o_asum = o_rec + b_rec, o_ssd = o_asum + b_asum, total = o_ssd + b_ssd;
   if (total > ctx->tqCap) {
     cudaFree(ctx->dTq); ctx->dTq = nullptr; ctx->tqCap = 0;
     if (ctx->hTq) { cudaFreeHost(ctx->hTq); ctx->hTq = nullptr; }
@@ -832,18 +842,32 @@ int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *
     CK(cudaMallocHost(&ctx->hTq, cap));
     ctx->tqCap = cap;
   }
+  int grid = (n + TQ_WARPS - 1) / TQ_WARPS < 8 * ctx->numSMs ? (n + TQ_WARPS - 1) / TQ_WARPS : 8 * ctx->numSMs;
+  if (rdoq) {                                      // 48 KB of global scratch per warp: fewer, longer-lived warps
+    if (grid > 2 * ctx->numSMs) grid = 2 * ctx->numSMs;
+    if (grid * TQ_WARPS > ctx->rdoqWarps) {
+      cudaFree(ctx->dRdoq); ctx->dRdoq = nullptr; ctx->rdoqWarps = 0;
+      CK(cudaMalloc(&ctx->dRdoq, (size_t)grid * TQ_WARPS * sizeof(RdoqScratch)));
+      ctx->rdoqWarps = grid * TQ_WARPS;
+    }
+  }
   uint8_t *hp = (uint8_t *)ctx->hTq, *dp = (uint8_t *)ctx->dTq;
   memcpy(hp + o_tus, tus, (size_t)n * sizeof(hevcdl_tu));
   memcpy(hp + o_resi, resi, nelem * 2);
+  if (rdoq) {
+    memcpy(hp + o_rq, rdoq, (size_t)n * sizeof(hevcdl_tu_rdoq));
+    memcpy(hp + o_est, est, (size_t)n_est * HEVCDL_EST_INTS * 4);
+  }
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(dp, hp, o_coeff, cudaMemcpyHostToDevice, st));
   // gaps between TU blocks (if the caller's offsets leave any) come back as zeros, not as stale bytes
   CK(cudaMemsetAsync(dp + o_coeff, 0, total - o_coeff, st));
-  const int grid = (n + TQ_WARPS - 1) / TQ_WARPS < 8 * ctx->numSMs ? (n + TQ_WARPS - 1) / TQ_WARPS : 8 * ctx->numSMs;
   k_tu_code<<<grid, TQ_WARPS * 32, sizeof(TqBlockS), st>>>(n, (const hevcdl_tu *)(dp + o_tus), (const int16_t *)(dp + o_resi),
                                                             coeff ? (int32_t *)(dp + o_coeff) : nullptr, (int16_t *)(dp + o_level),
                                                             deq ? (int32_t *)(dp + o_deq) : nullptr, (int16_t *)(dp + o_rec),
-                                                            (uint32_t *)(dp + o_asum), ssd ? (uint64_t *)(dp + o_ssd) : nullptr);
+                                                            (uint32_t *)(dp + o_asum), ssd ? (uint64_t *)(dp + o_ssd) : nullptr,
+                                                            rdoq ? (const hevcdl_tu_rdoq *)(dp + o_rq) : nullptr,
+                                                            rdoq ? (const int *)(dp + o_est) : nullptr, (RdoqScratch *)ctx->dRdoq);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
   CK(cudaMemcpyAsync(hp + o_coeff, dp + o_coeff, total - o_coeff, cudaMemcpyDeviceToHost, st));
@@ -855,6 +879,11 @@ int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *
   memcpy(abs_sum, hp + o_asum, (size_t)n * 4);
   if (ssd) memcpy(ssd, hp + o_ssd, (size_t)n * 8);
   return HEVCDL_OK;
+}
+
+int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level,
+                   int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd) {
+  return hevcdl_tu_code_rdoq(ctx, n, tus, nullptr, nullptr, 0, resi, nelem, coeff, level, deq, rec, abs_sum, ssd);
 }
 
 int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int iters, float ms[3], int *launches) {

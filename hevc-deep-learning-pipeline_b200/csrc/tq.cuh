@@ -18,13 +18,17 @@
 namespace hevcdl {
 
 // hevcdl_tu.flags
-constexpr int TQ_DST = 1, TQ_TSKIP = 2, TQ_INTER = 4;
+constexpr int TQ_DST = 1, TQ_TSKIP = 2, TQ_INTER = 4, TQ_RDOQ = 8, TQ_COEFF_IN = 16;
 
 __device__ __constant__ int8_t c_tq_cos[32] = {0, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
                                                61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4};
 __device__ __constant__ int8_t c_tq_dst[16] = {29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29};
 __device__ __constant__ int c_tq_qscale[6] = {26214, 23302, 20560, 18396, 16384, 14564};   // g_quantScales, TComRom.cpp:354
 __device__ __constant__ int c_tq_iqscale[6] = {40, 45, 51, 57, 64, 72};                    // g_invQuantScales
+
+}  // namespace hevcdl
+#include "tq_rdoq.cuh"
+namespace hevcdl {
 
 // entry (k, n) of the N-point core transform matrix (HEVC 8.6.4.2; TComRom.cpp:368-520 spells it out as macros)
 __device__ __forceinline__ int tq_matrix(int lgN, int k, int n) {
@@ -97,7 +101,7 @@ __device__ __forceinline__ void tq_pass(const __half *__restrict__ A, const int3
 __global__ void __launch_bounds__(TQ_WARPS * 32)
 k_tu_code(int n, const hevcdl_tu *__restrict__ tus, const int16_t *__restrict__ resi, int32_t *__restrict__ coeff_out,
           int16_t *__restrict__ level_out, int32_t *__restrict__ deq_out, int16_t *__restrict__ rec_out, uint32_t *__restrict__ abs_sum_out,
-          uint64_t *__restrict__ ssd_out) {
+          uint64_t *__restrict__ ssd_out, const hevcdl_tu_rdoq *__restrict__ rq, const int *__restrict__ est_tabs, RdoqScratch *__restrict__ scratch) {
   extern __shared__ __align__(16) uint8_t tq_smem[];
   TqBlockS &S = *reinterpret_cast<TqBlockS *>(tq_smem);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -124,7 +128,9 @@ k_tu_code(int n, const hevcdl_tu *__restrict__ tus, const int16_t *__restrict__ 
     __syncwarp();
     for (int i = lane; i < n2; i += 32) W.a[i] = resi[off + i];
     __syncwarp();
-    if (tskip) {                                                       // xTransformSkip, TComTrQuant.cpp:2010-2052
+    if (flags & TQ_COEFF_IN) {
+      // the caller hands over transform coefficients: quantiser, dequantiser and inverse transform only
+    } else if (tskip) {                                                // xTransformSkip, TComTrQuant.cpp:2010-2052
       for (int i = lane; i < n2; i += 32) W.a[i] = W.a[i] << tshift;
     } else {                                                           // xTrMxN, :860-925
       const int s1 = lg + 8 + 6 - 15, s2 = lg + 6;
@@ -142,12 +148,23 @@ k_tu_code(int n, const hevcdl_tu *__restrict__ tus, const int16_t *__restrict__ 
     const int tib = min(16, 32 + rs - 7);
     const int imin = -(1 << (tib - 1)), imax = (1 << (tib - 1)) - 1;
     uint32_t asum = 0;
+    // the quantiser: xQuant's flat branch, or (HEVCDL_TU_RDOQ) the rate-distortion optimised one of tq_rdoq.cuh
+    const bool use_rdoq = rq != nullptr && (flags & TQ_RDOQ);
+    RdoqScratch *RS = use_rdoq ? scratch + (blockIdx.x * TQ_WARPS + wid) : nullptr;
+    if (use_rdoq) {
+      const hevcdl_tu_rdoq r = rq[tu];
+      asum = rdoq_tu(W.a, lg, r.channel, r.scan_type, d.qp, r.lambda, est_tabs + (size_t)r.est_index * EST_INTS, r.ctx_cbf, r.flags, *RS, lane);
+    }
     for (int i = lane; i < n2; i += 32) {
       const int c = W.a[i];
-      const int mag = (int)(((long long)abs(c) * qs + qadd) >> qbits);
-      asum += (uint32_t)mag;
-      int q = c < 0 ? -mag : mag;
-      q = max(-32768, min(32767, q));
+      int q;
+      if (use_rdoq) q = RS->level[i];
+      else {
+        const int mag = (int)(((long long)abs(c) * qs + qadd) >> qbits);
+        asum += (uint32_t)mag;
+        q = c < 0 ? -mag : mag;
+        q = max(-32768, min(32767, q));
+      }
       const int cq = max(imin, min(imax, q));
       int v = rs > 0 ? (cq * iqs + (1 << (rs - 1))) >> rs : (int)((uint32_t)(cq * iqs) << (-rs));
       v = max(-32768, min(32767, v));
@@ -156,8 +173,10 @@ k_tu_code(int n, const hevcdl_tu *__restrict__ tus, const int16_t *__restrict__ 
       if (deq_out) deq_out[off + i] = v;
       W.b[tskip ? i : (i & (N - 1)) * N + (i >> lg)] = v;
     }
+    if (!use_rdoq) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    }
     __syncwarp();
     if (tskip) {                                                       // xITransformSkip, :2060-2104
       const int offs = tshift == 0 ? 0 : 1 << (tshift - 1);

@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
@@ -48,7 +48,9 @@ class FrameView(C.Structure):
 
 
 TU_DTYPE = np.dtype([("log2_size", "u1"), ("qp", "u1"), ("flags", "u1"), ("reserved", "u1"), ("offset", "<u4")])
-TU_DST, TU_TSKIP, TU_INTER = 1, 2, 4
+TU_DST, TU_TSKIP, TU_INTER, TU_RDOQ, TU_COEFF_IN = 1, 2, 4, 8, 16
+TU_RDOQ_DTYPE = np.dtype([("lambda", "<f8"), ("est_index", "<u4"), ("channel", "u1"), ("scan_type", "u1"), ("ctx_cbf", "u1"), ("flags", "u1")])
+EST_INTS = 224
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("part", "u1"), ("ctu", "<u2")])
 
 
@@ -100,6 +102,7 @@ def load_library():
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
     L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
+    L.hevcdl_tu_code_rdoq.argtypes = [vp, ip, vp, vp, vp, ip, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -252,10 +255,11 @@ class DepthPredictor:
         return satd, cand, ncand
 
     # -- transform-unit coding core --------------------------------------------------------------
-    def tu_code(self, blocks, qps, flags=None, want_coeff=True, want_deq=True):
+    def tu_code(self, blocks, qps, flags=None, want_coeff=True, want_deq=True, rdoq=None, est=None):
         """blocks: list of (N,N) int16 residual blocks (N = 4, 8, 16, 32); qps, flags: per block.  Forward transform, flat
-        quantiser, dequantiser, inverse transform (hevcdl_tu_code).  Returns dict of per-block lists coeff / level / deq /
-        rec plus arrays abs_sum, ssd."""
+        quantiser, dequantiser, inverse transform (hevcdl_tu_code).  rdoq (TU_RDOQ_DTYPE array, one per block) + est
+        ([n_est, 224] int32 bit-estimate tables): blocks flagged TU_RDOQ go through the rate-distortion optimised quantiser
+        (hevcdl_tu_code_rdoq).  Returns dict of per-block lists coeff / level / deq / rec plus arrays abs_sum, ssd."""
         n = len(blocks)
         tus = np.zeros(n, TU_DTYPE)
         sizes = np.array([b.shape[0] for b in blocks], np.int64)
@@ -272,8 +276,15 @@ class DepthPredictor:
         rec = np.zeros(nelem, np.int16)
         asum = np.zeros(n, np.uint32)
         ssd = np.zeros(n, np.uint64)
-        self._ck(self.lib.hevcdl_tu_code(self.h, n, _ptr(tus), _ptr(resi), nelem, _ptr(coeff), _ptr(level), _ptr(deq), _ptr(rec),
-                                         _ptr(asum), _ptr(ssd)), "tu_code")
+        if rdoq is None:
+            self._ck(self.lib.hevcdl_tu_code(self.h, n, _ptr(tus), _ptr(resi), nelem, _ptr(coeff), _ptr(level), _ptr(deq), _ptr(rec),
+                                             _ptr(asum), _ptr(ssd)), "tu_code")
+        else:
+            rq = np.ascontiguousarray(rdoq, TU_RDOQ_DTYPE)
+            et = np.ascontiguousarray(est, np.int32).reshape(-1, EST_INTS)
+            assert len(rq) == n
+            self._ck(self.lib.hevcdl_tu_code_rdoq(self.h, n, _ptr(tus), _ptr(rq), _ptr(et), len(et), _ptr(resi), nelem, _ptr(coeff),
+                                                  _ptr(level), _ptr(deq), _ptr(rec), _ptr(asum), _ptr(ssd)), "tu_code_rdoq")
 
         def split(a):
             return None if a is None else [a[off[i]:off[i + 1]].reshape(sizes[i], sizes[i]) for i in range(n)]

@@ -28,10 +28,10 @@
 //                     (InputFile, FrameSkip, FramesToBeEncoded); every prefetched frame is checked against the planes HM
 //                     hands over for that frame id (hash of all three planes) -- on a mismatch the prefetch is dropped
 //                     and the frame is uploaded from HM's planes as without lookahead.  8-bit 4:2:0 input without padding only.
-//   HEVCDL_TQ         1 = transform + flat quantiser + dequantiser + inverse transform of every TU of xIntraCodingTUBlock on the
-//                     device (hevcdl_tu_code, one synchronous call per TU): byte-identical bitstreams when the encoder runs
-//                     with --RDOQ=0 --RDOQTS=0 --SignHideFlag=0 (RDOQ and sign-bit hiding are not on the device); TUs the
-//                     core does not cover stay HM's (hm_plugin/rmd_hook.h)
+//   HEVCDL_TQ         1 = transform + quantiser (flat, or the rate-distortion optimised one with sign-bit hiding when the encoder
+//                     runs with RDOQ, its default) + dequantiser + inverse transform of every TU of xIntraCodingTUBlock on
+//                     the device (hevcdl_tu_code / hevcdl_tu_code_rdoq, one synchronous call per TU): byte-identical
+//                     bitstreams; TUs the core does not cover stay HM's (hm_plugin/rmd_hook.h)
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
 //                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
 //                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
@@ -490,8 +490,10 @@ bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu
 }
 
 // TU-coding hook (rmd_hook.h): called from the reference's xIntraCodingTUBlock in place of transformNxN + invTransformNxN.
+static_assert( sizeof(estBitsSbacStruct) == HEVCDL_EST_INTS * sizeof(int32_t), "hevcdl_tu_code_rdoq takes the reference's estBitsSbacStruct as is" );
+
 bool hevcdl_hm_tu_code( TComDataCU* pcCU, TComTU& rTu, int compIDi, short* piResi, unsigned uiStride, int* pcCoeff, int* puiAbsSum,
-                        int qp, bool useTransformSkip, bool rdoqOn )
+                        int qp, bool useTransformSkip, bool rdoqOn, const void* estBits )
 {
   HevcdlSession &S = g_session;
   if ( !S.gpu_tq || !S.ctx ) return false;
@@ -500,8 +502,10 @@ bool hevcdl_hm_tu_code( TComDataCU* pcCU, TComTU& rTu, int compIDi, short* piRes
   const TComRectangle &rect = rTu.getRect( compID );
   const UInt n = rect.width;
   // what the device core covers (csrc/tq.cuh): square 4..32 TUs, flat quantiser, no bypass, no scaling lists, 8-bit
-  if ( rdoqOn || rect.width != rect.height || n < 4 || n > 32 || pcCU->getCUTransquantBypass( uiAbsPartIdx ) ||
-       pcCU->getSlice()->getPPS()->getSignDataHidingEnabledFlag() || pcCU->getSlice()->getSPS()->getScalingListFlag() ||
+  // (the flat quantiser's own sign-bit hiding, signBitHidingHDQ, is not on the device: flat + SDH stays HM's)
+  const bool sdh = pcCU->getSlice()->getPPS()->getSignDataHidingEnabledFlag();
+  if ( rect.width != rect.height || n < 4 || n > 32 || pcCU->getCUTransquantBypass( uiAbsPartIdx ) || ( !rdoqOn && sdh ) ||
+       pcCU->getSlice()->getSPS()->getScalingListFlag() ||   /* RDOQ_CHROMA is 1 in the reference (TComTrQuant.cpp:64): chroma TUs take the same quantiser */
        qp < 0 || qp > 51 || ( useTransformSkip && n != 4 ) )
   {
     S.tq_declined++;
@@ -518,7 +522,21 @@ bool hevcdl_hm_tu_code( TComDataCU* pcCU, TComTU& rTu, int compIDi, short* piRes
   tu.reserved = 0;
   tu.offset = 0;
   uint32_t absSum = 0;
-  const int rc = hevcdl_tu_code( S.ctx, 1, &tu, resi, (size_t)n * n, NULL, level, NULL, rec, &absSum, NULL );
+  int rc;
+  if ( rdoqOn )
+  {
+    // what xRateDistOptQuant reads from encoder state (TComTrQuant.cpp:2130-2205, 2446-2460)
+    hevcdl_tu_rdoq rq;
+    rq.lambda = pcCU->getSlice()->getLambdas()[compID];      // = TComTrQuant::m_dLambda after selectLambda(compID) (TEncSlice.cpp:133,139)
+    rq.est_index = 0;
+    rq.channel = (uint8_t)toChannelType( compID );
+    rq.scan_type = (uint8_t)pcCU->getCoefScanIdx( uiAbsPartIdx, n, n, compID );
+    rq.ctx_cbf = (uint8_t)( pcCU->getCtxQtCbf( rTu, toChannelType( compID ) ) + getCBFContextOffset( compID ) );
+    rq.flags = (uint8_t)( ( sdh ? 1 : 0 ) | ( pcCU->isIntra( uiAbsPartIdx ) ? 2 : 0 ) | ( pcCU->getTransformIdx( uiAbsPartIdx ) == 0 ? 4 : 0 ) );
+    tu.flags |= HEVCDL_TU_RDOQ;
+    rc = hevcdl_tu_code_rdoq( S.ctx, 1, &tu, &rq, (const int32_t*)estBits, 1, resi, (size_t)n * n, NULL, level, NULL, rec, &absSum, NULL );
+  }
+  else rc = hevcdl_tu_code( S.ctx, 1, &tu, resi, (size_t)n * n, NULL, level, NULL, rec, &absSum, NULL );
   if ( rc ) HevcdlSession::die( "hevcdl_tu_code", rc, S.ctx );
   S.tq_calls++;
   // exactly what transformNxN (TComTrQuant.cpp:1450-1534) and the inverse-transform if/else (TEncSearch.cpp:1310-1328) leave behind

@@ -20,11 +20,14 @@ class TComTU;
  * TEncSearch::xIntraCodingTUBlock (TEncSearch.cpp:1301 m_pcTrQuant->transformNxN(...) through the inverse-transform
  * if/else ending before :1330 "//===== reconstruction =====") is wrapped in `if ( !hevcdl_hm_tu_code(...) ) { ... }` by a third
  * sed rule of hm_plugin/Makefile.  When the TU is one the device core covers -- flat quantiser, i.e. the encoder runs with
- * --RDOQ=0 --RDOQTS=0 --SignHideFlag=0, no transquant bypass -- the hook sends the residual block through hevcdl_tu_code
- * (one synchronous call per TU: a parity demonstration like HEVCDL_RMD=2, not a speed-up), writes levels, cbf, uiAbsSum and
- * the reconstructed residual exactly where the reference code would, and the bitstream stays byte-identical to the
- * reference run with the same options.  Otherwise it returns false and the reference code runs. */
+ * --RDOQ=0 --RDOQTS=0 --SignHideFlag=0, no transquant bypass -- or the rate-distortion optimised quantiser of the reference's
+ * default options (RDOQ 1, RDOQTS 1, SignHideFlag 1: hevcdl_tu_code_rdoq, fed the CABAC bit-estimate table TEncSbac::estBit
+ * has just filled, the component's lambda, the scan type and the cbf context) -- the hook sends the residual block to the
+ * device (one synchronous call per TU: a parity demonstration like HEVCDL_RMD=2, not a speed-up), writes levels, cbf,
+ * uiAbsSum and the reconstructed residual exactly where the reference code would, and the bitstream stays byte-identical to
+ * the reference run with the same options.  Otherwise (RDOQ on with sign-bit hiding off or vice versa is covered too; transquant
+ * bypass, scaling lists, non-square TUs are not) it returns false and the reference code runs. */
 bool hevcdl_hm_tu_code( TComDataCU* pcCU, TComTU& rTu, int compID, short* piResi, unsigned uiStride, int* pcCoeff, int* puiAbsSum,
-                        int qp, bool useTransformSkip, bool rdoqOn );
+                        int qp, bool useTransformSkip, bool rdoqOn, const void* estBits );
 bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu, unsigned y0InCu, unsigned width, unsigned mode,
                          const short* org, unsigned orgStride, unsigned* sad );

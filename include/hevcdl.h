@@ -177,8 +177,32 @@ typedef struct {
 #define HEVCDL_TU_DST 1    /* 4x4 intra luma: DST-VII (TComTU::useDST) */
 #define HEVCDL_TU_TSKIP 2  /* transform skip */
 #define HEVCDL_TU_INTER 4  /* rounding offset 85/512 instead of 171/512 (non-I slices) */
+#define HEVCDL_TU_RDOQ 8   /* hevcdl_tu_code_rdoq only: quantise this TU with the rate-distortion optimised quantiser */
+#define HEVCDL_TU_COEFF_IN 16 /* `resi` holds this TU's transform coefficients (16-bit by construction) instead of its residual: the
+                                 forward transform is skipped; ssd[i] is meaningless for such a TU */
 int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff,
                    int16_t *level, int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd);
+
+/* The same with the reference's rate-distortion optimised quantiser, TComTrQuant::xRateDistOptQuant (HM TLibCommon/
+ * TComTrQuant.cpp:2119-2670, sign-bit hiding included), for the TUs flagged HEVCDL_TU_RDOQ -- the reference's operating point
+ * (RDOQ 1, RDOQTS 1, SignHideFlag 1).  rdoq[i] carries what the reference reads from encoder state for TU i: the lambda of the
+ * component (TComTrQuant::m_dLambda after selectLambda = TComSlice::getLambdas()[compID]), the scan type
+ * (TComDataCU::getCoefScanIdx), the cbf context (getCtxQtCbf + getCBFContextOffset) and the index of the CABAC bit-estimate
+ * table in force (estBitsSbacStruct as filled by TEncSbac::estBit before the call, TEncSearch.cpp:1282-1286): est holds n_est
+ * tables of HEVCDL_EST_INTS int32 each, in the reference's own struct layout.  Bit-exact: every level decision compares
+ * double-precision costs built in the reference's order of operations.  Synchronous. */
+#define HEVCDL_EST_INTS 224
+typedef struct {
+  double lambda;
+  uint32_t est_index;
+  uint8_t channel;         /* 0 luma, 1 chroma */
+  uint8_t scan_type;       /* 0 diagonal, 1 horizontal, 2 vertical */
+  uint8_t ctx_cbf;
+  uint8_t flags;           /* bit 0: sign-bit hiding enabled, bit 1: intra CU, bit 2: transform index of the CU is 0 */
+} hevcdl_tu_rdoq;
+int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevcdl_tu_rdoq *rdoq, const int32_t *est, int n_est,
+                        const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level, int32_t *deq, int16_t *rec,
+                        uint32_t *abs_sum, uint64_t *ssd);
 
 /* Page-locked host memory for frame planes handed over with hevcdl_cfg.pinned_input = 1 (any page-locked memory will do;
  * this is the allocator for callers without a CUDA runtime of their own).  write_combined != 0: cudaHostAllocWriteCombined --

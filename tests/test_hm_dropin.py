@@ -232,8 +232,14 @@ def test_dropin_tu_core_on_the_device_keeps_the_bitstream(tmp_path, built, host,
     m = re.search(r"TUs coded on the device (\d+) / left to HM (\d+)", rb["stderr"])
     assert m and int(m.group(1)) > 1000 and int(m.group(2)) == 0, rb["stderr"][-300:]
     assert ra["sha1"] == rb["sha1"] and (ra["kbps"], ra["psnr_y"]) == (rb["kbps"], rb["psnr_y"])
-    # with RDOQ on (the reference's operating point) the hook must step aside and the stream still equals the reference's
+    # the reference's operating point (RDOQ, RDOQTS, sign-bit hiding on): every TU goes through the device RDOQ
+    # (hevcdl_tu_code_rdoq fed HM's live CABAC bit-estimate tables) and the stream again equals the reference's
     rc = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, out="rdoq.bin", env={"HEVCDL_TQ": "1", "HEVCDL_VERBOSE": "1"})
     rd = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp, out="rdoq.bin")
     m = re.search(r"TUs coded on the device (\d+) / left to HM (\d+)", rc["stderr"])
-    assert m and int(m.group(1)) == 0 and int(m.group(2)) > 1000 and rc["sha1"] == rd["sha1"]
+    assert m and int(m.group(1)) > 1000 and int(m.group(2)) == 0, rc["stderr"][-300:]
+    assert rc["sha1"] == rd["sha1"] and (rc["kbps"], rc["psnr_y"]) == (rd["kbps"], rd["psnr_y"])
+    # mixed: RDOQ on, sign-bit hiding off
+    re_ = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, out="m.bin", extra=("--SignHideFlag=0",), env={"HEVCDL_TQ": "1"})
+    rf = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp, out="m.bin", extra=("--SignHideFlag=0",))
+    assert re_["rc"] == 0 and re_["sha1"] == rf["sha1"]
