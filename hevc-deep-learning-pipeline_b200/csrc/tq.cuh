@@ -2,8 +2,9 @@
 // forward core transform (DCT 4..32 / DST 4 / transform skip) -> flat quantiser -> dequantiser -> inverse transform for a
 // batch of TUs, bit-exact with the reference's TComTrQuant::transformNxN / invTransformNxN
 // (HM TLibCommon/TComTrQuant.cpp:1450-1666: xT -> xTrMxN :860, xQuant :1126 non-RDOQ branch, xDeQuant :1308, xIT -> xITrMxN :927)
-// at the reference's operating point (8-bit video, dynamic range 15, no scaling lists).  RDOQ (:2119) and sign-bit hiding
-// (:991) are not on the device yet.
+// at the reference's operating point (8-bit video, dynamic range 15, no scaling lists).  The rate-distortion optimised
+// quantiser (xRateDistOptQuant :2119, with its sign-bit hiding) is tq_rdoq.cuh; the flat quantiser's own sign-bit hiding
+// (signBitHidingHDQ :991) is not on the device.
 //
 // Every 1-D pass is a small dense integer contraction  C = A x B,  A = the core matrix (|a| <= 90) or its transpose,
 // B = 16..19-bit data.  It runs on the tensor cores as mma.sync m16n8k16 with fp16 operands and fp32 accumulation, EXACTLY:

@@ -406,3 +406,50 @@ def test_two_contexts_interleaved(built, host, pkg):
         assert (vb["labels"] == want_b[i][0]).all() and (vb["satd"] == want_b[i][1]).all()
         a.release(i); b.release(i)
     a.close(); b.close()
+
+
+def test_output_flags_pinned_input_and_host_alloc(built, host, pkg):
+    """hevcdl_cfg.outputs = 0 (the C default): labels, PU list and candidates come back, logits / SATD tables do not, and asking
+    for them is an error, not stale memory.  pinned_input = 1 with planes from hevcdl_host_alloc gives the same results as the
+    staged path."""
+    w, h = 416, 240
+    Y, U, V = pkg.synth.synth_frame(w, h, 9)
+    full = _mk(host, w, h, 1, rmd=True)
+    full.submit(0, Y, U, V)
+    want = {k: v.copy() for k, v in full.view(0).items()}
+    full.release(0); full.close()
+    buf = host.PinnedBuffer(w * h * 3 // 2)
+    a = buf.a
+    a[:w * h] = Y.ravel(); a[w * h:w * h * 5 // 4] = U.ravel(); a[w * h * 5 // 4:] = V.ravel()
+    slim = _mk(host, w, h, 1, rmd=True, outputs=0, pinned_input=True, numa_bind=True)
+    slim.submit(0, a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), a[w * h * 5 // 4:].reshape(h // 2, w // 2))
+    v = slim.view(0)
+    for k in ("labels", "ctu_off", "pus", "cand"):
+        assert (v[k] == want[k]).all(), k
+    assert v["logits"].size == 0 and v["satd"].size == 0
+    with pytest.raises(host.HevcdlError):
+        slim.labels(0, want_logits=True)
+    pus, satd, cand = slim.pus(0)
+    assert satd is None and (cand == want["cand"]).all()
+    slim.release(0); slim.close(); buf.close()
+    assert host.numa_bind_thread(0) >= 0
+
+
+def test_results_do_not_depend_on_programmatic_dependent_launch(built, host, pkg, tmp_path):
+    """Every kernel of the pipeline starts early under programmatic dependent launch and orders itself behind its predecessor
+    with griddepcontrol.wait; HEVCDL_NO_PDL=1 launches in plain stream order.  Both must give identical bytes (a missing wait
+    in a warp that stores to global memory would show up as a difference here)."""
+    import subprocess, sys
+    code = ("import sys, importlib, numpy as np; sys.path.insert(0, %r); pkg = importlib.import_module('hevc-deep-learning-pipeline_b200'); "
+            "host = importlib.import_module('hevc-deep-learning-pipeline_b200.host'); "
+            "dp = host.DepthPredictor(1920, 1080, precision=1, rmd=True, slots=8, batch=4); "
+            "[dp.submit(i, *pkg.synth.synth_frame(1920, 1080, 40 + (i & 1))) for i in range(8)]; "
+            "out = [dp.view(i) for i in range(8)]; "
+            "np.savez(sys.argv[1], **{'%%s%%d' %% (k, i): v[k] for i, v in enumerate(out) for k in ('labels', 'logits', 'satd', 'cand', 'pus')})") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = []
+    for name, env in (("pdl", {}), ("nopdl", {"HEVCDL_NO_PDL": "1"})):
+        f = str(tmp_path / (name + ".npz"))
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, **env), timeout=600)
+        files.append(np.load(f))
+    for k in files[0].files:
+        assert (files[0][k] == files[1][k]).all(), k

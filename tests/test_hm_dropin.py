@@ -243,3 +243,24 @@ def test_dropin_tu_core_on_the_device_keeps_the_bitstream(tmp_path, built, host,
     re_ = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, out="m.bin", extra=("--SignHideFlag=0",), env={"HEVCDL_TQ": "1"})
     rf = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp, out="m.bin", extra=("--SignHideFlag=0",))
     assert re_["rc"] == 0 and re_["sha1"] == rf["sha1"]
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_sidecar_accepts_sizes_that_are_not_multiples_of_8(tmp_path, built, host, oracle, weights, pkg, monkeypatch):
+    """The reference sidecar takes any even picture size (PIL pads its crops with black, use_model.py:92-93).  Ours pads the
+    planes to the next multiple of 8 with video black, which converts to RGB (0,0,0): the labels must equal the oracle's on
+    the UNPADDED picture (whose crops are zero-padded exactly like PIL's)."""
+    import importlib
+    sidecar = importlib.import_module("hevc-deep-learning-pipeline_b200.sidecar")
+    w, h = 100, 70
+    Y, U, V = pkg.synth.synth_frame(104, 72, 5)
+    Y, U, V = np.ascontiguousarray(Y[:h, :w]), np.ascontiguousarray(U[:h // 2, :w // 2]), np.ascontiguousarray(V[:h // 2, :w // 2])
+    hm_util.write_yuv(str(tmp_path / "in.yuv"), [(Y, U, V)])
+    (tmp_path / "bitstream.cfg").write_text(BITSTREAM_CFG.format(yuv="in.yuv", w=w, h=h, n=1))
+    monkeypatch.chdir(tmp_path)
+    sidecar.main(["gen_frames"])
+    sidecar.main(["use_model", "--precision", "fp32"])
+    olab = oracle.frame_labels(weights, Y, U, V)
+    got = np.array([[int(t) for t in open(tmp_path / "pred" / "0" / ("ctu%d.txt" % i)).read().split()] for i in range(len(olab))], np.uint8)
+    assert got.shape == olab.shape == (4, 16) and (got == olab).all()
