@@ -23,7 +23,7 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def build():
     """Compile the C restatement (gcc, seconds)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c", "rdoq_oracle.c")]
+    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c", "rdoq_oracle.c", "dbf_oracle.c")]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so] + srcs + ["-lm"])
     return so
@@ -63,6 +63,8 @@ def lib():
         L.oracle_tq_tu.restype = C.c_uint32
         L.oracle_rdoq.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
         L.oracle_rdoq.restype = C.c_uint32
+        L.oracle_deblock_frame.argtypes = [i16p, C.c_int, i16p, i16p, C.c_int, C.c_int, C.c_int, u8p, np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS"),
+                                           C.c_int, C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -254,3 +256,13 @@ def rdoq(coeff, ch, scan_type, qp, tskip, lam, est, ctx_cbf, is_intra=1, tr_idx_
     s = lib().oracle_rdoq(np.ascontiguousarray(coeff, np.int32), int(n).bit_length() - 1, int(ch), int(scan_type), int(qp), int(tskip),
                           float(lam), np.ascontiguousarray(est, np.int32), int(ctx_cbf), int(is_intra), int(tr_idx_zero), int(sdh), out)
     return out, int(s)
+
+
+def deblock_frame(Y, U, V, tu_log2, qp, beta_off_div2=0, tc_off_div2=0, cb_qp_off=0, cr_qp_off=0):
+    """Deblocking filter of an all-intra picture (oracle/dbf_oracle.c).  Y, U, V: 8-bit planes (any integer dtype); tu_log2, qp: one
+    entry per 4x4 luma unit ((H/4, W/4) or flat).  Returns the filtered planes as uint8."""
+    H, W = Y.shape
+    y, u, v = (np.ascontiguousarray(p, np.int16).copy() for p in (Y, U, V))
+    lib().oracle_deblock_frame(y, W, u, v, W // 2, W, H, np.ascontiguousarray(tu_log2, np.uint8).ravel(), np.ascontiguousarray(qp, np.int8).ravel(),
+                               int(beta_off_div2), int(tc_off_div2), int(cb_qp_off), int(cr_qp_off))
+    return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)

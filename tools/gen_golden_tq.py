@@ -4,6 +4,7 @@ container (needs /root/reference and `make -C oracle ref`); the fixtures travel,
 
   tests/golden/tq_transform_ref.npz   random and extreme blocks through the reference's OWN xTrMxN / xITrMxN
                                       (oracle/_ref/libtqref.so = tq_ref_harness.cpp linked with libhmref.a), every size + DST
+  tests/golden/dbf_pictures.npz       reconstructed pictures before / after the reference's own deblocking filter + its TU / QP maps
   tests/golden/tq_rdoq_192x128_qp32.npz    calls of the reference's xRateDistOptQuant (inputs incl. the CABAC bit-estimate
                                       tables, outputs) dumped by oracle/_ref/TAppEncoder_rdoqtrace at the default options
   tests/golden/tq_trace_192x128_qp32.npz   per-TU dumps printed by oracle/_ref/TAppEncoder_tqtrace (the reference built with
@@ -192,7 +193,44 @@ def rdoq_vectors(per_class=7):
     print("tq_rdoq_192x128_qp32.npz:", len(rs), "calls,", os.path.getsize(os.path.join(GOLD, "tq_rdoq_192x128_qp32.npz")), "bytes")
 
 
+def dbf_vectors():
+    """tests/golden/dbf_pictures.npz: reconstructed pictures right before and right after the reference's own deblocking filter
+    (oracle/_ref/TAppEncoder_dbftrace, oracle/dbf_dump.h) with the TU-size and QP maps it reads: the 192x128 fixture frame at
+    QP 22 and 37 and the 416x240 frame (partial CTUs on both edges) at QP 32."""
+    cases = []
+    g = np.load(os.path.join(GOLD, "rmd_trace_192x128_qp32.npz"))
+    cases += [(g["Y"], g["U"], g["V"], g["labels"], 22), (g["Y"], g["U"], g["V"], g["labels"], 37)]
+    c = np.load(os.path.join(GOLD, "cnn_labels_416x240.npz"))
+    cases.append((c["Y"], c["U"], c["V"], c["labels"], 32))
+    out = {}
+    for k, (Y, U, V, labels, qp) in enumerate(cases):
+        H, W = Y.shape
+        with tempfile.TemporaryDirectory() as td:
+            hm_util.write_yuv(os.path.join(td, "in.yuv"), [(Y, U, V)])
+            hm_util.write_pred(os.path.join(td, "pred"), 0, labels)
+            cmd = [os.path.join(REFDIR, "TAppEncoder_dbftrace"), "-c", hm_util.CFG, "-i", "in.yuv", "-wdt", str(W), "-hgt", str(H), "-fr", "30",
+                   "-f", "1", "-q", str(qp), "-b", "t.bin", "--InputBitDepth=8", "--InputChromaFormat=420", "--Level=6.2"]
+            subprocess.check_call(cmd, cwd=td, env=dict(os.environ, HEVCDL_DBF_DUMP=os.path.join(td, "dbf.bin")), stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            raw = open(os.path.join(td, "dbf.bin"), "rb").read()
+        off = 0
+        for phase in (0, 1):
+            hdr = np.frombuffer(raw, np.int32, 12, off).copy(); off += 48
+            assert hdr[0] == 0x44424630 and hdr[1] == phase and hdr[2] == W and hdr[3] == H and hdr[9] == 1
+            for name, n in (("Y", W * H), ("U", W * H // 4), ("V", W * H // 4)):
+                out["%s%d_%d" % (name, phase, k)] = np.frombuffer(raw, np.int16, n, off).astype(np.uint8); off += 2 * n
+            if phase == 0:
+                out["hdr_%d" % k] = hdr
+                out["tu_%d" % k] = np.frombuffer(raw, np.uint8, (W // 4) * (H // 4), off).copy(); off += (W // 4) * (H // 4)
+                out["qp_%d" % k] = np.frombuffer(raw, np.int8, (W // 4) * (H // 4), off).copy(); off += (W // 4) * (H // 4)
+        print("case", k, W, H, qp, "samples changed by the reference's filter:", int((out["Y0_%d" % k] != out["Y1_%d" % k]).sum()))
+    out["ncases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, "dbf_pictures.npz"), **out)
+    print("dbf_pictures.npz:", os.path.getsize(os.path.join(GOLD, "dbf_pictures.npz")), "bytes")
+
+
 if __name__ == "__main__":
     transform_vectors()
     trace_vectors()
     rdoq_vectors()
+    dbf_vectors()
