@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "rmd.cuh"
 #include "tq.cuh"
+#include "dbf.cuh"
 #include "../../include/hevcdl_internal.h"
 
 using namespace hevcdl;
@@ -88,6 +89,10 @@ struct hevcdl_ctx {
   int rmdBlocks = 0;                   // persistent grid of k_rmd_items: resident blocks per SM x SMs
   std::string err;
   hevcdl_stats_t stats{};
+  // scratch for hevcdl_deblock_frame
+  void *dDbf = nullptr;
+  void *hDbf = nullptr;
+  size_t dbfCap = 0;
   // scratch for hevcdl_tu_code
   void *dRdoq = nullptr;               // RdoqScratch per resident warp of k_tu_code (RDOQ launches only)
   int rdoqWarps = 0;
@@ -629,7 +634,8 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     if (s.evT1) cudaEventDestroy(s.evT1);
     if (s.evT2) cudaEventDestroy(s.evT2);
   }
-  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact); cudaFree(ctx->dTq); cudaFree(ctx->dRdoq);
+  cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact); cudaFree(ctx->dTq); cudaFree(ctx->dRdoq); cudaFree(ctx->dDbf);
+  if (ctx->hDbf) cudaFreeHost(ctx->hDbf);
   if (ctx->hExact) cudaFreeHost(ctx->hExact);
   if (ctx->hTq) cudaFreeHost(ctx->hTq);
   tc_release(&ctx->tc);
@@ -805,6 +811,52 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
   if (satd) memcpy(satd, hp + o_satd, (size_t)n * 35 * 4);
   if (cand) memcpy(cand, hp + o_cand, (size_t)n * 10);
   if (ncand) memcpy(ncand, hp + o_nc, n);
+  return HEVCDL_OK;
+}
+
+int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int sc, int W, int H, const uint8_t *tu_log2, const int8_t *qp,
+                         int beta_off, int tc_off, int cb_off, int cr_off) {
+  if (!ctx || !y || !u || !v || !tu_log2 || !qp || W < 8 || H < 8 || (W & 7) || (H & 7) || W > 8192 || H > 8192 || sy < W || sc < W / 2 ||
+      beta_off < -6 || beta_off > 6 || tc_off < -6 || tc_off > 6 || cb_off < -12 || cb_off > 12 || cr_off < -12 || cr_off > 12)
+    return HEVCDL_E_INVAL;
+  const size_t nu = (size_t)(W / 4) * (H / 4);
+  for (size_t i = 0; i < nu; i++)
+    if (tu_log2[i] < 2 || tu_log2[i] > 5 || qp[i] < 0 || qp[i] > 51) { ctx->err = "hevcdl_deblock_frame: tu_log2 in 2..5, qp in 0..51"; return HEVCDL_E_INVAL; }
+  cudaSetDevice(ctx->cfg.device);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_m = al(nu);
+  const size_t o_y = 0, o_u = o_y + b_y, o_v = o_u + b_c, o_tu = o_v + b_c, o_qp = o_tu + b_m, total = o_qp + b_m;
+  if (total > ctx->dbfCap) {
+    cudaFree(ctx->dDbf); ctx->dDbf = nullptr; ctx->dbfCap = 0;
+    if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
+    CK(cudaMalloc(&ctx->dDbf, total));
+    CK(cudaMallocHost(&ctx->hDbf, total));
+    ctx->dbfCap = total;
+  }
+  uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
+  for (int r = 0; r < H; r++) memcpy(hp + o_y + (size_t)r * W * 2, y + (size_t)r * sy, (size_t)W * 2);      // dense planes on the device
+  for (int r = 0; r < H / 2; r++) {
+    memcpy(hp + o_u + (size_t)r * (W / 2) * 2, u + (size_t)r * sc, (size_t)(W / 2) * 2);
+    memcpy(hp + o_v + (size_t)r * (W / 2) * 2, v + (size_t)r * sc, (size_t)(W / 2) * 2);
+  }
+  memcpy(hp + o_tu, tu_log2, nu);
+  memcpy(hp + o_qp, qp, nu);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dp, hp, total, cudaMemcpyHostToDevice, st));
+  DbfParams P{(int16_t *)(dp + o_y), (int16_t *)(dp + o_u), (int16_t *)(dp + o_v), W, W / 2, W, H, dp + o_tu, (const int8_t *)(dp + o_qp),
+              beta_off, tc_off, cb_off, cr_off};
+  const int nv = (W / 8 - 1) * (H / 4), nh = (W / 4) * (H / 8 - 1);
+  if (nv > 0) k_dbf<true><<<(nv + 255) / 256, 256, 0, st>>>(P);
+  if (nh > 0) k_dbf<false><<<(nh + 255) / 256, 256, 0, st>>>(P);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches += (nv > 0) + (nh > 0);
+  CK(cudaMemcpyAsync(hp, dp, o_tu, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int r = 0; r < H; r++) memcpy(y + (size_t)r * sy, hp + o_y + (size_t)r * W * 2, (size_t)W * 2);
+  for (int r = 0; r < H / 2; r++) {
+    memcpy(u + (size_t)r * sc, hp + o_u + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
+    memcpy(v + (size_t)r * sc, hp + o_v + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
+  }
   return HEVCDL_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
@@ -101,6 +101,7 @@ def load_library():
     L.hevcdl_host_alloc.restype = vp
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
+    L.hevcdl_deblock_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip]
     L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     L.hevcdl_tu_code_rdoq.argtypes = [vp, ip, vp, vp, vp, ip, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     _lib = L
@@ -289,6 +290,19 @@ class DepthPredictor:
         def split(a):
             return None if a is None else [a[off[i]:off[i + 1]].reshape(sizes[i], sizes[i]) for i in range(n)]
         return {"coeff": split(coeff), "level": split(level), "deq": split(deq), "rec": split(rec), "abs_sum": asum, "ssd": ssd}
+
+    # -- in-loop deblocking filter -----------------------------------------------------------------
+    def deblock_frame(self, Y, U, V, tu_log2, qp, beta_off_div2=0, tc_off_div2=0, cb_qp_off=0, cr_qp_off=0):
+        """Deblocking filter of an all-intra reconstructed picture (hevcdl_deblock_frame).  Y, U, V: 8-bit planes of any integer
+        dtype; tu_log2, qp: one entry per 4x4 luma unit.  Returns the filtered planes as uint8."""
+        H, W = Y.shape
+        y, u, v = (np.ascontiguousarray(p, np.int16).copy() for p in (Y, U, V))
+        tu = np.ascontiguousarray(tu_log2, np.uint8).ravel()
+        q = np.ascontiguousarray(qp, np.int8).ravel()
+        assert tu.size == q.size == (W // 4) * (H // 4)
+        self._ck(self.lib.hevcdl_deblock_frame(self.h, _ptr(y), W, _ptr(u), _ptr(v), W // 2, W, H, _ptr(tu), _ptr(q), int(beta_off_div2),
+                                               int(tc_off_div2), int(cb_qp_off), int(cr_qp_off)), "deblock_frame")
+        return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)
 
     # -- measurement -------------------------------------------------------------------------
     def bench_resident(self, frames, iters):

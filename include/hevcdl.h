@@ -204,6 +204,18 @@ int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevc
                         const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level, int32_t *deq, int16_t *rec,
                         uint32_t *abs_sum, uint64_t *ssd);
 
+/* Deblocking filter of one ALL-INTRA reconstructed picture, in place: replaces TComLoopFilter::loopFilterPic
+ * (HM TLibCommon/TComLoopFilter.cpp:130-158 with everything below it: edge selection, boundary strength -- 2 on every edge of
+ * an all-intra picture --, the luma and chroma filters) as TEncGOP::compressGOP calls it after the last CTU of a picture
+ * (HM TLibEncoder/TEncGOP.cpp:1742).  y / u / v: HM's Pel (int16) planes of the 8-bit 4:2:0 reconstruction, width x height luma
+ * samples (multiples of 8), strides in samples.  tu_log2 / qp: one entry per 4x4 luma unit, raster order ((height/4) x (width/4)):
+ * log2 of the size of the transform unit covering it (2..5; = 6 - CU depth - transform index) and its QP.  The offsets are the
+ * slice's deblocking offsets (div 2) and the PPS chroma QP offsets.  Restrictions = the reference's operating point: every CU
+ * intra, one slice, no tiles, no PCM / lossless blocks, deblocking enabled.  Bit-exact.  Synchronous. */
+int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int stride_y, int16_t *u, int16_t *v, int stride_c, int width, int height,
+                         const uint8_t *tu_log2, const int8_t *qp, int beta_offset_div2, int tc_offset_div2, int cb_qp_offset,
+                         int cr_qp_offset);
+
 /* Page-locked host memory for frame planes handed over with hevcdl_cfg.pinned_input = 1 (any page-locked memory will do;
  * this is the allocator for callers without a CUDA runtime of their own).  write_combined != 0: cudaHostAllocWriteCombined --
  * not snooped during the transfer, which some hosts move faster over PCIe; the CPU should only WRITE such memory (reads

@@ -1,0 +1,87 @@
+"""Deblocking filter on the device (hevcdl_deblock_frame, csrc/dbf.cuh) through the C-ABI: identical to the reference's own
+loopFilterPic on the dumped pictures (tests/golden/dbf_pictures.npz), to the oracle on synthetic pictures of other sizes, QPs
+and offsets, and -- inside the real encoder (HEVCDL_DBF=1) -- byte-identical bitstreams."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hm_util
+from test_oracle_dbf import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dp(built, host):
+    d = host.DepthPredictor(64, 64, precision=host.PREC_FP32, rmd=False, outputs=0)
+    yield d
+    d.close()
+
+
+def test_deblocking_vs_the_references_own_filter(dp):
+    n = 0
+    for k, h, pre, post, tu, qp in cases():
+        out = dp.deblock_frame(*pre, tu, qp, int(h[4]), int(h[5]), int(h[6]), int(h[7]))
+        for a, b, name in zip(out, post, "YUV"):
+            assert (a == b).all(), (k, name, int((a != b).sum()))
+        n += 1
+    assert n == 3
+
+
+def test_deblocking_vs_oracle_synthetic(dp, oracle, pkg):
+    """Random TU-size maps (consistent quadtrees of 32/16/8/4 blocks), per-unit QPs over the whole range, non-zero deblocking
+    and chroma QP offsets, pictures from 8x8 to 1920x1080 with blocky content so that every filter branch fires."""
+    rng = np.random.default_rng(4)
+    for (W, H) in ((8, 8), (16, 8), (8, 24), (72, 200), (416, 240), (1920, 1080)):
+        w4, h4 = W // 4, H // 4
+        tu = np.full((h4, w4), 2, np.uint8)
+        for by in range(0, H, 32):
+            for bx in range(0, W, 32):
+                def fill(x0, y0, lg):
+                    s = 1 << lg
+                    if x0 + s <= W and y0 + s <= H and (lg == 2 or rng.random() < 0.45):
+                        tu[y0 // 4:(y0 + s) // 4, x0 // 4:(x0 + s) // 4] = lg
+                    elif lg > 2:
+                        for k in range(4):
+                            if x0 + (k & 1) * (s // 2) < W and y0 + (k >> 1) * (s // 2) < H:
+                                fill(x0 + (k & 1) * (s // 2), y0 + (k >> 1) * (s // 2), lg - 1)
+                fill(bx, by, 5)
+        qp = rng.integers(0, 52, (h4, w4)).astype(np.int8) if W < 400 else np.full((h4, w4), int(rng.integers(20, 45)), np.int8)
+        base = np.kron(rng.integers(30, 226, ((H + 7) // 8, (W + 7) // 8)), np.ones((8, 8)))[:H, :W]       # blocky: edges on the 8x8 grid
+        Y = np.clip(base + rng.integers(-3, 4, (H, W)), 0, 255).astype(np.uint8)
+        U = np.clip(np.kron(rng.integers(60, 196, ((H + 15) // 16, (W + 15) // 16)), np.ones((8, 8)))[:H // 2, :W // 2] + rng.integers(-2, 3, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+        V = np.clip(U.astype(np.int32)[::-1, ::-1] + 7, 0, 255).astype(np.uint8)
+        offs = (int(rng.integers(-2, 3)), int(rng.integers(-2, 3)), int(rng.integers(-4, 5)), int(rng.integers(-4, 5)))
+        want = oracle.deblock_frame(Y, U, V, tu, qp, *offs)
+        got = dp.deblock_frame(Y, U, V, tu, qp, *offs)
+        for a, b, name in zip(got, want, "YUV"):
+            assert (a == b).all(), (W, H, name, int((a != b).sum()))
+        if W >= 72:
+            assert (want[0] != Y).sum() > 50
+
+
+@pytest.mark.skipif(not hm_util.have("ref", "dec", "hevcdl"), reason="reference / drop-in encoder binaries not built")
+@pytest.mark.parametrize("w,h,qp", [(192, 128, 32), (416, 240, 27)])
+def test_dropin_deblocking_on_the_device_keeps_the_bitstream(tmp_path, built, host, pkg, w, h, qp):
+    """HEVCDL_DBF=1: TComLoopFilter::loopFilterPic of every picture runs on the B200.  The deblocked reconstruction feeds SAO and
+    the picture-hash SEI, so any differing sample would change the bitstream: it must stay byte-identical to the reference's."""
+    frames = [pkg.synth.synth_frame(w, h, 95 + i) for i in range(2)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    dpx = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=False)
+    for f, (Y, U, V) in enumerate(frames):
+        hm_util.write_pred(str(a / "pred"), f, dpx.predict_frame(Y, U, V, frame=f))
+    dpx.close()
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp)
+    rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp, env={"HEVCDL_DBF": "1", "HEVCDL_VERBOSE": "1"})
+    assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-400:])
+    m = re.search(r"pictures deblocked on the device (\d+) / by the reference's filter (\d+)", rb["stderr"])
+    assert m and int(m.group(1)) == 2 and int(m.group(2)) == 0, rb["stderr"][-300:]
+    assert ra["sha1"] == rb["sha1"] and (ra["kbps"], ra["psnr_y"]) == (rb["kbps"], rb["psnr_y"])
+    if w % 64 == 0 and h % 64 == 0:
+        ok, out = hm_util.decode_ok(str(b))
+        assert ok, out[-400:]
