@@ -23,7 +23,7 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def build():
     """Compile the C restatement (gcc, seconds)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c", "rdoq_oracle.c", "dbf_oracle.c")]
+    srcs = [os.path.join(_HERE, s) for s in ("cnn_oracle.c", "rmd_oracle.c", "tq_oracle.c", "rdoq_oracle.c", "dbf_oracle.c", "sao_oracle.c")]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so] + srcs + ["-lm"])
     return so
@@ -266,3 +266,17 @@ def deblock_frame(Y, U, V, tu_log2, qp, beta_off_div2=0, tc_off_div2=0, cb_qp_of
     lib().oracle_deblock_frame(y, W, u, v, W // 2, W, H, np.ascontiguousarray(tu_log2, np.uint8).ravel(), np.ascontiguousarray(qp, np.int8).ravel(),
                                int(beta_off_div2), int(tc_off_div2), int(cb_qp_off), int(cr_qp_off))
     return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)
+
+
+def sao_stats(org, src):
+    """SAO statistics of a picture (oracle/sao_oracle.c).  org, src: (Y, U, V) 8-bit planes (original, deblocked).  Returns
+    int64 [nctu, 3 components, 5 types (EO 0 / 90 / 135 / 45, BO), 2 (diff, count), 32 classes]."""
+    H, W = org[0].shape
+    n = ((W + 63) // 64) * ((H + 63) // 64)
+    o = [np.ascontiguousarray(p, np.int16) for p in org]
+    s = [np.ascontiguousarray(p, np.int16) for p in src]
+    P = C.POINTER(C.c_int16) * 3
+    out = np.zeros((n, 3, 5, 2, 32), np.int64)
+    lib().oracle_sao_stats(P(*[p.ctypes.data_as(C.POINTER(C.c_int16)) for p in o]), P(*[p.ctypes.data_as(C.POINTER(C.c_int16)) for p in s]),
+                           W, H, out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out

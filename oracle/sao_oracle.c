@@ -1,0 +1,57 @@
+/* oracle/sao_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the reference's SAO statistics pass: TEncSampleAdaptiveOffset::getStatistics
+ * (HM_dl/source/Lib/TLibEncoder/TEncSampleAdaptiveOffset.cpp:295-341) and getBlkStats (:943-1345) for deblocked samples
+ * (isCalculatePreDeblockSamples = false; SAOLcuBoundary 0, encoder_intra_main.cfg:55), one slice, no tiles, 8-bit 4:2:0,
+ * 64x64 CTUs.  For every CTU, colour component and SAO type it accumulates, per class, the number of samples and the sum of
+ * (original - deblocked): the four edge-offset types classify a sample by the signs of its differences to the two
+ * neighbours along the direction (class index 2 + sgn + sgn), band offset by the sample's upper five bits.  The reference
+ * walks lines with running sign buffers; the classes do not depend on that, so they are written per sample here.  What a CTU
+ * counts excludes the columns / rows its right / lower neighbours have not deblocked yet (skipLinesR = 5 luma / 3 chroma,
+ * skipLinesB = 4 / 2, :126-133) and, for the edge types, samples whose neighbour lies outside the picture.
+ * Pinned by tests/golden/sao_stats.npz: inputs and output of the reference's own getStatistics (TAppEncoder_saotrace).
+ *
+ * out: [nctu][3][5] x { int64 diff[32], int64 count[32] } exactly as the reference's SAOStatData arrays.
+ */
+#include <stdint.h>
+#include <string.h>
+
+static int sgn(int v) { return (v > 0) - (v < 0); }
+
+void oracle_sao_stats(const int16_t *org[3], const int16_t *src[3], int W, int H, int64_t *out) {
+  const int cw = (W + 63) / 64, ch = (H + 63) / 64;
+  memset(out, 0, sizeof(int64_t) * (size_t)cw * ch * 3 * 5 * 64);
+  for (int a = 0; a < cw * ch; a++) {
+    const int xp = (a % cw) * 64, yp = (a / cw) * 64;
+    const int hl = yp + 64 > H ? H - yp : 64, wl = xp + 64 > W ? W - xp : 64;
+    const int left = xp > 0, above = yp > 0, right = xp + 64 < W, below = yp + 64 < H, above_left = left && above;
+    for (int c = 0; c < 3; c++) {
+      const int sh = c ? 1 : 0, stride = W >> sh, width = wl >> sh, height = hl >> sh;
+      const int16_t *s = src[c] + (size_t)(yp >> sh) * stride + (xp >> sh), *o = org[c] + (size_t)(yp >> sh) * stride + (xp >> sh);
+      const int skip_r = c ? 3 : 5, skip_b = c ? 2 : 4;
+      for (int t = 0; t < 5; t++) {
+        int64_t *diff = out + (((size_t)a * 3 + c) * 5 + t) * 64, *count = diff + 32;
+        const int x0 = (t == 1 || t == 4) ? 0 : (left ? 0 : 1);
+        const int x1 = right ? width - skip_r : ((t == 1 || t == 4) ? width : width - 1);
+        const int y0 = (t == 1) ? (above ? 0 : 1) : 0;
+        const int y1 = below ? height - skip_b : ((t == 0 || t == 4) ? height : height - 1);
+        for (int y = y0; y < y1; y++) {
+          int xa = x0, xb = x1;
+          if (y == 0 && t == 2) { xa = above_left ? 0 : 1; xb = above ? x1 : 1; }         /* first line of the 135-degree type */
+          if (y == 0 && t == 3) { xa = above ? x0 : x1; }                                 /* ... of the 45-degree type */
+          for (int x = xa; x < xb; x++) {
+            const int v = s[y * stride + x];
+            int cls;
+            if (t == 0) cls = 2 + sgn(v - s[y * stride + x - 1]) + sgn(v - s[y * stride + x + 1]);
+            else if (t == 1) cls = 2 + sgn(v - s[(y - 1) * stride + x]) + sgn(v - s[(y + 1) * stride + x]);
+            else if (t == 2) cls = 2 + sgn(v - s[(y - 1) * stride + x - 1]) + sgn(v - s[(y + 1) * stride + x + 1]);
+            else if (t == 3) cls = 2 + sgn(v - s[(y - 1) * stride + x + 1]) + sgn(v - s[(y + 1) * stride + x - 1]);
+            else cls = v >> 3;
+            diff[cls] += o[y * stride + x] - v;
+            count[cls]++;
+          }
+        }
+      }
+    }
+  }
+}

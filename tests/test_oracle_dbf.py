@@ -26,3 +26,24 @@ def test_deblocking_equals_the_references_own_filter(oracle):
         assert (pre[0] != post[0]).sum() > 1000 and (pre[1] != post[1]).sum() > 100      # the filter did something
         n += 1
     assert n == 3
+
+
+def sao_cases():
+    g = np.load(os.path.join(GOLDEN, "sao_stats.npz"))
+    for k in range(int(g["ncases"])):
+        W, H = (int(v) for v in g["dims_%d" % k])
+        shp = ((H, W), (H // 2, W // 2), (H // 2, W // 2))
+        org = [g["org%s_%d" % (n, k)].reshape(s) for n, s in zip("YUV", shp)]
+        src = [g["src%s_%d" % (n, k)].reshape(s) for n, s in zip("YUV", shp)]
+        yield k, org, src, g["stats_%d" % k]
+
+
+def test_sao_statistics_equal_the_references_own(oracle):
+    """oracle/sao_oracle.c against inputs / output of the reference's own TEncSampleAdaptiveOffset::getStatistics."""
+    n = 0
+    for k, org, src, want in sao_cases():
+        got = oracle.sao_stats(org, src)
+        assert got.shape == want.shape and (got == want).all(), (k, int((got != want).sum()))
+        assert want[:, :, :, 1].sum() > 10000
+        n += 1
+    assert n == 2

@@ -4,6 +4,7 @@ container (needs /root/reference and `make -C oracle ref`); the fixtures travel,
 
   tests/golden/tq_transform_ref.npz   random and extreme blocks through the reference's OWN xTrMxN / xITrMxN
                                       (oracle/_ref/libtqref.so = tq_ref_harness.cpp linked with libhmref.a), every size + DST
+  tests/golden/sao_stats.npz          original + deblocked pictures and the statistics the reference's own SAO getStatistics made of them
   tests/golden/dbf_pictures.npz       reconstructed pictures before / after the reference's own deblocking filter + its TU / QP maps
   tests/golden/tq_rdoq_192x128_qp32.npz    calls of the reference's xRateDistOptQuant (inputs incl. the CABAC bit-estimate
                                       tables, outputs) dumped by oracle/_ref/TAppEncoder_rdoqtrace at the default options
@@ -229,8 +230,42 @@ def dbf_vectors():
     print("dbf_pictures.npz:", os.path.getsize(os.path.join(GOLD, "dbf_pictures.npz")), "bytes")
 
 
+def sao_vectors():
+    """tests/golden/sao_stats.npz: inputs (original and deblocked pictures) and output (per CTU / component / SAO type class
+    statistics) of the reference's own TEncSampleAdaptiveOffset::getStatistics (oracle/_ref/TAppEncoder_saotrace,
+    oracle/sao_dump.h): the 192x128 fixture frame and the 416x240 frame (interior CTUs and partial CTUs on both edges), QP 32."""
+    g = np.load(os.path.join(GOLD, "rmd_trace_192x128_qp32.npz"))
+    c = np.load(os.path.join(GOLD, "cnn_labels_416x240.npz"))
+    out = {}
+    for k, (Y, U, V, labels) in enumerate(((g["Y"], g["U"], g["V"], g["labels"]), (c["Y"], c["U"], c["V"], c["labels"]))):
+        H, W = Y.shape
+        with tempfile.TemporaryDirectory() as td:
+            hm_util.write_yuv(os.path.join(td, "in.yuv"), [(Y, U, V)])
+            hm_util.write_pred(os.path.join(td, "pred"), 0, labels)
+            cmd = [os.path.join(REFDIR, "TAppEncoder_saotrace"), "-c", hm_util.CFG, "-i", "in.yuv", "-wdt", str(W), "-hgt", str(H), "-fr", "30",
+                   "-f", "1", "-q", "32", "-b", "t.bin", "--InputBitDepth=8", "--InputChromaFormat=420", "--Level=6.2"]
+            subprocess.check_call(cmd, cwd=td, env=dict(os.environ, HEVCDL_SAO_DUMP=os.path.join(td, "sao.bin")), stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            raw = open(os.path.join(td, "sao.bin"), "rb").read()
+        hdr = np.frombuffer(raw, np.int32, 8, 0)
+        assert hdr[0] == 0x53414F30 and hdr[1] == W and hdr[2] == H and hdr[4] == 0
+        n, off = int(hdr[3]), 32
+        for kind in ("org", "src"):
+            for name, cnt in (("Y", W * H), ("U", W * H // 4), ("V", W * H // 4)):
+                out["%s%s_%d" % (kind, name, k)] = np.frombuffer(raw, np.int16, cnt, off).astype(np.uint8); off += 2 * cnt
+        st = np.frombuffer(raw, np.int64, n * 3 * 5 * 64, off); off += 8 * n * 3 * 5 * 64
+        assert off == len(raw) and np.abs(st).max() < 2 ** 31
+        out["stats_%d" % k] = st.astype(np.int32).reshape(n, 3, 5, 2, 32)
+        out["dims_%d" % k] = np.array([W, H])
+        print("case", k, W, H, n, "CTUs, samples counted:", int(out["stats_%d" % k][:, :, :, 1].sum()))
+    out["ncases"] = np.array(2)
+    np.savez_compressed(os.path.join(GOLD, "sao_stats.npz"), **out)
+    print("sao_stats.npz:", os.path.getsize(os.path.join(GOLD, "sao_stats.npz")), "bytes")
+
+
 if __name__ == "__main__":
     transform_vectors()
     trace_vectors()
     rdoq_vectors()
     dbf_vectors()
+    sao_vectors()
