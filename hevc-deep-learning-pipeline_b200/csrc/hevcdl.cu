@@ -18,6 +18,7 @@
 #include "rmd.cuh"
 #include "tq.cuh"
 #include "dbf.cuh"
+#include "sao.cuh"
 #include "../../include/hevcdl_internal.h"
 
 using namespace hevcdl;
@@ -857,6 +858,44 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_
     memcpy(u + (size_t)r * sc, hp + o_u + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
     memcpy(v + (size_t)r * sc, hp + o_v + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
   }
+  return HEVCDL_OK;
+}
+
+int hevcdl_sao_stats(hevcdl_ctx *ctx, const int16_t *oy, const int16_t *ou, const int16_t *ov, int osy, int osc, const int16_t *ry, const int16_t *ru,
+                     const int16_t *rv, int rsy, int rsc, int W, int H, int64_t *stats) {
+  if (!ctx || !oy || !ou || !ov || !ry || !ru || !rv || !stats || W < 8 || H < 8 || (W & 7) || (H & 7) || W > 8192 || H > 8192 || osy < W || rsy < W ||
+      osc < W / 2 || rsc < W / 2)
+    return HEVCDL_E_INVAL;
+  cudaSetDevice(ctx->cfg.device);
+  const int cw = (W + 63) / 64, chh = (H + 63) / 64, nctu = cw * chh;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_out = al((size_t)nctu * 3 * 5 * 64 * 8);
+  const size_t o_oy = 0, o_ou = o_oy + b_y, o_ov = o_ou + b_c, o_ry = o_ov + b_c, o_ru = o_ry + b_y, o_rv = o_ru + b_c, o_out = o_rv + b_c, total = o_out + b_out;
+  if (total > ctx->dbfCap) {                      // shares the deblocking entry point's grow-only scratch
+    cudaFree(ctx->dDbf); ctx->dDbf = nullptr; ctx->dbfCap = 0;
+    if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
+    CK(cudaMalloc(&ctx->dDbf, total));
+    CK(cudaMallocHost(&ctx->hDbf, total));
+    ctx->dbfCap = total;
+  }
+  uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
+  auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {
+    for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
+  };
+  pack(o_oy, oy, osy, W, H); pack(o_ou, ou, osc, W / 2, H / 2); pack(o_ov, ov, osc, W / 2, H / 2);
+  pack(o_ry, ry, rsy, W, H); pack(o_ru, ru, rsc, W / 2, H / 2); pack(o_rv, rv, rsc, W / 2, H / 2);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dp, hp, o_out, cudaMemcpyHostToDevice, st));
+  SaoParams P{};
+  P.org[0] = (const int16_t *)(dp + o_oy); P.org[1] = (const int16_t *)(dp + o_ou); P.org[2] = (const int16_t *)(dp + o_ov);
+  P.src[0] = (const int16_t *)(dp + o_ry); P.src[1] = (const int16_t *)(dp + o_ru); P.src[2] = (const int16_t *)(dp + o_rv);
+  P.W = W; P.H = H; P.ctu_w = cw; P.out = (long long *)(dp + o_out);
+  k_sao_stats<<<nctu * 3, 256, 0, st>>>(P);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(hp + o_out, dp + o_out, (size_t)nctu * 3 * 5 * 64 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(stats, hp + o_out, (size_t)nctu * 3 * 5 * 64 * 8);
   return HEVCDL_OK;
 }
 

@@ -1,0 +1,74 @@
+// sao.cuh -- SAO statistics of a deblocked picture on the device: the data pass of the reference's SAO
+// parameter estimation, TEncSampleAdaptiveOffset::getStatistics / getBlkStats (HM TLibEncoder/TEncSampleAdaptiveOffset.cpp:
+// 295-341, 943-1345) for deblocked samples (isCalculatePreDeblockSamples = false), one slice, no tiles, 8-bit 4:2:0, 64x64
+// CTUs.  Per CTU, colour component and SAO type (edge offset 0 / 90 / 135 / 45 degrees, band offset): per class the number of
+// samples and the sum of (original - deblocked).  The parameter decision (an RD search with CABAC bit estimates over these
+// 7.7 KB per CTU) stays the reference's.
+//
+// Byte work bound by HBM: one block per (CTU, component) reads the CTU's samples of both pictures once (plus a one-sample
+// ring of the deblocked picture) into shared memory, every thread classifies its samples for all five types and adds into
+// shared-memory histograms (int32: at most 4096 samples x 255 per class), which are written out as the reference's int64
+// arrays.  What a CTU counts excludes the columns / rows its right / lower neighbours have not deblocked yet (5 / 4 luma,
+// 3 / 2 chroma) and, for the edge types, samples whose neighbour lies outside the picture.
+#pragma once
+#include "common.cuh"
+
+namespace hevcdl {
+
+struct SaoParams {
+  const int16_t *org[3], *src[3];
+  int W, H, ctu_w;
+  long long *out;            // [nctu][3][5][2][32]
+};
+
+__global__ void __launch_bounds__(256)
+k_sao_stats(const SaoParams P) {
+  __shared__ int16_t s_src[66][66];                          // the CTU's deblocked samples with a one-sample ring
+  __shared__ int s_hist[8][5][2][32];                        // one histogram per warp: the edge types have only five classes
+  const int a = blockIdx.x / 3, c = blockIdx.x - 3 * a;
+  const int xp = (a % P.ctu_w) * 64, yp = (a / P.ctu_w) * 64;
+  const int hl = yp + 64 > P.H ? P.H - yp : 64, wl = xp + 64 > P.W ? P.W - xp : 64;
+  const bool left = xp > 0, above = yp > 0, right = xp + 64 < P.W, below = yp + 64 < P.H;
+  const int sh = c ? 1 : 0, stride = P.W >> sh, pw = P.W >> sh, ph = P.H >> sh, width = wl >> sh, height = hl >> sh;
+  const int x0p = xp >> sh, y0p = yp >> sh;
+  const int16_t *__restrict__ src = P.src[c], *__restrict__ org = P.org[c];
+  for (int i = threadIdx.x; i < 8 * 5 * 2 * 32; i += blockDim.x) (&s_hist[0][0][0][0])[i] = 0;
+  int (*hist)[2][32] = s_hist[threadIdx.x >> 5];
+  for (int i = threadIdx.x; i < (height + 2) * (width + 2); i += blockDim.x) {
+    const int ly = i / (width + 2), lx = i - ly * (width + 2);
+    const int gy = y0p + ly - 1, gx = x0p + lx - 1;
+    s_src[ly][lx] = (gy >= 0 && gy < ph && gx >= 0 && gx < pw) ? src[(size_t)gy * stride + gx] : (int16_t)0;   // ring samples outside the picture are never used
+  }
+  __syncthreads();
+  const int skip_r = c ? 3 : 5, skip_b = c ? 2 : 4;
+  // per-type ranges (getBlkStats): x in [x0, x1), y in [y0, y1); the diagonal types restrict their first line further
+  const int ex0 = left ? 0 : 1, ex1 = right ? width - skip_r : width - 1;          // types that look left / right
+  const int fx1 = right ? width - skip_r : width;                                   // types that do not (EO 90, BO)
+  const int ey1 = below ? height - skip_b : height - 1, fy1 = below ? height - skip_b : height;
+  for (int i = threadIdx.x; i < height * width; i += blockDim.x) {
+    const int y = i / width, x = i - y * width;
+    const int v = s_src[y + 1][x + 1];
+    const int d = (int)org[(size_t)(y0p + y) * stride + x0p + x] - v;
+    auto sgn = [](int t) { return (t > 0) - (t < 0); };
+    auto add = [&](int t, int cls) { atomicAdd(&hist[t][0][cls], d); atomicAdd(&hist[t][1][cls], 1); };
+    if (x >= ex0 && x < ex1 && y < fy1) add(0, 2 + sgn(v - s_src[y + 1][x]) + sgn(v - s_src[y + 1][x + 2]));
+    if (x < fx1 && y >= (above ? 0 : 1) && y < ey1) add(1, 2 + sgn(v - s_src[y][x + 1]) + sgn(v - s_src[y + 2][x + 1]));
+    if (y < ey1) {
+      const bool in135 = y == 0 ? (x >= ((left && above) ? 0 : 1) && x < (above ? ex1 : 1)) : (x >= ex0 && x < ex1);
+      if (in135) add(2, 2 + sgn(v - s_src[y][x]) + sgn(v - s_src[y + 2][x + 2]));
+      const bool in45 = y == 0 ? (above && x >= ex0 && x < ex1) : (x >= ex0 && x < ex1);
+      if (in45) add(3, 2 + sgn(v - s_src[y][x + 2]) + sgn(v - s_src[y + 2][x]));
+    }
+    if (x < fx1 && y < fy1) add(4, v >> 3);
+  }
+  __syncthreads();
+  long long *o = P.out + ((size_t)a * 3 + c) * 5 * 64;
+  for (int i = threadIdx.x; i < 5 * 2 * 32; i += blockDim.x) {
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += (&s_hist[w][0][0][0])[i];
+    o[i] = t;
+  }
+}
+
+}  // namespace hevcdl

@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
@@ -101,6 +101,7 @@ def load_library():
     L.hevcdl_host_alloc.restype = vp
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
+    L.hevcdl_sao_stats.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
     L.hevcdl_deblock_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip]
     L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     L.hevcdl_tu_code_rdoq.argtypes = [vp, ip, vp, vp, vp, ip, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
@@ -303,6 +304,18 @@ class DepthPredictor:
         self._ck(self.lib.hevcdl_deblock_frame(self.h, _ptr(y), W, _ptr(u), _ptr(v), W // 2, W, H, _ptr(tu), _ptr(q), int(beta_off_div2),
                                                int(tc_off_div2), int(cb_qp_off), int(cr_qp_off)), "deblock_frame")
         return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)
+
+    def sao_stats(self, org, rec):
+        """SAO statistics of a deblocked picture (hevcdl_sao_stats).  org, rec: (Y, U, V) 8-bit planes.  Returns int64
+        [nctu, 3 components, 5 types (EO 0 / 90 / 135 / 45, BO), 2 (diff, count), 32 classes]."""
+        H, W = org[0].shape
+        n = ((W + 63) // 64) * ((H + 63) // 64)
+        o = [np.ascontiguousarray(p, np.int16) for p in org]
+        r = [np.ascontiguousarray(p, np.int16) for p in rec]
+        out = np.zeros((n, 3, 5, 2, 32), np.int64)
+        self._ck(self.lib.hevcdl_sao_stats(self.h, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), W, W // 2, _ptr(r[0]), _ptr(r[1]), _ptr(r[2]), W, W // 2,
+                                           W, H, _ptr(out)), "sao_stats")
+        return out
 
     # -- measurement -------------------------------------------------------------------------
     def bench_resident(self, frames, iters):

@@ -216,6 +216,17 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int stride_y, int16_t *u, 
                          const uint8_t *tu_log2, const int8_t *qp, int beta_offset_div2, int tc_offset_div2, int cb_qp_offset,
                          int cr_qp_offset);
 
+/* SAO statistics of one deblocked picture: replaces the data pass of the reference's SAO parameter estimation,
+ * TEncSampleAdaptiveOffset::getStatistics (HM TLibEncoder/TEncSampleAdaptiveOffset.cpp:295-341 -> getBlkStats :943-1345) as
+ * SAOProcess calls it (:258) for deblocked samples.  org_* / rec_*: HM's Pel (int16) planes of the original and the deblocked
+ * 8-bit 4:2:0 pictures, width x height luma samples, strides in samples.  stats receives, for every 64x64 CTU in raster order,
+ * component (Y, Cb, Cr) and SAO type (edge offset 0 / 90 / 135 / 45 degrees, band offset): int64 diff[32] then int64 count[32]
+ * -- the reference's SAOStatData arrays (TEncSampleAdaptiveOffset.h:66-70) laid end to end, nctu * 3 * 5 * 64 values.
+ * Restrictions = the reference's operating point: one slice, no tiles, SAOLcuBoundary 0.  Bit-exact.  Synchronous. */
+int hevcdl_sao_stats(hevcdl_ctx *ctx, const int16_t *org_y, const int16_t *org_u, const int16_t *org_v, int org_stride_y,
+                     int org_stride_c, const int16_t *rec_y, const int16_t *rec_u, const int16_t *rec_v, int rec_stride_y,
+                     int rec_stride_c, int width, int height, int64_t *stats);
+
 /* Page-locked host memory for frame planes handed over with hevcdl_cfg.pinned_input = 1 (any page-locked memory will do;
  * this is the allocator for callers without a CUDA runtime of their own).  write_combined != 0: cudaHostAllocWriteCombined --
  * not snooped during the transfer, which some hosts move faster over PCIe; the CPU should only WRITE such memory (reads

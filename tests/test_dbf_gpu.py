@@ -1,6 +1,6 @@
 """Deblocking filter on the device (hevcdl_deblock_frame, csrc/dbf.cuh) through the C-ABI: identical to the reference's own
 loopFilterPic on the dumped pictures (tests/golden/dbf_pictures.npz), to the oracle on synthetic pictures of other sizes, QPs
-and offsets, and -- inside the real encoder (HEVCDL_DBF=1) -- byte-identical bitstreams."""
+and offsets, and -- inside the real encoder (HEVCDL_DBF=1) -- byte-identical bitstreams.  The same three levels for the SAO statistics pass (hevcdl_sao_stats, csrc/sao.cuh, HEVCDL_SAO=1)."""
 import os
 import re
 
@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import hm_util
-from test_oracle_dbf import cases
+from test_oracle_dbf import cases, sao_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -85,3 +85,56 @@ def test_dropin_deblocking_on_the_device_keeps_the_bitstream(tmp_path, built, ho
     if w % 64 == 0 and h % 64 == 0:
         ok, out = hm_util.decode_ok(str(b))
         assert ok, out[-400:]
+
+
+def test_sao_statistics_vs_the_references_own(dp):
+    n = 0
+    for k, org, src, want in sao_cases():
+        got = dp.sao_stats(org, src)
+        assert got.shape == want.shape and (got == want).all(), (k, int((got != want).sum()))
+        n += 1
+    assert n == 2
+
+
+def test_sao_statistics_vs_oracle_synthetic(dp, oracle):
+    """Picture sizes with partial CTUs on the right and bottom, one-CTU pictures, and 1080p; the 'deblocked' picture is the
+    original plus noise and a smoothing pass, so that every edge class and most bands are populated."""
+    rng = np.random.default_rng(9)
+    for (W, H) in ((64, 64), (8, 8), (72, 40), (200, 136), (416, 240), (1920, 1080)):
+        org, src = [], []
+        for c in range(3):
+            w, h = (W, H) if c == 0 else (W // 2, H // 2)
+            o = np.clip(np.kron(rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8)), np.ones((8, 8)))[:h, :w] + rng.integers(-20, 21, (h, w)), 0, 255)
+            s = o + rng.integers(-6, 7, (h, w))
+            s[:, 1:-1] = (s[:, :-2] + 2 * s[:, 1:-1] + s[:, 2:]) // 4 if w > 2 else s[:, 1:-1]
+            org.append(o.astype(np.uint8))
+            src.append(np.clip(s, 0, 255).astype(np.uint8))
+        want = oracle.sao_stats(org, src)
+        got = dp.sao_stats(org, src)
+        assert got.shape == want.shape and (got == want).all(), (W, H, int((got != want).sum()))
+        if W >= 200:
+            assert (want[:, :, :, 1] > 0).sum() > 100
+
+
+@pytest.mark.skipif(not hm_util.have("ref", "dec", "hevcdl"), reason="reference / drop-in encoder binaries not built")
+@pytest.mark.parametrize("w,h,qp", [(192, 128, 37), (416, 240, 32)])
+def test_dropin_sao_statistics_on_the_device_keep_the_bitstream(tmp_path, built, host, pkg, w, h, qp):
+    """HEVCDL_SAO=1: TEncSampleAdaptiveOffset::getStatistics of every picture runs on the B200; the offsets SAO signals are decided
+    from these sums, so a differing count or difference would change the bitstream: it must stay byte-identical."""
+    frames = [pkg.synth.synth_frame(w, h, 120 + i) for i in range(2)]
+    a, b = tmp_path / "ref", tmp_path / "dl"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        hm_util.write_yuv(str(d / "in.yuv"), frames)
+    dpx = host.DepthPredictor(w, h, precision=host.PREC_FP32, rmd=False)
+    for f, (Y, U, V) in enumerate(frames):
+        hm_util.write_pred(str(a / "pred"), f, dpx.predict_frame(Y, U, V, frame=f))
+    dpx.close()
+    ra = hm_util.encode("ref", str(a), "in.yuv", w, h, 2, qp)
+    rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, 2, qp,
+                        env={"HEVCDL_PRECISION": "fp32", "HEVCDL_SAO": "1", "HEVCDL_DBF": "1", "HEVCDL_VERBOSE": "1"})
+    assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-600:])
+    assert re.search(r"SAO statistics passes on the device 2 / by the reference's code 0", rb["stderr"]), rb["stderr"][-600:]
+    assert ra["sha1"] == rb["sha1"]
+    ok, out = hm_util.decode_ok(str(b))
+    assert ok, out[-400:]
