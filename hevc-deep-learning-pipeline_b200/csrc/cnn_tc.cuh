@@ -320,9 +320,11 @@ k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo
       float s[8], q[8], pool64[4][8];
 #pragma unroll
       for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
-#pragma unroll 1
+      // fully unrolled: the tile index t is a compile-time constant below, so pool64[] stays in registers (no select chains /
+      // local memory for a dynamic index), the conv64 / conv1 branches and the reduction points are resolved statically
+#pragma unroll
       for (int pi = 0; pi < 4; pi++) {
-        const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
+        const uint32_t n = npair + pi, p = pi & 1, use = n >> 1;   // npair is a multiple of 4
         MBAR_WAIT(&bar_full[p], use & 1, 2);
         fence_after_sync();
 #pragma unroll

@@ -90,6 +90,8 @@ struct hevcdl_ctx {
   int rmdBlocks = 0;                   // persistent grid of k_rmd_items: resident blocks per SM x SMs
   std::string err;
   hevcdl_stats_t stats{};
+  // device time of the most recent hevcdl_tu_code* / hevcdl_deblock_frame / hevcdl_sao_stats kernels (hevcdl_last_aux_ms)
+  cudaEvent_t evAux0 = nullptr, evAux1 = nullptr;
   // scratch for hevcdl_deblock_frame
   void *dDbf = nullptr;
   void *hDbf = nullptr;
@@ -120,6 +122,15 @@ thread_local std::string g_create_err;
       return HEVCDL_E_CUDA;                                                                 \
     }                                                                                       \
   } while (0)
+
+cudaError_t aux_begin(hevcdl_ctx *ctx) {          // start of the timed kernel region of an auxiliary entry point
+  if (!ctx->evAux0) {
+    cudaError_t e = cudaEventCreate(&ctx->evAux0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->evAux1);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaEventRecord(ctx->evAux0, ctx->stream);
+}
 
 Slot *find_slot(hevcdl_ctx *ctx, int frame) {
   for (auto &s : ctx->slots)
@@ -637,6 +648,8 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
   }
   cudaFree(ctx->dWeights); cudaFree(ctx->dPacked); cudaFree(ctx->dExact); cudaFree(ctx->dTq); cudaFree(ctx->dRdoq); cudaFree(ctx->dDbf);
   if (ctx->hDbf) cudaFreeHost(ctx->hDbf);
+  if (ctx->evAux0) cudaEventDestroy(ctx->evAux0);
+  if (ctx->evAux1) cudaEventDestroy(ctx->evAux1);
   if (ctx->hExact) cudaFreeHost(ctx->hExact);
   if (ctx->hTq) cudaFreeHost(ctx->hTq);
   tc_release(&ctx->tc);
@@ -847,9 +860,11 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_
   DbfParams P{(int16_t *)(dp + o_y), (int16_t *)(dp + o_u), (int16_t *)(dp + o_v), W, W / 2, W, H, dp + o_tu, (const int8_t *)(dp + o_qp),
               beta_off, tc_off, cb_off, cr_off};
   const int nv = (W / 8 - 1) * (H / 4), nh = (W / 4) * (H / 8 - 1);
+  CK(aux_begin(ctx));
   if (nv > 0) k_dbf<true><<<(nv + 255) / 256, 256, 0, st>>>(P);
   if (nh > 0) k_dbf<false><<<(nh + 255) / 256, 256, 0, st>>>(P);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->evAux1, st));
   ctx->stats.kernel_launches += (nv > 0) + (nh > 0);
   CK(cudaMemcpyAsync(hp, dp, o_tu, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -890,8 +905,10 @@ int hevcdl_sao_stats(hevcdl_ctx *ctx, const int16_t *oy, const int16_t *ou, cons
   P.org[0] = (const int16_t *)(dp + o_oy); P.org[1] = (const int16_t *)(dp + o_ou); P.org[2] = (const int16_t *)(dp + o_ov);
   P.src[0] = (const int16_t *)(dp + o_ry); P.src[1] = (const int16_t *)(dp + o_ru); P.src[2] = (const int16_t *)(dp + o_rv);
   P.W = W; P.H = H; P.ctu_w = cw; P.out = (long long *)(dp + o_out);
+  CK(aux_begin(ctx));
   k_sao_stats<<<nctu * 3, 256, 0, st>>>(P);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->evAux1, st));
   ctx->stats.kernel_launches++;
   CK(cudaMemcpyAsync(hp + o_out, dp + o_out, (size_t)nctu * 3 * 5 * 64 * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -953,6 +970,7 @@ int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevc
   CK(cudaMemcpyAsync(dp, hp, o_coeff, cudaMemcpyHostToDevice, st));
   // gaps between TU blocks (if the caller's offsets leave any) come back as zeros, not as stale bytes
   CK(cudaMemsetAsync(dp + o_coeff, 0, total - o_coeff, st));
+  CK(aux_begin(ctx));
   k_tu_code<<<grid, TQ_WARPS * 32, sizeof(TqBlockS), st>>>(n, (const hevcdl_tu *)(dp + o_tus), (const int16_t *)(dp + o_resi),
                                                             coeff ? (int32_t *)(dp + o_coeff) : nullptr, (int16_t *)(dp + o_level),
                                                             deq ? (int32_t *)(dp + o_deq) : nullptr, (int16_t *)(dp + o_rec),
@@ -960,6 +978,7 @@ int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevc
                                                             rdoq ? (const hevcdl_tu_rdoq *)(dp + o_rq) : nullptr,
                                                             rdoq ? (const int *)(dp + o_est) : nullptr, (RdoqScratch *)ctx->dRdoq);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->evAux1, st));
   ctx->stats.kernel_launches++;
   CK(cudaMemcpyAsync(hp + o_coeff, dp + o_coeff, total - o_coeff, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -975,6 +994,15 @@ int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevc
 int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level,
                    int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd) {
   return hevcdl_tu_code_rdoq(ctx, n, tus, nullptr, nullptr, 0, resi, nelem, coeff, level, deq, rec, abs_sum, ssd);
+}
+
+int hevcdl_last_aux_ms(hevcdl_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return HEVCDL_E_INVAL;
+  if (!ctx->evAux0) return HEVCDL_E_NOFRAME;
+  cudaSetDevice(ctx->cfg.device);
+  CK(cudaEventSynchronize(ctx->evAux1));
+  CK(cudaEventElapsedTime(ms, ctx->evAux0, ctx->evAux1));
+  return HEVCDL_OK;
 }
 
 int hevcdl_bench_resident(hevcdl_ctx *ctx, const int *frames, int nframes, int iters, float ms[3], int *launches) {

@@ -27,7 +27,8 @@ EXPORTS = [
     "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
-EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream"]
+EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream",
+                    "hevcdl_last_aux_ms"]
 
 
 class Cfg(C.Structure):
@@ -94,6 +95,7 @@ def load_library():
     L.hevcdl_debug_rerun_rmd.argtypes = [vp, ip, vp]
     L.hevcdl_debug_copy.argtypes = [vp, ip, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.hevcdl_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.hevcdl_last_aux_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hevcdl_stream.argtypes = [vp]
     L.hevcdl_stream.restype = vp
     L.hevcdl_numa_bind_thread.argtypes = [ip]
@@ -318,6 +320,12 @@ class DepthPredictor:
         return out
 
     # -- measurement -------------------------------------------------------------------------
+    def last_aux_ms(self):
+        """Device time of the kernels of the most recent tu_code / deblock_frame / sao_stats call (hevcdl_last_aux_ms)."""
+        ms = C.c_float()
+        self._ck(self.lib.hevcdl_last_aux_ms(self.h, C.byref(ms)), "last_aux_ms")
+        return ms.value
+
     def bench_resident(self, frames, iters):
         fr = np.ascontiguousarray(frames, np.int32)
         ms = (C.c_float * 3)()

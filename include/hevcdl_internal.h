@@ -37,6 +37,11 @@ int hevcdl_debug_copy(hevcdl_ctx *ctx, int which, void *dst, size_t nbytes, size
  * getters return the new labels and their PU lists. */
 int hevcdl_debug_rerun_rmd(hevcdl_ctx *ctx, int frame, const uint8_t *labels);
 
+/* Measurement: device time (CUDA events on the context's stream, around the kernels only -- the copies are outside) of the
+ * most recent hevcdl_tu_code / hevcdl_tu_code_rdoq / hevcdl_deblock_frame / hevcdl_sao_stats call of this context.
+ * HEVCDL_E_NOFRAME before the first such call. */
+int hevcdl_last_aux_ms(hevcdl_ctx *ctx, float *ms);
+
 /* CUDA stream handle (cudaStream_t) of the context, for callers that time with their own events */
 void *hevcdl_stream(hevcdl_ctx *ctx);
 
