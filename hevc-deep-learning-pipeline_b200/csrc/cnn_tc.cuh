@@ -196,7 +196,7 @@ k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo
 #ifndef HEVCDL_K1_LDG
       STAGE_BAR_SYNC();                           // every staging thread has read the other raw buffer (CTU j-1)
       if (stid == 0 && ctu + (int)gridDim.x < total) issue_raw(ctu + gridDim.x, (j + 1) & 1);
-      MBAR_WAIT(&bar_raw[j & 1], (j >> 1) & 1, 13);
+      MBAR_WAIT(&bar_raw[j & 1], (j >> 1) & 1, 23);
       const uint8_t *raw = sm + K1_RAW + (j & 1) * RAW_BYTES;
 #pragma unroll
       for (int k = 0; k < K1_STAGE_ITERS; k++) {
@@ -235,7 +235,7 @@ k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo
           b0[k][i] = pack_bf16((float)b, 0.f);
         }
       }
-      if (j) MBAR_WAIT(&bar_pfree[0], (j - 1) & 1, 3);
+      if (j) MBAR_WAIT(&bar_pfree[0], (j - 1) & 1, 20);
 #pragma unroll
       for (int k = 0; k < K1_STAGE_ITERS; k++) {
         const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
@@ -250,7 +250,7 @@ k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_pfull[0]);
-      if (j) MBAR_WAIT(&bar_pfree[1], (j - 1) & 1, 4);
+      if (j) MBAR_WAIT(&bar_pfree[1], (j - 1) & 1, 21);
 #pragma unroll
       for (int k = 0; k < K1_STAGE_ITERS; k++) {
         const int it = stid + K1_STAGE_THREADS * k, y = it >> 4, x4 = (it & 15) * 4;
@@ -278,7 +278,7 @@ k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo
 #pragma unroll 1
         for (int pi = 0; pi < 4; pi++) {
           const uint32_t n = npair + pi, p = n & 1, use = n >> 1;
-          if ((pi & 1) == 0) MBAR_WAIT(&bar_pfull[pi >> 1], j & 1, 5);
+          if ((pi & 1) == 0) MBAR_WAIT(&bar_pfull[pi >> 1], j & 1, 22);
           MBAR_WAIT(&bar_empty[p], (use & 1) ^ 1, 1);
           fence_after_sync();
           const bool c1 = pi >= 2;
@@ -320,101 +320,103 @@ k_tc_l1(const FrameBatch fb, const __grid_constant__ TmapBatch tm, FrameGeom geo
       float s[8], q[8], pool64[4][8];
 #pragma unroll
       for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
-      // fully unrolled: the tile index t is a compile-time constant below, so pool64[] stays in registers (no select chains /
-      // local memory for a dynamic index), the conv64 / conv1 branches and the reduction points are resolved statically
-#pragma unroll
-      for (int pi = 0; pi < 4; pi++) {
-        const uint32_t n = npair + pi, p = pi & 1, use = n >> 1;   // npair is a multiple of 4
-        MBAR_WAIT(&bar_full[p], use & 1, 2);
-        fence_after_sync();
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int t = pi * 2 + e;
-          float v[8][8];                            // [position in the 4x2 super-pixel][channel 8h + c]: 64 contiguous columns
-          tmem_ld32(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + 64 * h), &v[0][0]);
-          tmem_ld32(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + 64 * h + 32), &v[4][0]);
-          tmem_ld_wait();
-          if (e == 1) {   // both accumulators of the pair are in registers: hand the TMEM slots back
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[p]);
-          }
+      // One tile of accumulators: load, hand the pair's slots back after its second tile, statistics, then either the
+      // conv64 4x4 max-pool into pool64[T] (T compile-time: registers, no select chains) or -- conv1 -- the sample's
+      // batch statistics, normalisation, 2x2 max-pool and store.  conv64's four tiles are unrolled; conv1's four run as a
+      // loop over one body (the instruction footprint of the three roles of this kernel has to stay cache-resident).
+      uint8_t *cbase = cat + (size_t)ctu * CAT_BYTES;
+      auto tile = [&](auto Tc, const int t) {
+        constexpr int T = decltype(Tc)::value;      // 0..3: conv64 tile T; 4: a conv1 tile (t = 4..7 at run time)
+        const uint32_t pi = t >> 1, e = t & 1, p = pi & 1, use = (npair + pi) >> 1;   // npair is a multiple of 4
+        if (e == 0) { MBAR_WAIT(&bar_full[p], use & 1, 2); fence_after_sync(); }
+        float v[8][8];                              // [position in the 4x2 super-pixel][channel 8h + c]: 64 contiguous columns
+        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + 64 * h), &v[0][0]);
+        tmem_ld32(tmem_addr(tbase, lq * 32, (2 * p + e) * 128 + 64 * h + 32), &v[4][0]);
+        tmem_ld_wait();
+        if (e == 1) {   // both accumulators of the pair are in registers: hand the TMEM slots back
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_empty[p]);
+        }
 #ifdef HEVCDL_ABLATE_EPI
-          if (v[0][0] != 12345.f) continue;
+        if (v[0][0] != 12345.f) return;
 #endif
-          // sums and sums of squares, two channels per instruction (packed fp32 add / fma of sm_100)
+        // sums and sums of squares, two channels per instruction (packed fp32 add / fma of sm_100)
 #pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            float2 s2 = make_float2(s[c], s[c + 1]), q2 = make_float2(q[c], q[c + 1]);
+        for (int c = 0; c < 8; c += 2) {
+          float2 s2 = make_float2(s[c], s[c + 1]), q2 = make_float2(q[c], q[c + 1]);
 #pragma unroll
-            for (int pos = 0; pos < 8; pos++) {
-              const float2 x = make_float2(v[pos][c], v[pos][c + 1]);
-              s2 = __fadd2_rn(s2, x);
-              q2 = __ffma2_rn(x, x, q2);
-            }
-            s[c] = s2.x; s[c + 1] = s2.y; q[c] = q2.x; q[c + 1] = q2.y;
+          for (int pos = 0; pos < 8; pos++) {
+            const float2 x = make_float2(v[pos][c], v[pos][c + 1]);
+            s2 = __fadd2_rn(s2, x);
+            q2 = __ffma2_rn(x, x, q2);
           }
-          if (t < 4) {
+          s[c] = s2.x; s[c + 1] = s2.y; q[c] = q2.x; q[c + 1] = q2.y;
+        }
+        if (T < 4) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-              float mx = v[0][c];
+          for (int c = 0; c < 8; c++) {
+            float mx = v[0][c];
 #pragma unroll
-              for (int pos = 1; pos < 8; pos++) mx = fmaxf(mx, v[pos][c]);
-              mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));     // other row pair of the 4x4 window
-              pool64[t & 3][c] = mx;
-            }
-          }
-          const bool reduce_now = t >= 3;
-          if (reduce_now) {
-            // per-channel totals over the sample: transposing reduction inside the warp (lane l & 15 ends with value
-            // l: sums of channels 0..7, then sums of squares), the 4 warps of this channel half through shared memory
-            float pv[16];
-#pragma unroll
-            for (int c = 0; c < 8; c++) { pv[c] = s[c]; pv[8 + c] = q[c]; }
-            const float wt = warp_transpose_sum16(pv, lane);
-            if (lane < 16) red[(rb * 8 + warp) * 16 + lane] = wt;
-            EPI_BAR_SYNC();
-            float tot = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; k++) tot += red[(rb * 8 + h * 4 + k) * 16 + (lane & 15)];
-            const float totq = __shfl_down_sync(0xffffffffu, tot, 8);       // lanes 0..7: sum of squares of channel `lane`
-            float sc1, sh1;                                                  // scale/shift of channel lane & 7 (valid in lanes 0..7)
-            bn_scale_shift(tot, totq, t == 3 ? 1.f / 4096.f : 1.f / 1024.f, 1e-5f * 255.f * 255.f, t == 3 ? g64r : g1r, t == 3 ? b64r : b1r, sc1, sh1);
-            float sc[8], sh[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) { sc[c] = __shfl_sync(0xffffffffu, sc1, c); sh[c] = __shfl_sync(0xffffffffu, sh1, c); }
-            rb ^= 1;
-            uint8_t *cbase = cat + (size_t)ctu * CAT_BYTES;
-            if (t == 3) {
-              if ((g & 1) == 0) {
-#pragma unroll
-                for (int tt = 0; tt < 4; tt++) {
-                  float yv[8];
-#pragma unroll
-                  for (int c = 0; c < 8; c++) yv[c] = fmaxf(fmaf(pool64[tt][c], sc[c], sh[c]), 0.f);
-                  const int py = (tt >> 1) * 8 + (g >> 1), px = (tt & 1) * 8 + ii;
-                  *reinterpret_cast<uint4 *>(cbase + (8 + h) * CAT_PLANE + ((py + 1) * 18 + px + 1) * 16) = pack8_bf16(yv);
-                }
-              }
-            } else {
-              const int smp = t - 4;
-              float y0[8], y1[8];
-#pragma unroll
-              for (int c = 0; c < 8; c++) {
-                const float w0 = fmaxf(fmaxf(v[0][c], v[1][c]), fmaxf(v[4][c], v[5][c]));
-                const float w1 = fmaxf(fmaxf(v[2][c], v[3][c]), fmaxf(v[6][c], v[7][c]));
-                y0[c] = fmaxf(fmaf(w0, sc[c], sh[c]), 0.f);
-                y1[c] = fmaxf(fmaf(w1, sc[c], sh[c]), 0.f);
-              }
-              uint8_t *d = cbase + (smp * 2 + h) * CAT_PLANE + ((g + 1) * 18 + 2 * ii + 1) * 16;
-              *reinterpret_cast<uint4 *>(d) = pack8_bf16(y0);
-              *reinterpret_cast<uint4 *>(d + 16) = pack8_bf16(y1);
-            }
-#pragma unroll
-            for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
+            for (int pos = 1; pos < 8; pos++) mx = fmaxf(mx, v[pos][c]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));     // other row pair of the 4x4 window
+            pool64[T & 3][c] = mx;
           }
         }
-      }
+        if (T >= 3) {
+          // per-channel totals over the sample: transposing reduction inside the warp (lane l & 15 ends with value
+          // l: sums of channels 0..7, then sums of squares), the 4 warps of this channel half through shared memory
+          float pv[16];
+#pragma unroll
+          for (int c = 0; c < 8; c++) { pv[c] = s[c]; pv[8 + c] = q[c]; }
+          const float wt = warp_transpose_sum16(pv, lane);
+          if (lane < 16) red[(rb * 8 + warp) * 16 + lane] = wt;
+          EPI_BAR_SYNC();
+          float tot = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; k++) tot += red[(rb * 8 + h * 4 + k) * 16 + (lane & 15)];
+          const float totq = __shfl_down_sync(0xffffffffu, tot, 8);       // lanes 0..7: sum of squares of channel `lane`
+          float sc1, sh1;                                                  // scale/shift of channel lane & 7 (valid in lanes 0..7)
+          bn_scale_shift(tot, totq, T == 3 ? 1.f / 4096.f : 1.f / 1024.f, 1e-5f * 255.f * 255.f, T == 3 ? g64r : g1r, T == 3 ? b64r : b1r, sc1, sh1);
+          float sc[8], sh[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) { sc[c] = __shfl_sync(0xffffffffu, sc1, c); sh[c] = __shfl_sync(0xffffffffu, sh1, c); }
+          rb ^= 1;
+          if (T == 3) {
+            if ((g & 1) == 0) {
+#pragma unroll
+              for (int tt = 0; tt < 4; tt++) {
+                float yv[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) yv[c] = fmaxf(fmaf(pool64[tt][c], sc[c], sh[c]), 0.f);
+                const int py = (tt >> 1) * 8 + (g >> 1), px = (tt & 1) * 8 + ii;
+                *reinterpret_cast<uint4 *>(cbase + (8 + h) * CAT_PLANE + ((py + 1) * 18 + px + 1) * 16) = pack8_bf16(yv);
+              }
+            }
+          } else {
+            const int smp = t - 4;
+            float y0[8], y1[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+              const float w0 = fmaxf(fmaxf(v[0][c], v[1][c]), fmaxf(v[4][c], v[5][c]));
+              const float w1 = fmaxf(fmaxf(v[2][c], v[3][c]), fmaxf(v[6][c], v[7][c]));
+              y0[c] = fmaxf(fmaf(w0, sc[c], sh[c]), 0.f);
+              y1[c] = fmaxf(fmaf(w1, sc[c], sh[c]), 0.f);
+            }
+            uint8_t *d = cbase + (smp * 2 + h) * CAT_PLANE + ((g + 1) * 18 + 2 * ii + 1) * 16;
+            *reinterpret_cast<uint4 *>(d) = pack8_bf16(y0);
+            *reinterpret_cast<uint4 *>(d + 16) = pack8_bf16(y1);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c++) { s[c] = 0.f; q[c] = 0.f; }
+        }
+      };
+      tile(std::integral_constant<int, 0>{}, 0);
+      tile(std::integral_constant<int, 1>{}, 1);
+      tile(std::integral_constant<int, 2>{}, 2);
+      tile(std::integral_constant<int, 3>{}, 3);
+#pragma unroll 1
+      for (int t = 4; t < 8; t++) tile(std::integral_constant<int, 4>{}, t);
     }
   }
   fence_before_sync();

@@ -3,6 +3,7 @@
 #include <cuda.h>           // CUtensorMap (type only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/hevcdl.h"
 

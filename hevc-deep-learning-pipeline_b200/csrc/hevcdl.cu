@@ -619,10 +619,10 @@ void hevcdl_destroy(hevcdl_ctx *ctx) {
     unsigned long long tr[64];
     if (cudaMemcpyFromSymbol(tr, tc::g_trace, sizeof tr) == cudaSuccess) {
       fprintf(stderr, "hevcdl trace (block 0 cycles, summed over all launches; epilogue sites are summed over the epilogue warps):\n"
-                      " K1: total %llu | mma: w %llu empty %llu | epi: full %llu\n"
+                      " K1: total %llu | mma: w %llu empty %llu planes %llu | epi: full %llu | staging (3 warps): raw %llu free64 %llu free1 %llu\n"
                       " K2: total %llu | mma: cfree %llu cfull %llu empty %llu | epi: full %llu\n"
                       " K3: total %llu | mma: w %llu empty %llu afull %llu afree %llu | epi: full %llu\n",
-              tr[16], tr[0], tr[1], tr[2], tr[17], tr[4], tr[5], tr[6], tr[7], tr[18], tr[8], tr[9], tr[10], tr[11], tr[12]);
+              tr[16], tr[0], tr[1], tr[22], tr[2], tr[23], tr[20], tr[21], tr[17], tr[4], tr[5], tr[6], tr[7], tr[18], tr[8], tr[9], tr[10], tr[11], tr[12]);
       memset(tr, 0, sizeof tr);
       cudaMemcpyToSymbol(tc::g_trace, tr, sizeof tr);
     }

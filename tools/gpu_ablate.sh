@@ -4,7 +4,7 @@
 # the ablated builds; only the launch durations are read (K6 depends on the labels and is ignored).
 TAG=${1:-r02o}
 mkdir -p gpurun_out
-for v in base EPI MMA; do
+for v in ${VARIANTS:-base EPI MMA}; do
   if [ $v = base ]; then unset HEVCDL_LIB; else export HEVCDL_LIB=$PWD/tools/ab/libhevcdl_ablate_$v.so; fi
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_tc -s 16 -c 32 --csv \
     --log-file gpurun_out/${TAG}_ablate_${v}.csv python bench.py --steps 12 --warmup 3 --pool 8 --no-cpu-baseline --no-parity > gpurun_out/${TAG}_ablate_${v}.log 2>&1
