@@ -24,5 +24,22 @@ rng = np.random.default_rng(1)
 blocks = [rng.integers(-255, 256, (n, n)).astype(np.int16) for n in (4, 8, 16, 32) * 64]
 out = dp.tu_code(blocks, rng.integers(0, 52, len(blocks)), [host.TU_DST if b.shape[0] == 4 and i % 3 == 0 else (host.TU_TSKIP if b.shape[0] == 4 and i % 3 == 1 else 0) for i, b in enumerate(blocks)])
 tot += int(out["abs_sum"].sum() & 0xFFFF)
+# ... the same core with the rate-distortion optimised quantiser (real bit-estimate tables from the RDOQ fixture)
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "tq_rdoq_192x128_qp32.npz"))
+hdr = g["hdr"]
+sel = [i for i in range(len(hdr)) if hdr[i][7] == 0][:96]
+blocks = [rng.integers(-40, 41, (int(hdr[i][1]), int(hdr[i][1]))).astype(np.int16) for i in sel]
+rq = np.array([(float(g["lam"][i]), k, 0 if hdr[i][2] == 0 else 1, int(hdr[i][6]), int(hdr[i][8]), 3) for k, i in enumerate(sel)], host.TU_RDOQ_DTYPE)
+out = dp.tu_code(blocks, [int(hdr[i][3]) for i in sel], [host.TU_RDOQ] * len(sel), rdoq=rq, est=np.stack([g["est"][i] for i in sel]))
+tot += int(out["abs_sum"].sum() & 0xFFFF)
+# the in-loop passes: deblocking filter and SAO statistics of a 416x240 picture (partial CTUs right and bottom)
+W, H = 416, 240
+Y = np.clip(np.kron(rng.integers(30, 226, (H // 8, W // 8)), np.ones((8, 8))) + rng.integers(-3, 4, (H, W)), 0, 255).astype(np.uint8)
+U = np.clip(np.kron(rng.integers(60, 196, (H // 16, W // 16)), np.ones((8, 8))) + rng.integers(-2, 3, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+V = U[::-1, ::-1].copy()
+tu = np.kron(rng.integers(3, 6, (H // 32 + 1, W // 32 + 1)), np.ones((8, 8), np.int64))[:H // 4, :W // 4].astype(np.uint8)
+rec = dp.deblock_frame(Y, U, V, tu, np.full(tu.shape, 34, np.int8))
+st = dp.sao_stats((Y, U, V), rec)
+tot += int(rec[0].sum() & 0xFFFF) + int(st[:, :, :, 1].sum() & 0xFFFF)
 dp.close()
 print("sanitize_frame ok: checksum", tot)
