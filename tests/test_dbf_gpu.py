@@ -138,3 +138,42 @@ def test_dropin_sao_statistics_on_the_device_keep_the_bitstream(tmp_path, built,
     assert ra["sha1"] == rb["sha1"]
     ok, out = hm_util.decode_ok(str(b))
     assert ok, out[-400:]
+
+
+@pytest.mark.parametrize("W,H", [(3840, 2160), (7680, 4320)])
+def test_inloop_passes_at_baseline_sizes(dp, oracle, W, H):
+    """BASELINE configs[3] / [4] picture sizes: deblocking and SAO statistics equal the oracle on the whole picture, and the
+    size-independent properties hold: a flat picture passes the filter unchanged; per CTU and component the band-offset
+    counts add up to the samples SAO may touch (block minus the not-yet-deblocked right / bottom lines) and the band-offset
+    differences to the plain sum of (original - reconstructed) over the same samples."""
+    rng = np.random.default_rng(W)
+    base = np.kron(rng.integers(30, 226, (H // 8, W // 8)), np.ones((8, 8)))
+    Y = np.clip(base + rng.integers(-3, 4, (H, W)), 0, 255).astype(np.uint8)
+    U = np.clip(np.kron(rng.integers(60, 196, (H // 16, W // 16)), np.ones((8, 8))) + rng.integers(-2, 3, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+    V = U[::-1, ::-1].copy()
+    tu = np.kron(rng.integers(2, 6, (H // 32 + 1, W // 32 + 1)), np.ones((8, 8), np.int64))[:H // 4, :W // 4].astype(np.uint8)
+    qp = np.kron(rng.integers(18, 46, (H // 64 + 1, W // 64 + 1)), np.ones((16, 16), np.int64))[:H // 4, :W // 4].astype(np.int8)
+    want = oracle.deblock_frame(Y, U, V, tu, qp, 1, -1, 2, -2)
+    got = dp.deblock_frame(Y, U, V, tu, qp, 1, -1, 2, -2)
+    for a, b, name in zip(got, want, "YUV"):
+        assert (a == b).all(), (name, int((a != b).sum()))
+    assert (got[0] != Y).sum() > W * H // 100
+    flat = [np.full_like(Y, 97), np.full_like(U, 140), np.full_like(V, 99)]
+    for a, b in zip(dp.deblock_frame(*flat, tu, qp), flat):
+        assert (a == b).all()
+    st = dp.sao_stats((Y, U, V), got)
+    assert (st == oracle.sao_stats((Y, U, V), got)).all()
+    cw, chh = (W + 63) // 64, (H + 63) // 64
+    for c, (o, r, s, skr, skb) in enumerate(((Y, got[0], 64, 5, 4), (U, got[1], 32, 3, 2), (V, got[2], 32, 3, 2))):
+        h, w = o.shape
+        d = o.astype(np.int64) - r
+        cnt = np.zeros((chh, cw), np.int64)
+        dif = np.zeros((chh, cw), np.int64)
+        for cy in range(chh):
+            y1 = min(h, (cy + 1) * s) - (skb if cy < chh - 1 else 0)
+            for cx in range(cw):
+                x1 = min(w, (cx + 1) * s) - (skr if cx < cw - 1 else 0)
+                cnt[cy, cx] = (y1 - cy * s) * (x1 - cx * s)
+                dif[cy, cx] = d[cy * s:y1, cx * s:x1].sum()
+        assert (st[:, c, 4, 1, :].sum(axis=1).reshape(chh, cw) == cnt).all(), c
+        assert (st[:, c, 4, 0, :].sum(axis=1).reshape(chh, cw) == dif).all(), c

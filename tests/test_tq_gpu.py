@@ -144,3 +144,37 @@ def test_rdoq_full_path_vs_oracle_random(dp, oracle, host):
         assert (out["level"][k] == lev).all() and out["abs_sum"][k] == s, ("level", k, b.shape, qps[k], scan, ts)
         nz += s > 0
     assert nz > 200
+
+
+def test_tu_core_one_8k_picture_of_tus(dp, oracle, host):
+    """BASELINE configs[4] scale: the luma area of a 7680x4320 picture as ~690 k TUs (a quarter of the area per size) in ONE
+    call.  Size-independent properties on all of them -- abs_sum is the sum of |level|, ssd the squared error of the
+    reconstructed residual, an all-zero residual codes to nothing, the coding of a block does not depend on its neighbours
+    in the batch -- and equality with the oracle on a sample of 400."""
+    rng = np.random.default_rng(3)
+    blocks, qps, flags = [], [], []
+    for n in (4, 8, 16, 32):
+        cnt = 7680 * 4320 // 4 // (n * n)
+        lap = np.round(rng.laplace(0, 5, (cnt, n, n))).clip(-255, 255).astype(np.int16)
+        lap[::97] = 0
+        blocks += list(lap)
+        qps += list(rng.integers(12, 45, cnt))
+        flags += [host.TU_DST if n == 4 else 0] * cnt
+    out = dp.tu_code(blocks, qps, flags, want_coeff=False, want_deq=False)
+    n = len(blocks)
+    assert n > 600000
+    for i in rng.integers(0, n, 400):
+        c, q, d, r, s = oracle.tq_tu(blocks[i], int(qps[i]), flags[i])
+        assert (out["level"][i] == q).all() and (out["rec"][i] == r).all() and out["abs_sum"][i] == s, i
+    lev = np.concatenate([x.ravel() for x in out["level"]]).astype(np.int64)
+    rec = np.concatenate([x.ravel() for x in out["rec"]]).astype(np.int64)
+    res = np.concatenate([b.ravel() for b in blocks]).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum([b.size for b in blocks])])
+    assert (np.add.reduceat(np.abs(lev), off[:-1]) == out["abs_sum"]).all()
+    assert (np.add.reduceat((res - rec) ** 2, off[:-1]) == out["ssd"]).all()
+    zero = np.add.reduceat(np.abs(res), off[:-1]) == 0
+    assert zero.sum() > 5000 and (out["abs_sum"][zero] == 0).all()
+    sub = rng.integers(0, n, 2000)
+    again = dp.tu_code([blocks[i] for i in sub], [qps[i] for i in sub], [flags[i] for i in sub], want_coeff=False, want_deq=False)
+    for k, i in enumerate(sub):
+        assert (again["level"][k] == out["level"][i]).all() and (again["rec"][k] == out["rec"][i]).all()
