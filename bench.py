@@ -445,6 +445,13 @@ def run_b200(args, rank, world, local_rank):
         for k, name in pick.items():
             if k in bd.get("bd", {}):
                 out["bd_rate"][name] = {"bd_rate_y_pct": round(bd["bd"][k]["bd_rate_y_pct"], 3), "bd_psnr_y_db": round(bd["bd"][k]["bd_psnr_y_db"], 4)}
+    bp8 = os.path.join(ROOT, "profiles", "r02_bdrate_8k_8f.json")
+    if os.path.exists(bp8) and "bd_rate" in out:     # BASELINE configs[4], same procedure on 8 frames 7680x4320
+        bd8 = json.load(open(bp8))
+        out["bd_rate"]["config_8k"] = {"source": "profiles/r02_bdrate_8k_8f.json: %dx%d, %d frames, QP %s" % (bd8["width"], bd8["height"], bd8["frames"], bd8["qps"])}
+        for k, name in (("hm_dl_vs_anchor", "reference_hm_dl_vs_anchor"), ("dropin_bf16_gpu_rmd_fix0_vs_hm_dl", "dropin_bf16_labels_gpu_rmd_vs_reference_hm_dl")):
+            if k in bd8.get("bd", {}):
+                out["bd_rate"]["config_8k"][name] = {"bd_rate_y_pct": round(bd8["bd"][k]["bd_rate_y_pct"], 3), "bd_psnr_y_db": round(bd8["bd"][k]["bd_psnr_y_db"], 4)}
     if world > 1 or args.probe:
         out["copy_probe"] = copy_probe(host, torch, dist, world, frame_bytes)
         out["copy_probe"]["what"] = "all %d ranks copying one frame's planes at once from / to pinned host memory, per-rank GB/s" % world
