@@ -19,6 +19,7 @@
 #include "tq.cuh"
 #include "dbf.cuh"
 #include "sao.cuh"
+#include "pred.cuh"
 #include "../../include/hevcdl_internal.h"
 
 using namespace hevcdl;
@@ -873,6 +874,48 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_
     memcpy(u + (size_t)r * sc, hp + o_u + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
     memcpy(v + (size_t)r * sc, hp + o_v + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
   }
+  return HEVCDL_OK;
+}
+
+int hevcdl_intra_pred(hevcdl_ctx *ctx, int n, const hevcdl_pred_req *reqs, const int16_t *lines, size_t nline, int16_t *pred, size_t npred) {
+  static_assert(sizeof(hevcdl_pred_req) == sizeof(IntraPredReq), "hevcdl_pred_req layout");
+  if (!ctx || n < 0 || (n && (!reqs || !lines || !pred))) return HEVCDL_E_INVAL;
+  if (n == 0) return HEVCDL_OK;
+  for (int i = 0; i < n; i++) {
+    const hevcdl_pred_req &r = reqs[i];
+    const size_t sz = r.log2_size >= 2 && r.log2_size <= 6 ? (size_t)1 << r.log2_size : 0;
+    if (!sz || r.mode > 34 || (size_t)r.line_offset + 4 * sz + 1 > nline || (size_t)r.pred_offset + sz * sz > npred) {
+      ctx->err = "hevcdl_intra_pred: log2_size 2..6, mode 0..34, line and block inside the buffers";
+      return HEVCDL_E_INVAL;
+    }
+  }
+  cudaSetDevice(ctx->cfg.device);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_req = al((size_t)n * sizeof(hevcdl_pred_req)), b_line = al(nline * 2), b_pred = al(npred * 2);
+  const size_t o_req = 0, o_line = o_req + b_req, o_pred = o_line + b_line, total = o_pred + b_pred;
+  if (total > ctx->tqCap) {                       // shares the TU core's grow-only scratch
+    cudaFree(ctx->dTq); ctx->dTq = nullptr; ctx->tqCap = 0;
+    if (ctx->hTq) { cudaFreeHost(ctx->hTq); ctx->hTq = nullptr; }
+    const size_t cap = total < (1u << 20) ? (1u << 20) : total + total / 2;
+    CK(cudaMalloc(&ctx->dTq, cap));
+    CK(cudaMallocHost(&ctx->hTq, cap));
+    ctx->tqCap = cap;
+  }
+  uint8_t *hp = (uint8_t *)ctx->hTq, *dp = (uint8_t *)ctx->dTq;
+  memcpy(hp + o_req, reqs, (size_t)n * sizeof(hevcdl_pred_req));
+  memcpy(hp + o_line, lines, nline * 2);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dp, hp, o_pred, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(dp + o_pred, 0, b_pred, st));          // gaps between blocks come back as zeros
+  const int grid = (n + PRED_WARPS - 1) / PRED_WARPS < 8 * ctx->numSMs ? (n + PRED_WARPS - 1) / PRED_WARPS : 8 * ctx->numSMs;
+  CK(aux_begin(ctx));
+  k_intra_pred<<<grid, PRED_WARPS * 32, 0, st>>>(n, (const IntraPredReq *)(dp + o_req), (const int16_t *)(dp + o_line), (int16_t *)(dp + o_pred));
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->evAux1, st));
+  ctx->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(hp + o_pred, dp + o_pred, npred * 2, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(pred, hp + o_pred, npred * 2);
   return HEVCDL_OK;
 }
 

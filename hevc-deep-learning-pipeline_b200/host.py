@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream",
@@ -52,6 +52,8 @@ TU_DTYPE = np.dtype([("log2_size", "u1"), ("qp", "u1"), ("flags", "u1"), ("reser
 TU_DST, TU_TSKIP, TU_INTER, TU_RDOQ, TU_COEFF_IN = 1, 2, 4, 8, 16
 TU_RDOQ_DTYPE = np.dtype([("lambda", "<f8"), ("est_index", "<u4"), ("channel", "u1"), ("scan_type", "u1"), ("ctx_cbf", "u1"), ("flags", "u1")])
 EST_INTS = 224
+PRED_REQ_DTYPE = np.dtype([("log2_size", "u1"), ("mode", "u1"), ("flags", "u1"), ("reserved", "u1"), ("line_offset", "<u4"), ("pred_offset", "<u4")])
+PRED_EDGE = 1
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("part", "u1"), ("ctu", "<u2")])
 
 
@@ -104,6 +106,7 @@ def load_library():
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
     L.hevcdl_sao_stats.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
+    L.hevcdl_intra_pred.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, C.c_size_t]
     L.hevcdl_deblock_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip]
     L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     L.hevcdl_tu_code_rdoq.argtypes = [vp, ip, vp, vp, vp, ip, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
@@ -293,6 +296,25 @@ class DepthPredictor:
         def split(a):
             return None if a is None else [a[off[i]:off[i + 1]].reshape(sizes[i], sizes[i]) for i in range(n)]
         return {"coeff": split(coeff), "level": split(level), "deq": split(deq), "rec": split(rec), "abs_sum": asum, "ssd": ssd}
+
+    # -- intra prediction of single blocks ------------------------------------------------------------
+    def intra_pred(self, lines, modes, edge):
+        """lines: list of reference lines (4N+1 int16 each: left column bottom-up, corner, top row); modes, edge: per block the
+        intra mode 0..34 and whether the luma edge filters apply (hevcdl_intra_pred).  Returns the list of (N, N) int16 blocks."""
+        n = len(lines)
+        sizes = np.array([(len(l) - 1) // 4 for l in lines], np.int64)
+        loff = np.concatenate([[0], np.cumsum([len(l) for l in lines])])
+        poff = np.concatenate([[0], np.cumsum(sizes * sizes)])
+        rq = np.zeros(n, PRED_REQ_DTYPE)
+        rq["log2_size"] = [int(s).bit_length() - 1 for s in sizes]
+        rq["mode"] = modes
+        rq["flags"] = [PRED_EDGE if e else 0 for e in edge]
+        rq["line_offset"] = loff[:-1]
+        rq["pred_offset"] = poff[:-1]
+        ln = np.concatenate([np.asarray(l, np.int16) for l in lines]) if n else np.zeros(0, np.int16)
+        out = np.zeros(int(poff[-1]), np.int16)
+        self._ck(self.lib.hevcdl_intra_pred(self.h, n, _ptr(rq), _ptr(ln), ln.size, _ptr(out), out.size), "intra_pred")
+        return [out[poff[i]:poff[i + 1]].reshape(sizes[i], sizes[i]) for i in range(n)]
 
     # -- in-loop deblocking filter -----------------------------------------------------------------
     def deblock_frame(self, Y, U, V, tu_log2, qp, beta_off_div2=0, tc_off_div2=0, cb_qp_off=0, cr_qp_off=0):

@@ -34,6 +34,9 @@
 //                     bitstreams; TUs the core does not cover stay HM's (hm_plugin/rmd_hook.h)
 //   HEVCDL_DBF        1 = the deblocking filter of every picture on the device (hevcdl_deblock_frame; hm_plugin/
 //                     TComLoopFilter_hevcdl.cpp replaces TComLoopFilter::loopFilterPic): byte-identical bitstreams
+//   HEVCDL_PRED       1 = every intra-predicted block (TComPrediction::predIntraAng: first pass and RD pass, luma and chroma) on
+//                     the device (hevcdl_intra_pred; hm_plugin/TComPrediction_hevcdl.cpp), one synchronous call per block:
+//                     byte-identical bitstreams
 //   HEVCDL_SAO        1 = the statistics pass of the SAO parameter estimation on the device (hevcdl_sao_stats; hm_plugin/
 //                     TEncSAO_hevcdl.cpp replaces TEncSampleAdaptiveOffset::getStatistics): byte-identical bitstreams
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
@@ -235,6 +238,7 @@ struct HevcdlSession {
   unsigned ex_x = ~0u, ex_y = ~0u, ex_n = 0;      // PU whose 35 SATDs are cached in ex_satd
   uint32_t ex_satd[35];
   unsigned long long exact_calls = 0;
+  unsigned long long pred_device = 0, pred_host = 0; // intra-predicted blocks on the device / by the reference's own code
   unsigned long long sao_device = 0, sao_host = 0;   // SAO statistics passes on the device / by the reference's own code
   unsigned long long dbf_device = 0, dbf_host = 0;   // pictures deblocked on the device / by the reference's own filter
   bool gpu_tq = false;          // HEVCDL_TQ=1: TU transform / quantisation / inverse transform on the device
@@ -401,6 +405,7 @@ struct HevcdlSession {
     if (ctx) {
       if (getenv("HEVCDL_VERBOSE")) {
         fprintf(stderr, "hevcdl: pictures deblocked on the device %llu / by the reference's filter %llu\n", dbf_device, dbf_host);
+        fprintf(stderr, "hevcdl: blocks predicted on the device %llu / by the reference's code %llu\n", pred_device, pred_host);
         fprintf(stderr, "hevcdl: SAO statistics passes on the device %llu / by the reference's code %llu\n", sao_device, sao_host);
         fprintf(stderr, "hevcdl: lookahead %d: %llu frames were on the device before HM asked, %llu uploaded from HM's planes, %llu mismatches\n",
                 lookahead, la_hits, la_direct, la_mismatch);
@@ -498,6 +503,7 @@ bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu
 }
 
 hevcdl_ctx *hevcdl_hm_context() { return g_session.ctx; }
+void hevcdl_hm_count_pred( bool onDevice ) { ( onDevice ? g_session.pred_device : g_session.pred_host )++; }
 void hevcdl_hm_count_sao( bool onDevice ) { ( onDevice ? g_session.sao_device : g_session.sao_host )++; }
 void hevcdl_hm_count_dbf( bool onDevice ) { ( onDevice ? g_session.dbf_device : g_session.dbf_host )++; }
 

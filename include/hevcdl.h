@@ -216,6 +216,24 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int stride_y, int16_t *u, 
                          const uint8_t *tu_log2, const int8_t *qp, int beta_offset_div2, int tc_offset_div2, int cb_qp_offset,
                          int cr_qp_offset);
 
+/* Intra prediction of `n` blocks from explicit reference samples: the arithmetic of TComPrediction::predIntraAng (HM TLibCommon/
+ * TComPrediction.cpp:390-472: planar, DC with boundary smoothing, the 33 angular predictors with the projected side reference and
+ * the first-column filter of the pure vertical / horizontal modes), which the RD pass calls for every luma and chroma transform
+ * block (TEncSearch.cpp:1208) and the first pass for every mode (:2303).  Per block: log2_size 2..6, mode 0..34, flags bit 0 =
+ * luma edge filters enabled (what the reference applies for luma blocks up to 16x16; clear for chroma), line_offset = start, in
+ * samples, of its reference line in `lines` -- 4*size+1 samples in the order of hevcdl_rmd_exact: left column bottom-up, corner,
+ * top row (what getPredictorPtr holds after TComPattern's availability / substitution / smoothing steps, filtered or not as the
+ * reference chose) --, pred_offset = where its size*size predicted samples go in `pred` (dense, row-major).  8-bit.  Bit-exact.
+ * Synchronous. */
+typedef struct hevcdl_pred_req {
+  uint8_t log2_size, mode, flags, reserved;
+  uint32_t line_offset;
+  uint32_t pred_offset;
+} hevcdl_pred_req;
+#define HEVCDL_PRED_EDGE 1u
+int hevcdl_intra_pred(hevcdl_ctx *ctx, int n, const hevcdl_pred_req *reqs, const int16_t *lines, size_t nline, int16_t *pred,
+                      size_t npred);
+
 /* SAO statistics of one deblocked picture: replaces the data pass of the reference's SAO parameter estimation,
  * TEncSampleAdaptiveOffset::getStatistics (HM TLibEncoder/TEncSampleAdaptiveOffset.cpp:295-341 -> getBlkStats :943-1345) as
  * SAOProcess calls it (:258) for deblocked samples.  org_* / rec_*: HM's Pel (int16) planes of the original and the deblocked

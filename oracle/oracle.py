@@ -44,6 +44,7 @@ def lib():
         L.oracle_mode_uses_filter.argtypes = [C.c_int, C.c_int]
         L.oracle_mode_uses_filter.restype = C.c_int
         L.oracle_predict.argtypes = [i16p, C.c_int, C.c_int, i16p]
+        L.oracle_predict_ex.argtypes = [i16p, C.c_int, C.c_int, C.c_int, i16p]
         L.oracle_satd.argtypes = [u8p, C.c_int, i16p, C.c_int]
         L.oracle_satd.restype = C.c_uint32
         L.oracle_pu_satd35.argtypes = [C.c_void_p, C.c_int, i16p, C.c_int, u32p]
@@ -132,9 +133,11 @@ def filter_ref_line(line, n):
     return out
 
 
-def predict(line, n, mode):
+def predict(line, n, mode, edge=True):
+    """One intra-predicted block from a reference line (4n+1 samples: left column bottom-up, corner, top row).  edge: luma
+    edge filters (False = chroma)."""
     out = np.zeros((n, n), np.int16)
-    lib().oracle_predict(np.ascontiguousarray(line), n, mode, out)
+    lib().oracle_predict_ex(np.ascontiguousarray(line, np.int16), n, mode, 1 if edge else 0, out)
     return out
 
 

@@ -270,8 +270,8 @@ def test_sidecar_accepts_sizes_that_are_not_multiples_of_8(tmp_path, built, host
 @pytest.mark.gpu
 def test_dropin_every_device_component_at_once(tmp_path, built, host, pkg):
     """Labels (CNN, fp32), frame lookahead, exact first-pass SATDs from HM's reconstructed references (HEVCDL_RMD=2), transform +
-    RDOQ + dequantiser + inverse transform of every TU (HEVCDL_TQ=1), the deblocking filter (HEVCDL_DBF=1) and the SAO statistics
-    (HEVCDL_SAO=1) all on the B200
+    RDOQ + dequantiser + inverse transform of every TU (HEVCDL_TQ=1), every intra-predicted block of the RD pass (HEVCDL_PRED=1),
+    the deblocking filter (HEVCDL_DBF=1) and the SAO statistics (HEVCDL_SAO=1) all on the B200
     inside one encode at the reference's default options: the bitstream must still be byte-identical to the unmodified
     reference encoder's, and the stream must decode with matching picture hashes."""
     import re
@@ -288,7 +288,7 @@ def test_dropin_every_device_component_at_once(tmp_path, built, host, pkg):
     ra = hm_util.encode("ref", str(a), "in.yuv", w, h, n, qp)
     rb = hm_util.encode("hevcdl", str(b), "in.yuv", w, h, n, qp,
                         env={"HEVCDL_PRECISION": "fp32", "HEVCDL_RMD": "2", "HEVCDL_TQ": "1", "HEVCDL_DBF": "1", "HEVCDL_SAO": "1",
-                             "HEVCDL_VERBOSE": "1"})
+                             "HEVCDL_PRED": "1", "HEVCDL_VERBOSE": "1"})
     assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-600:])
     err = rb["stderr"]
     assert int(re.search(r"exact PU calls (\d+)", err).group(1)) > 100
@@ -296,6 +296,8 @@ def test_dropin_every_device_component_at_once(tmp_path, built, host, pkg):
     assert int(m.group(1)) > 1000 and int(m.group(2)) == 0
     assert re.search(r"pictures deblocked on the device %d / by the reference's filter 0" % n, err)
     assert re.search(r"SAO statistics passes on the device %d / by the reference's code 0" % n, err)
+    m = re.search(r"blocks predicted on the device (\d+) / by the reference's code (\d+)", err)
+    assert int(m.group(1)) > 5000 and int(m.group(2)) == 0
     assert re.search(r"lookahead 3: %d frames were on the device before HM asked" % (n - 1), err)
     assert ra["sha1"] == rb["sha1"]
     ok, out = hm_util.decode_ok(str(b))

@@ -4,6 +4,7 @@ container (needs /root/reference and `make -C oracle ref`); the fixtures travel,
 
   tests/golden/tq_transform_ref.npz   random and extreme blocks through the reference's OWN xTrMxN / xITrMxN
                                       (oracle/_ref/libtqref.so = tq_ref_harness.cpp linked with libhmref.a), every size + DST
+  tests/golden/pred_trace_192x128_qp32.npz  reference samples + predicted blocks of the reference's own predIntraAng (luma and chroma)
   tests/golden/sao_stats.npz          original + deblocked pictures and the statistics the reference's own SAO getStatistics made of them
   tests/golden/dbf_pictures.npz       reconstructed pictures before / after the reference's own deblocking filter + its TU / QP maps
   tests/golden/tq_rdoq_192x128_qp32.npz    calls of the reference's xRateDistOptQuant (inputs incl. the CABAC bit-estimate
@@ -263,9 +264,41 @@ def sao_vectors():
     print("sao_stats.npz:", os.path.getsize(os.path.join(GOLD, "sao_stats.npz")), "bytes")
 
 
+def pred_vectors():
+    """tests/golden/pred_trace_192x128_qp32.npz: reference samples and output of the reference's own TComPrediction::predIntraAng
+    (oracle/_ref/TAppEncoder_predtrace, oracle/pred_dump.h) during an encode of the 192x128 fixture frame: up to 6 calls per
+    (luma / chroma, block size, mode) -- first pass and RD pass, filtered and unfiltered references, Cb and Cr."""
+    g = np.load(os.path.join(GOLD, "rmd_trace_192x128_qp32.npz"))
+    Y, U, V, labels = g["Y"], g["U"], g["V"], g["labels"]
+    H, W = Y.shape
+    with tempfile.TemporaryDirectory() as td:
+        hm_util.write_yuv(os.path.join(td, "in.yuv"), [(Y, U, V)])
+        hm_util.write_pred(os.path.join(td, "pred"), 0, labels)
+        cmd = [os.path.join(REFDIR, "TAppEncoder_predtrace"), "-c", hm_util.CFG, "-i", "in.yuv", "-wdt", str(W), "-hgt", str(H), "-fr", "30",
+               "-f", "1", "-q", "32", "-b", "t.bin", "--InputBitDepth=8", "--InputChromaFormat=420", "--Level=6.2"]
+        subprocess.check_call(cmd, cwd=td, env=dict(os.environ, HEVCDL_PRED_DUMP=os.path.join(td, "pred.bin")), stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        raw = open(os.path.join(td, "pred.bin"), "rb").read()
+    hdrs, lines, preds, off = [], [], [], 0
+    while off < len(raw):
+        h = np.frombuffer(raw, np.int32, 8, off); off += 32
+        assert h[0] == 0x50524430
+        n = int(h[3])
+        lines.append(np.frombuffer(raw, np.int16, 4 * n + 1, off)); off += 2 * (4 * n + 1)
+        preds.append(np.frombuffer(raw, np.int16, n * n, off)); off += 2 * n * n
+        hdrs.append(h[1:6])
+    hdrs = np.array(hdrs, np.int32)
+    out = {"hdr": hdrs, "line": np.concatenate(lines), "pred": np.concatenate(preds),
+           "line_off": np.concatenate([[0], np.cumsum([len(x) for x in lines])]), "pred_off": np.concatenate([[0], np.cumsum([len(x) for x in preds])])}
+    np.savez_compressed(os.path.join(GOLD, "pred_trace_192x128_qp32.npz"), **out)
+    print("pred_trace: %d calls (luma %d, chroma %d), sizes %s, %d bytes" % (len(hdrs), (hdrs[:, 0] == 0).sum(), (hdrs[:, 0] != 0).sum(),
+          sorted(set(hdrs[:, 2].tolist())), os.path.getsize(os.path.join(GOLD, "pred_trace_192x128_qp32.npz"))))
+
+
 if __name__ == "__main__":
     transform_vectors()
     trace_vectors()
     rdoq_vectors()
     dbf_vectors()
     sao_vectors()
+    pred_vectors()
