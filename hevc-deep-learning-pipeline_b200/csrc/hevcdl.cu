@@ -877,6 +877,55 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_
   return HEVCDL_OK;
 }
 
+int hevcdl_sao_apply(hevcdl_ctx *ctx, const int16_t *sy, const int16_t *su, const int16_t *sv, int ssy, int ssc, int16_t *ry, int16_t *ru, int16_t *rv,
+                     int rsy, int rsc, int W, int H, const hevcdl_sao_param *params) {
+  if (!ctx || !sy || !su || !sv || !ry || !ru || !rv || !params || W < 8 || H < 8 || (W & 7) || (H & 7) || W > 8192 || H > 8192 || ssy < W || rsy < W ||
+      ssc < W / 2 || rsc < W / 2)
+    return HEVCDL_E_INVAL;
+  const int cw = (W + 63) / 64, chh = (H + 63) / 64, nctu = cw * chh;
+  for (int i = 0; i < nctu * 3; i++)
+    if (params[i].type < -1 || params[i].type > 4) { ctx->err = "hevcdl_sao_apply: type in -1..4"; return HEVCDL_E_INVAL; }
+  cudaSetDevice(ctx->cfg.device);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_t = al((size_t)nctu * 3), b_o = al((size_t)nctu * 3 * 32);
+  const size_t o_sy = 0, o_su = o_sy + b_y, o_sv = o_su + b_c, o_t = o_sv + b_c, o_o = o_t + b_t, o_ry = o_o + b_o, o_ru = o_ry + b_y, o_rv = o_ru + b_c,
+               total = o_rv + b_c;
+  if (total > ctx->dbfCap) {                      // shares the deblocking entry point's grow-only scratch
+    cudaFree(ctx->dDbf); ctx->dDbf = nullptr; ctx->dbfCap = 0;
+    if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
+    CK(cudaMalloc(&ctx->dDbf, total));
+    CK(cudaMallocHost(&ctx->hDbf, total));
+    ctx->dbfCap = total;
+  }
+  uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
+  auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {
+    for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
+  };
+  pack(o_sy, sy, ssy, W, H); pack(o_su, su, ssc, W / 2, H / 2); pack(o_sv, sv, ssc, W / 2, H / 2);
+  for (int i = 0; i < nctu * 3; i++) {
+    hp[o_t + i] = (uint8_t)params[i].type;
+    memcpy(hp + o_o + (size_t)i * 32, params[i].offset, 32);
+  }
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dp, hp, o_ry, cudaMemcpyHostToDevice, st));
+  SaoApplyParams P{};
+  P.src[0] = (const int16_t *)(dp + o_sy); P.src[1] = (const int16_t *)(dp + o_su); P.src[2] = (const int16_t *)(dp + o_sv);
+  P.res[0] = (int16_t *)(dp + o_ry); P.res[1] = (int16_t *)(dp + o_ru); P.res[2] = (int16_t *)(dp + o_rv);
+  P.W = W; P.H = H; P.ctu_w = cw; P.type = (const int8_t *)(dp + o_t); P.offset = (const int8_t *)(dp + o_o);
+  CK(aux_begin(ctx));
+  k_sao_apply<<<nctu * 3, 256, 0, st>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->evAux1, st));
+  ctx->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(hp + o_ry, dp + o_ry, total - o_ry, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  auto unpack = [&](size_t off, int16_t *p, int stride, int w, int h) {
+    for (int r = 0; r < h; r++) memcpy(p + (size_t)r * stride, hp + off + (size_t)r * w * 2, (size_t)w * 2);
+  };
+  unpack(o_ry, ry, rsy, W, H); unpack(o_ru, ru, rsc, W / 2, H / 2); unpack(o_rv, rv, rsc, W / 2, H / 2);
+  return HEVCDL_OK;
+}
+
 int hevcdl_intra_pred(hevcdl_ctx *ctx, int n, const hevcdl_pred_req *reqs, const int16_t *lines, size_t nline, int16_t *pred, size_t npred) {
   static_assert(sizeof(hevcdl_pred_req) == sizeof(IntraPredReq), "hevcdl_pred_req layout");
   if (!ctx || n < 0 || (n && (!reqs || !lines || !pred))) return HEVCDL_E_INVAL;

@@ -71,4 +71,66 @@ k_sao_stats(const SaoParams P) {
   }
 }
 
+// ---- SAO application -----------------------------------------------------------------------------------------------
+// TComSampleAdaptiveOffset::offsetCTU / offsetBlock (HM TLibCommon/TComSampleAdaptiveOffset.cpp:554-611, 313-552) for every
+// CTU of the picture: res = clip(src + offset[class]) for the samples the CTU's SAO type may touch (edge types leave out
+// samples whose neighbour lies outside the picture -- one slice, no tiles -- with the reference's first / last line ranges
+// of the diagonal types), every other sample keeps its deblocked value.  Classification reads only `src`, so all CTUs are
+// independent: one block per (CTU, component), neighbours straight from global memory (each sample is read at most three
+// times, from L1 / L2), each thread one row segment.  HBM-bound byte work: two pictures' worth of int16 traffic.
+struct SaoApplyParams {
+  const int16_t *src[3];
+  int16_t *res[3];
+  int W, H, ctu_w;
+  const int8_t *type;        // [nctu][3]: -1 off, 0..3 edge offset 0 / 90 / 135 / 45 degrees, 4 band offset
+  const int8_t *offset;      // [nctu][3][32]
+};
+
+__global__ void __launch_bounds__(256)
+k_sao_apply(const SaoApplyParams P) {
+  __shared__ int s_off[32];
+  const int a = blockIdx.x / 3, c = blockIdx.x - 3 * a;
+  const int xp = (a % P.ctu_w) * 64, yp = (a / P.ctu_w) * 64;
+  const int hl = yp + 64 > P.H ? P.H - yp : 64, wl = xp + 64 > P.W ? P.W - xp : 64;
+  const int sh = c ? 1 : 0, stride = P.W >> sh, width = wl >> sh, height = hl >> sh;
+  const int16_t *__restrict__ s = P.src[c] + (size_t)(yp >> sh) * stride + (xp >> sh);
+  int16_t *__restrict__ r = P.res[c] + (size_t)(yp >> sh) * stride + (xp >> sh);
+  const int t = P.type[a * 3 + c];
+  if (threadIdx.x < 32) s_off[threadIdx.x] = P.offset[(size_t)(a * 3 + c) * 32 + threadIdx.x];
+  __syncthreads();
+  const bool L = xp > 0, A = yp > 0, R = xp + 64 < P.W, B = yp + 64 < P.H, AL = L && A, AR = A && R, BL = B && L, BR = B && R;
+  const int sx = L ? 0 : 1, ex = R ? width : width - 1;
+  for (int i = threadIdx.x; i < width * height; i += blockDim.x) {
+    const int y = i / width, x = i - y * width;
+    const int v = s[y * stride + x];
+    int out = v;
+    if (t >= 0) {
+      int xa, xb;
+      if (t == 4) { xa = 0; xb = width; }
+      else if (t == 0) { xa = sx; xb = ex; }
+      else if (t == 1) { xa = 0; xb = (y < (A ? 0 : 1) || y >= (B ? height : height - 1)) ? 0 : width; }
+      else if (t == 2) {
+        if (y == 0) { xa = AL ? 0 : 1; xb = A ? ex : 1; }
+        else if (y == height - 1) { xa = B ? sx : width - 1; xb = BR ? width : width - 1; }
+        else { xa = sx; xb = ex; }
+      } else {
+        if (y == 0) { xa = A ? sx : width - 1; xb = AR ? width : width - 1; }
+        else if (y == height - 1) { xa = BL ? 0 : 1; xb = B ? ex : 1; }
+        else { xa = sx; xb = ex; }
+      }
+      if (x >= xa && x < xb) {
+        int cls;
+        if (t == 4) cls = v >> 3;
+        else {
+          const int dx = t == 1 ? 0 : (t == 3 ? -1 : 1), dy = t == 0 ? 0 : 1;   // second neighbour at (+dx, +dy), first at (-dx, -dy)
+          const int n0 = s[(y - dy) * stride + x - dx], n1 = s[(y + dy) * stride + x + dx];
+          cls = 2 + ((v > n0) - (v < n0)) + ((v > n1) - (v < n1));
+        }
+        out = min(255, max(0, v + s_off[cls]));
+      }
+    }
+    r[y * stride + x] = (int16_t)out;
+  }
+}
+
 }  // namespace hevcdl

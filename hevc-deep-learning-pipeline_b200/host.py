@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_sao_apply", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream",
@@ -54,6 +54,7 @@ TU_RDOQ_DTYPE = np.dtype([("lambda", "<f8"), ("est_index", "<u4"), ("channel", "
 EST_INTS = 224
 PRED_REQ_DTYPE = np.dtype([("log2_size", "u1"), ("mode", "u1"), ("flags", "u1"), ("reserved", "u1"), ("line_offset", "<u4"), ("pred_offset", "<u4")])
 PRED_EDGE = 1
+SAO_PARAM_DTYPE = np.dtype([("type", "i1"), ("reserved", "i1", 3), ("offset", "i1", 32)])
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("size", "u1"), ("part", "u1"), ("ctu", "<u2")])
 
 
@@ -106,6 +107,7 @@ def load_library():
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
     L.hevcdl_sao_stats.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
+    L.hevcdl_sao_apply.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
     L.hevcdl_intra_pred.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, C.c_size_t]
     L.hevcdl_deblock_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip]
     L.hevcdl_tu_code.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
@@ -340,6 +342,20 @@ class DepthPredictor:
         self._ck(self.lib.hevcdl_sao_stats(self.h, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), W, W // 2, _ptr(r[0]), _ptr(r[1]), _ptr(r[2]), W, W // 2,
                                            W, H, _ptr(out)), "sao_stats")
         return out
+
+    def sao_apply(self, src, types, offsets):
+        """SAO application over a deblocked picture (hevcdl_sao_apply).  src: (Y, U, V) 8-bit planes; types: int8 [nctu, 3]
+        (-1 off, 0..3 edge offset, 4 band offset); offsets: int8 [nctu, 3, 32].  Returns the (Y, U, V) planes as uint8."""
+        H, W = src[0].shape
+        n = ((W + 63) // 64) * ((H + 63) // 64)
+        s = [np.ascontiguousarray(p, np.int16) for p in src]
+        r = [np.zeros_like(p) for p in s]
+        prm = np.zeros((n, 3), SAO_PARAM_DTYPE)
+        prm["type"] = np.asarray(types, np.int8).reshape(n, 3)
+        prm["offset"] = np.asarray(offsets, np.int8).reshape(n, 3, 32)
+        self._ck(self.lib.hevcdl_sao_apply(self.h, _ptr(s[0]), _ptr(s[1]), _ptr(s[2]), W, W // 2, _ptr(r[0]), _ptr(r[1]), _ptr(r[2]), W, W // 2,
+                                           W, H, _ptr(prm)), "sao_apply")
+        return [p.astype(np.uint8) for p in r]
 
     # -- measurement -------------------------------------------------------------------------
     def last_aux_ms(self):

@@ -245,6 +245,23 @@ int hevcdl_sao_stats(hevcdl_ctx *ctx, const int16_t *org_y, const int16_t *org_u
                      int org_stride_c, const int16_t *rec_y, const int16_t *rec_u, const int16_t *rec_v, int rec_stride_y,
                      int rec_stride_c, int width, int height, int64_t *stats);
 
+/* SAO application over one picture: TComSampleAdaptiveOffset::offsetCTU for every CTU (HM TLibCommon/TComSampleAdaptiveOffset.cpp:
+ * 554-611 -> offsetBlock :313-552) as the encoder runs it from decideBlkParams (TLibEncoder/TEncSampleAdaptiveOffset.cpp:894) once
+ * a CTU's parameters are decided and its merge candidates resolved (reconstructBlkSAOParam).  src_*: the deblocked picture (HM's
+ * m_tempPicYuv copy), res_*: receives every sample of the picture -- src + offset[class] clipped to 8 bits where the CTU's SAO
+ * type applies, the deblocked value elsewhere.  params: for every 64x64 CTU in raster order and component (Y, Cb, Cr) the type
+ * (-1 off; 0..3 edge offset 0 / 90 / 135 / 45 degrees; 4 band offset) and SAOOffset::offset[32] (entries 0..4 = the five edge
+ * classes, 0..31 = the bands).  Restrictions = the reference's operating point: one slice, no tiles, 8-bit 4:2:0.  Bit-exact.
+ * Synchronous. */
+typedef struct hevcdl_sao_param {
+  int8_t type;
+  int8_t reserved[3];
+  int8_t offset[32];
+} hevcdl_sao_param;
+int hevcdl_sao_apply(hevcdl_ctx *ctx, const int16_t *src_y, const int16_t *src_u, const int16_t *src_v, int src_stride_y,
+                     int src_stride_c, int16_t *res_y, int16_t *res_u, int16_t *res_v, int res_stride_y, int res_stride_c, int width,
+                     int height, const hevcdl_sao_param *params);
+
 /* Page-locked host memory for frame planes handed over with hevcdl_cfg.pinned_input = 1 (any page-locked memory will do;
  * this is the allocator for callers without a CUDA runtime of their own).  write_combined != 0: cudaHostAllocWriteCombined --
  * not snooped during the transfer, which some hosts move faster over PCIe; the CPU should only WRITE such memory (reads

@@ -283,3 +283,20 @@ def sao_stats(org, src):
     lib().oracle_sao_stats(P(*[p.ctypes.data_as(C.POINTER(C.c_int16)) for p in o]), P(*[p.ctypes.data_as(C.POINTER(C.c_int16)) for p in s]),
                            W, H, out.ctypes.data_as(C.POINTER(C.c_int64)))
     return out
+
+
+def sao_apply(src, types, offsets):
+    """SAO application over a picture (oracle/sao_oracle.c: oracle_sao_apply).  src: (Y, U, V) deblocked 8-bit planes; types:
+    int8 [nctu, 3] (-1 off, 0..3 edge offset 0 / 90 / 135 / 45, 4 band offset); offsets: int8 [nctu, 3, 32].  Returns the
+    (Y, U, V) planes with the offsets applied, as uint8."""
+    H, W = src[0].shape
+    s = [np.ascontiguousarray(p, np.int16) for p in src]
+    r = [np.zeros_like(p) for p in s]
+    t = np.ascontiguousarray(types, np.int8)
+    o = np.ascontiguousarray(offsets, np.int8)
+    n = ((W + 63) // 64) * ((H + 63) // 64)
+    assert t.shape == (n, 3) and o.shape == (n, 3, 32)
+    P = C.POINTER(C.c_int16) * 3
+    lib().oracle_sao_apply(P(*[p.ctypes.data_as(C.POINTER(C.c_int16)) for p in s]), P(*[p.ctypes.data_as(C.POINTER(C.c_int16)) for p in r]),
+                           W, H, t.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+    return [p.astype(np.uint8) for p in r]

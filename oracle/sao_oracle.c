@@ -55,3 +55,57 @@ void oracle_sao_stats(const int16_t *org[3], const int16_t *src[3], int W, int H
     }
   }
 }
+
+/* SAO application: TComSampleAdaptiveOffset::offsetCTU / offsetBlock (HM_dl/source/Lib/TLibCommon/TComSampleAdaptiveOffset.cpp:
+ * 554-611, 313-552) for every CTU of a picture, as the encoder runs it from decideBlkParams (TEncSampleAdaptiveOffset.cpp:894)
+ * with the merge candidates already resolved (reconstructBlkSAOParam): res = src + offset[class], clipped to 8 bits, for the
+ * samples the type may touch -- edge types leave out samples whose neighbour lies outside the picture (one slice, no tiles:
+ * a neighbouring CTU is available iff it exists), with the reference's special first / last line ranges of the diagonal
+ * types; every other sample keeps its deblocked value.  All classification reads `src`, never `res`, so CTUs are independent.
+ * type[nctu*3]: -1 = off, 0..3 edge offset 0 / 90 / 135 / 45 degrees, 4 band offset; offset[nctu*3][32]: entries 0..4 for the
+ * edge classes (index 2 + sgn + sgn), 0..31 for the bands.  Pinned by tests/golden/sao_apply.npz (TAppEncoder_saoapplytrace). */
+static int clip8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+void oracle_sao_apply(const int16_t *src[3], int16_t *res[3], int W, int H, const int8_t *type, const int8_t *offset) {
+  const int cw = (W + 63) / 64, ch = (H + 63) / 64;
+  for (int c = 0; c < 3; c++) memcpy(res[c], src[c], sizeof(int16_t) * (size_t)(W >> (c ? 1 : 0)) * (H >> (c ? 1 : 0)));
+  for (int a = 0; a < cw * ch; a++) {
+    const int xp = (a % cw) * 64, yp = (a / cw) * 64;
+    const int hl = yp + 64 > H ? H - yp : 64, wl = xp + 64 > W ? W - xp : 64;
+    const int L = xp > 0, A = yp > 0, R = xp + 64 < W, B = yp + 64 < H, AL = L && A, AR = A && R, BL = B && L, BR = B && R;
+    for (int c = 0; c < 3; c++) {
+      const int t = type[a * 3 + c];
+      if (t < 0) continue;
+      const int8_t *of = offset + (size_t)(a * 3 + c) * 32;
+      const int sh = c ? 1 : 0, stride = W >> sh, width = wl >> sh, height = hl >> sh;
+      const int16_t *s = src[c] + (size_t)(yp >> sh) * stride + (xp >> sh);
+      int16_t *r = res[c] + (size_t)(yp >> sh) * stride + (xp >> sh);
+      const int sx = L ? 0 : 1, ex = R ? width : width - 1;
+      for (int y = 0; y < height; y++) {
+        int xa, xb;
+        if (t == 4) { xa = 0; xb = width; }
+        else if (t == 0) { xa = sx; xb = ex; }
+        else if (t == 1) { xa = 0; xb = (y < (A ? 0 : 1) || y >= (B ? height : height - 1)) ? 0 : width; }
+        else if (t == 2) {
+          if (y == 0) { xa = AL ? 0 : 1; xb = A ? ex : 1; }
+          else if (y == height - 1) { xa = B ? sx : width - 1; xb = BR ? width : width - 1; }
+          else { xa = sx; xb = ex; }
+        } else {
+          if (y == 0) { xa = A ? sx : width - 1; xb = AR ? width : width - 1; }
+          else if (y == height - 1) { xa = BL ? 0 : 1; xb = B ? ex : 1; }
+          else { xa = sx; xb = ex; }
+        }
+        for (int x = xa; x < xb; x++) {
+          const int v = s[y * stride + x];
+          int cls;
+          if (t == 0) cls = 2 + sgn(v - s[y * stride + x - 1]) + sgn(v - s[y * stride + x + 1]);
+          else if (t == 1) cls = 2 + sgn(v - s[(y - 1) * stride + x]) + sgn(v - s[(y + 1) * stride + x]);
+          else if (t == 2) cls = 2 + sgn(v - s[(y - 1) * stride + x - 1]) + sgn(v - s[(y + 1) * stride + x + 1]);
+          else if (t == 3) cls = 2 + sgn(v - s[(y - 1) * stride + x + 1]) + sgn(v - s[(y + 1) * stride + x - 1]);
+          else cls = v >> 3;
+          r[y * stride + x] = (int16_t)clip8(v + of[cls]);
+        }
+      }
+    }
+  }
+}

@@ -1,6 +1,7 @@
 """Deblocking filter on the device (hevcdl_deblock_frame, csrc/dbf.cuh) through the C-ABI: identical to the reference's own
 loopFilterPic on the dumped pictures (tests/golden/dbf_pictures.npz), to the oracle on synthetic pictures of other sizes, QPs
-and offsets, and -- inside the real encoder (HEVCDL_DBF=1) -- byte-identical bitstreams.  The same three levels for the SAO statistics pass (hevcdl_sao_stats, csrc/sao.cuh, HEVCDL_SAO=1)."""
+and offsets, and -- inside the real encoder (HEVCDL_DBF=1) -- byte-identical bitstreams.  The same three levels for the two SAO passes (hevcdl_sao_stats, hevcdl_sao_apply, csrc/sao.cuh,
+HEVCDL_SAO=1)."""
 import os
 import re
 
@@ -8,7 +9,7 @@ import numpy as np
 import pytest
 
 import hm_util
-from test_oracle_dbf import cases, sao_cases
+from test_oracle_dbf import cases, sao_apply_cases, sao_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -119,8 +120,10 @@ def test_sao_statistics_vs_oracle_synthetic(dp, oracle):
 @pytest.mark.skipif(not hm_util.have("ref", "dec", "hevcdl"), reason="reference / drop-in encoder binaries not built")
 @pytest.mark.parametrize("w,h,qp", [(192, 128, 37), (416, 240, 32)])
 def test_dropin_sao_statistics_on_the_device_keep_the_bitstream(tmp_path, built, host, pkg, w, h, qp):
-    """HEVCDL_SAO=1: TEncSampleAdaptiveOffset::getStatistics of every picture runs on the B200; the offsets SAO signals are decided
-    from these sums, so a differing count or difference would change the bitstream: it must stay byte-identical."""
+    """HEVCDL_SAO=1: TEncSampleAdaptiveOffset::getStatistics of every picture and the application of the decided offsets
+    (TComSampleAdaptiveOffset::offsetCTU, one deferred pass per picture) run on the B200; the offsets SAO signals are decided from
+    these sums and the decoded-picture hash is taken from the offset picture, so any differing count, difference or sample would
+    change the bitstream: it must stay byte-identical."""
     frames = [pkg.synth.synth_frame(w, h, 120 + i) for i in range(2)]
     a, b = tmp_path / "ref", tmp_path / "dl"
     a.mkdir(); b.mkdir()
@@ -135,6 +138,7 @@ def test_dropin_sao_statistics_on_the_device_keep_the_bitstream(tmp_path, built,
                         env={"HEVCDL_PRECISION": "fp32", "HEVCDL_SAO": "1", "HEVCDL_DBF": "1", "HEVCDL_VERBOSE": "1"})
     assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-600:])
     assert re.search(r"SAO statistics passes on the device 2 / by the reference's code 0", rb["stderr"]), rb["stderr"][-600:]
+    assert re.search(r"SAO offsets applied on the device for 2 pictures / by the reference's code for 0", rb["stderr"]), rb["stderr"][-600:]
     assert ra["sha1"] == rb["sha1"]
     ok, out = hm_util.decode_ok(str(b))
     assert ok, out[-400:]
@@ -177,3 +181,32 @@ def test_inloop_passes_at_baseline_sizes(dp, oracle, W, H):
                 dif[cy, cx] = d[cy * s:y1, cx * s:x1].sum()
         assert (st[:, c, 4, 1, :].sum(axis=1).reshape(chh, cw) == cnt).all(), c
         assert (st[:, c, 4, 0, :].sum(axis=1).reshape(chh, cw) == dif).all(), c
+
+
+def test_sao_application_vs_the_references_own(dp):
+    n = 0
+    for k, src, t, o, res in sao_apply_cases():
+        got = dp.sao_apply(src, t, o)
+        for a, b, name in zip(got, res, "YUV"):
+            assert (a == b).all(), (k, name, int((a != b).sum()))
+        n += 1
+    assert n == 3
+
+
+def test_sao_application_vs_oracle_synthetic(dp, oracle):
+    """Random types and offsets (-7..7) per CTU and component on pictures from one partial CTU to 1920x1080 and 3840x2160:
+    every type meets every border configuration; all-off parameters return the picture unchanged."""
+    rng = np.random.default_rng(12)
+    for (W, H) in ((8, 8), (64, 64), (72, 40), (200, 136), (416, 240), (1920, 1080), (3840, 2160)):
+        src = [rng.integers(0, 256, s).astype(np.uint8) if W < 1000 else
+               np.clip(np.kron(rng.integers(0, 256, ((s[0] + 3) // 4, (s[1] + 3) // 4)), np.ones((4, 4)))[:s[0], :s[1]] + rng.integers(-9, 10, s), 0, 255).astype(np.uint8)
+               for s in ((H, W), (H // 2, W // 2), (H // 2, W // 2))]
+        n = ((W + 63) // 64) * ((H + 63) // 64)
+        t = rng.integers(-1, 5, (n, 3)).astype(np.int8)
+        o = rng.integers(-7, 8, (n, 3, 32)).astype(np.int8)
+        want = oracle.sao_apply(src, t, o)
+        got = dp.sao_apply(src, t, o)
+        for a, b, name in zip(got, want, "YUV"):
+            assert (a == b).all(), (W, H, name, int((a != b).sum()))
+        same = dp.sao_apply(src, np.full((n, 3), -1, np.int8), o)
+        assert all((a == b).all() for a, b in zip(same, src))

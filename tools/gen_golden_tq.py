@@ -5,6 +5,7 @@ container (needs /root/reference and `make -C oracle ref`); the fixtures travel,
   tests/golden/tq_transform_ref.npz   random and extreme blocks through the reference's OWN xTrMxN / xITrMxN
                                       (oracle/_ref/libtqref.so = tq_ref_harness.cpp linked with libhmref.a), every size + DST
   tests/golden/pred_trace_192x128_qp32.npz  reference samples + predicted blocks of the reference's own predIntraAng (luma and chroma)
+  tests/golden/sao_apply.npz          deblocked pictures + per-CTU SAO parameters + the pictures after the reference's own offsetCTU
   tests/golden/sao_stats.npz          original + deblocked pictures and the statistics the reference's own SAO getStatistics made of them
   tests/golden/dbf_pictures.npz       reconstructed pictures before / after the reference's own deblocking filter + its TU / QP maps
   tests/golden/tq_rdoq_192x128_qp32.npz    calls of the reference's xRateDistOptQuant (inputs incl. the CABAC bit-estimate
@@ -264,6 +265,42 @@ def sao_vectors():
     print("sao_stats.npz:", os.path.getsize(os.path.join(GOLD, "sao_stats.npz")), "bytes")
 
 
+def saoapply_vectors():
+    """tests/golden/sao_apply.npz: the deblocked picture, the resolved per-CTU SAO parameters and the picture after the reference's
+    own TComSampleAdaptiveOffset::offsetCTU ran over every CTU (oracle/_ref/TAppEncoder_saoapplytrace, oracle/saoapply_dump.h):
+    the 192x128 fixture frame at QP 37 and the 416x240 frame (partial CTUs on both edges) at QP 32 and 22 (the latter uses all five SAO types)."""
+    g = np.load(os.path.join(GOLD, "rmd_trace_192x128_qp32.npz"))
+    c = np.load(os.path.join(GOLD, "cnn_labels_416x240.npz"))
+    out, k = {}, 0
+    for (Y, U, V, labels, qp) in ((g["Y"], g["U"], g["V"], g["labels"], 37), (c["Y"], c["U"], c["V"], c["labels"], 32), (c["Y"], c["U"], c["V"], c["labels"], 22)):
+        H, W = Y.shape
+        with tempfile.TemporaryDirectory() as td:
+            hm_util.write_yuv(os.path.join(td, "in.yuv"), [(Y, U, V)])
+            hm_util.write_pred(os.path.join(td, "pred"), 0, labels)
+            cmd = [os.path.join(REFDIR, "TAppEncoder_saoapplytrace"), "-c", hm_util.CFG, "-i", "in.yuv", "-wdt", str(W), "-hgt", str(H), "-fr", "30",
+                   "-f", "1", "-q", str(qp), "-b", "t.bin", "--InputBitDepth=8", "--InputChromaFormat=420", "--Level=6.2"]
+            subprocess.check_call(cmd, cwd=td, env=dict(os.environ, HEVCDL_SAOAPPLY_DUMP=os.path.join(td, "sao.bin")), stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            raw = open(os.path.join(td, "sao.bin"), "rb").read()
+        hdr = np.frombuffer(raw, np.int32, 8, 0)
+        assert hdr[0] == 0x53414F41 and hdr[1] == W and hdr[2] == H
+        n, off = int(hdr[3]), 32
+        for name, cnt in (("Y", W * H), ("U", W * H // 4), ("V", W * H // 4)):
+            out["src%s_%d" % (name, k)] = np.frombuffer(raw, np.int16, cnt, off).astype(np.uint8); off += 2 * cnt
+        out["type_%d" % k] = np.frombuffer(raw, np.int8, n * 3, off).reshape(n, 3); off += n * 3
+        out["offset_%d" % k] = np.frombuffer(raw, np.int8, n * 3 * 32, off).reshape(n, 3, 32); off += n * 3 * 32
+        for name, cnt in (("Y", W * H), ("U", W * H // 4), ("V", W * H // 4)):
+            out["res%s_%d" % (name, k)] = np.frombuffer(raw, np.int16, cnt, off).astype(np.uint8); off += 2 * cnt
+        assert off == len(raw)
+        out["dims_%d" % k] = np.array([W, H, qp])
+        ch = sum(int((out["src%s_%d" % (nm, k)] != out["res%s_%d" % (nm, k)]).sum()) for nm in "YUV")
+        print("case", k, W, H, "qp", qp, "types used:", sorted(set(out["type_%d" % k].ravel().tolist())), "samples changed:", ch)
+        k += 1
+    out["ncases"] = np.array(k)
+    np.savez_compressed(os.path.join(GOLD, "sao_apply.npz"), **out)
+    print("sao_apply.npz:", os.path.getsize(os.path.join(GOLD, "sao_apply.npz")), "bytes")
+
+
 def pred_vectors():
     """tests/golden/pred_trace_192x128_qp32.npz: reference samples and output of the reference's own TComPrediction::predIntraAng
     (oracle/_ref/TAppEncoder_predtrace, oracle/pred_dump.h) during an encode of the 192x128 fixture frame: up to 6 calls per
@@ -302,3 +339,4 @@ if __name__ == "__main__":
     dbf_vectors()
     sao_vectors()
     pred_vectors()
+    saoapply_vectors()
