@@ -110,6 +110,27 @@ def main():
             want = oracle.sao_stats(org, src_)
             d["cpu_port_ms"] = (time.perf_counter() - t) * 1e3
             d["identical"] = bool((got == want).all())
+        # ---- SAO application ---------------------------------------------------------------------------
+        nctu = ((W + 63) // 64) * ((H8 + 63) // 64)
+        ty = rng.integers(-1, 5, (nctu, 3)).astype(np.int8)
+        of = rng.integers(-7, 8, (nctu, 3, 32)).astype(np.int8)
+        got, wall, dev = timed(dp, lambda: dp.sao_apply(src_, ty, of), a.reps)
+        byts = 6 * W * H8            # one int16 picture read, one written
+        d = out["sao_apply"] = {"device_ms": dev, "call_ms": wall, "algorithmic_mb": byts / 1e6, "achieved_gbs": byts / dev / 1e6,
+                                "hbm_frac": byts / dev / 1e6 / hbm}
+        if not a.no_cpu:
+            t = time.perf_counter()
+            want = oracle.sao_apply(src_, ty, of)
+            d["cpu_port_ms"] = (time.perf_counter() - t) * 1e3
+            d["identical"] = bool(all((x == y).all() for x, y in zip(got, want)))
+        # ---- intra predictor: every 16x16 block of the luma picture x 35 modes -----------------------------
+        nblk = (W // 16) * (H8 // 16)
+        lines = [rng.integers(0, 256, 65).astype(np.int16) for _ in range(64)]
+        ll = [lines[i % 64] for i in range(nblk * 35)]
+        mm = [i % 35 for i in range(nblk * 35)]
+        got, wall, dev = timed(dp, lambda: dp.intra_pred(ll, mm, [True] * len(ll)), 3)
+        out["intra_pred_16x16_x35"] = {"blocks": len(ll), "device_ms": dev, "call_ms_incl_python_marshalling": wall,
+                                       "mblocks_per_s": len(ll) / dev / 1e3, "gsamples_per_s": len(ll) * 256 / dev / 1e6}
         # ---- transform-unit core: the luma area of one picture, a quarter of it per TU size -------------
         blocks, qps, flags, rq, ests = [], [], [], [], []
         hdr = g["hdr"]
@@ -148,8 +169,8 @@ def main():
                 tr = (time.perf_counter() - t) / len(sub)
                 cpu[str(n)] = {"flat_us_per_tu": tf * 1e6, "with_rdoq_us_per_tu": tr * 1e6}
             cnts = {n: W * H8 // 4 // (n * n) for n in (4, 8, 16, 32)}
-            out["tu_code_flat"]["cpu_port_ms_extrapolated"] = sum(cnts[n] * cpu[str(n)]["flat_us_per_tu"] for n in cnts) / 1e3
-            out["tu_code_rdoq"]["cpu_port_ms_extrapolated"] = sum(cnts[n] * cpu[str(n)]["with_rdoq_us_per_tu"] for n in cnts) / 1e3
+            out["tu_code_flat"]["cpu_port_ms_extrapolated_incl_ctypes_call_overhead"] = sum(cnts[n] * cpu[str(n)]["flat_us_per_tu"] for n in cnts) / 1e3
+            out["tu_code_rdoq"]["cpu_port_ms_extrapolated_incl_ctypes_call_overhead"] = sum(cnts[n] * cpu[str(n)]["with_rdoq_us_per_tu"] for n in cnts) / 1e3
             out["tu_cpu_port_per_size"] = cpu
     dp.close()
     s = json.dumps(rep, indent=1)
