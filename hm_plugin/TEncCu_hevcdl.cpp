@@ -46,6 +46,7 @@
 //                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
 //                     2 = exact mode: per PU, HM's reconstructed reference samples go to hevcdl_rmd_exact (bit-exact,
 //                     byte-identical bitstream, one synchronous call per PU) (default 0: HM's own pass)
+//   HEVCDL_EARLY_CREATE 0 = create the device context at the first CTU instead of on a background thread at program load
 // There is no fallback: any library failure aborts the encoder with the library's error text.
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -97,6 +98,7 @@ uint64_t hash_pel_plane(uint64_t h, const Pel *p, int stride, int w, int hgt, st
 struct InputSpec {
   std::string file;
   long skip = 0, frames = -1, tsr = 1;
+  int width = 0, height = 0;
   bool eight_bit = true;
   static std::string value_of(const std::string &line, const char *key) {      // "Key : value   # comment"
     size_t i = 0;
@@ -119,11 +121,13 @@ struct InputSpec {
     else if (!strcmp(key, "FramesToBeEncoded")) frames = atol(v.c_str());
     else if (!strcmp(key, "TemporalSubsampleRatio")) tsr = atol(v.c_str());
     else if (!strcmp(key, "InputBitDepth")) eight_bit = atol(v.c_str()) == 8 || atol(v.c_str()) == 0;
+    else if (!strcmp(key, "SourceWidth")) width = atoi(v.c_str());
+    else if (!strcmp(key, "SourceHeight")) height = atoi(v.c_str());
   }
   void parse_cfg(const std::string &path) {
     std::ifstream f(path);
     std::string line;
-    static const char *keys[] = {"InputFile", "FrameSkip", "FramesToBeEncoded", "TemporalSubsampleRatio", "InputBitDepth"};
+    static const char *keys[] = {"InputFile", "FrameSkip", "FramesToBeEncoded", "TemporalSubsampleRatio", "InputBitDepth", "SourceWidth", "SourceHeight"};
     while (std::getline(f, line))
       for (const char *k : keys) take(k, value_of(line, k));
   }
@@ -133,7 +137,8 @@ struct InputSpec {
     std::string a;
     while (std::getline(f, a, '\0')) av.push_back(a);
     static const struct { const char *sh, *lg; } opt[] = {{"-i", "InputFile"}, {"-fs", "FrameSkip"}, {"-f", "FramesToBeEncoded"},
-                                                           {"-ts", "TemporalSubsampleRatio"}, {nullptr, "InputBitDepth"}};
+                                                           {"-ts", "TemporalSubsampleRatio"}, {nullptr, "InputBitDepth"},
+                                                           {"-wdt", "SourceWidth"}, {"-hgt", "SourceHeight"}};
     for (size_t i = 1; i < av.size(); i++) {       // later options override earlier ones, as in the reference's parser
       if (av[i] == "-c" && i + 1 < av.size()) { parse_cfg(av[++i]); continue; }
       for (const auto &o : opt) {
@@ -256,7 +261,7 @@ struct HevcdlSession {
   long submitted_hi = -1;       // highest frame id handed to the device from the file
   std::vector<std::pair<long, uint64_t>> ahead;   // (frame id, hash of the file's planes) of frames submitted from the file
   unsigned long long la_hits = 0, la_direct = 0, la_mismatch = 0;
-  double t_create = 0, t_wait_first = 0, t_wait_later = 0;   // seconds: hevcdl_create; blocked in the first label query of frame 0 / of later frames
+  double t_create = 0, t_create_total = 0, t_wait_first = 0, t_wait_later = 0;   // seconds: encoder thread blocked for hevcdl_create / its whole duration; blocked in the first label query of frame 0 / of later frames
   static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   std::vector<uint8_t> rowbuf;
 
@@ -265,30 +270,25 @@ struct HevcdlSession {
     exit(EXIT_FAILURE);
   }
 
-  void open(int w, int h) {
+  // Everything hevcdl_create needs, from the environment (the signature of compressCtu leaves no room for it)
+  static int env_lookahead() {
+    const char *e = getenv("HEVCDL_LOOKAHEAD");
+    const int k = e ? atoi(e) : 3;
+    return k < 0 ? 0 : (k > 16 ? 16 : k);
+  }
+  static hevcdl_cfg make_cfg(int w, int h) {
     hevcdl_cfg cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.abi_version = HEVCDL_ABI_VERSION;
     const char *e;
     cfg.device = (e = getenv("HEVCDL_DEVICE")) ? atoi(e) : 0;
     cfg.width = w; cfg.height = h;
-    lookahead = (e = getenv("HEVCDL_LOOKAHEAD")) ? atoi(e) : 3;
-    if (lookahead < 0) lookahead = 0;
-    if (lookahead > 16) lookahead = 16;
-    if (lookahead) {
-      InputSpec in;
-      in.parse_cmdline();
-      if (!reader.open(in, w, h, lookahead + 1)) lookahead = 0;    // no usable input file: behave as without lookahead
-    }
-    cfg.slots = 2 + lookahead;
+    cfg.slots = 2 + env_lookahead();
     cfg.batch = 1;
     cfg.precision = ((e = getenv("HEVCDL_PRECISION")) && !strcmp(e, "bf16")) ? HEVCDL_PREC_BF16_TC : HEVCDL_PREC_FP32;
     const int rmd_mode = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
     cfg.rmd = rmd_mode == 1;
     cfg.outputs = rmd_mode == 1 ? HEVCDL_OUT_SATD : 0;   // the first-pass hook re-ranks with HM's own mode bits: it needs the SATD table
-    gpu_rmd = rmd_mode == 1;
-    exact_rmd = rmd_mode == 2;
-    gpu_tq = (e = getenv("HEVCDL_TQ")) && atoi(e) == 1;
     cfg.boundary_fix = (e = getenv("HEVCDL_BOUNDARY_FIX")) ? atoi(e) : 0;
     // weights: HEVCDL_WEIGHTS, else the path baked in at build time, else <dir of this executable>/../../weights/
     static char relpath[4096];
@@ -301,10 +301,63 @@ struct HevcdlSession {
         if (slash) { strcpy(slash, "/../../weights/hevc_encoder_model.hdlw"); cfg.weights_path = relpath; }
       }
     }
+    return cfg;
+  }
+
+  // hevcdl_create costs 0.3-4 s (CUDA context creation) and compressCtu is first called only after HM has parsed its
+  // configuration, allocated its pictures and read the first frame: a thread started when the program is loaded creates the
+  // context meanwhile, from the picture size on the encoder's own command line / -c files (HEVCDL_EARLY_CREATE=0: off).
+  struct Early {
+    std::thread th;
+    hevcdl_cfg cfg;
+    hevcdl_ctx *ctx = nullptr;
+    int rc = 0;
+    double seconds = 0;
+  };
+  static Early *&early() { static Early *e = nullptr; return e; }
+  static void start_early() {
+    const char *e = getenv("HEVCDL_EARLY_CREATE");
+    if (e && atoi(e) == 0) return;
+    InputSpec in;
+    in.parse_cmdline();
+    if (in.width < 8 || in.height < 8) return;
+    Early *y = new Early;
+    y->cfg = make_cfg(in.width, in.height);
+    y->th = std::thread([y] {
+      const double t0 = now();
+      y->rc = hevcdl_create(&y->cfg, &y->ctx);
+      y->seconds = now() - t0;
+    });
+    early() = y;
+  }
+
+  void open(int w, int h) {
+    const char *e;
+    lookahead = env_lookahead();
+    if (lookahead) {
+      InputSpec in;
+      in.parse_cmdline();
+      if (!reader.open(in, w, h, lookahead + 1)) lookahead = 0;    // no usable input file: behave as without lookahead
+    }
+    const int rmd_mode = (e = getenv("HEVCDL_RMD")) ? atoi(e) : 0;
+    gpu_rmd = rmd_mode == 1;
+    exact_rmd = rmd_mode == 2;
+    gpu_tq = (e = getenv("HEVCDL_TQ")) && atoi(e) == 1;
     const double t0 = now();
-    const int rc = hevcdl_create(&cfg, &ctx);
+    if (Early *y = early()) {                      // created in the background since program load: wait for the rest of it
+      y->th.join();
+      if (y->rc == 0 && y->cfg.width == w && y->cfg.height == h) { ctx = y->ctx; t_create_total = y->seconds; }
+      else if (y->ctx) hevcdl_destroy(y->ctx);     // the command line did not say what HM ended up encoding
+      delete y;
+      early() = nullptr;
+    }
+    if (!ctx) {
+      hevcdl_cfg cfg = make_cfg(w, h);
+      const int rc = hevcdl_create(&cfg, &ctx);
+      if (rc) die("hevcdl_create", rc, nullptr);
+      t_create_total = now() - t0;
+    }
     t_create = now() - t0;
-    if (rc) die("hevcdl_create", rc, nullptr);
     width = w; height = h;
   }
 
@@ -413,8 +466,9 @@ struct HevcdlSession {
         fprintf(stderr, "hevcdl: SAO offsets applied on the device for %llu pictures / by the reference's code for %llu\n", saoapply_device, saoapply_host);
         fprintf(stderr, "hevcdl: lookahead %d: %llu frames were on the device before HM asked, %llu uploaded from HM's planes, %llu mismatches\n",
                 lookahead, la_hits, la_direct, la_mismatch);
-        fprintf(stderr, "hevcdl: encoder thread blocked %.3f s in hevcdl_create (CUDA context + weights + buffers), %.4f s waiting for the "
-                        "labels of the first frame, %.4f s for all later frames together\n", t_create, t_wait_first, t_wait_later);
+        fprintf(stderr, "hevcdl: encoder thread blocked %.3f s for hevcdl_create (CUDA context + weights + buffers: %.3f s, started at program "
+                        "load), %.4f s waiting for the labels of the first frame, %.4f s for all later frames together\n",
+                t_create, t_create_total, t_wait_first, t_wait_later);
         hevcdl_stats_t st;
         if (!hevcdl_get_stats(ctx, &st))
           fprintf(stderr, "hevcdl: %llu frames, %llu CTUs, CNN %.3f ms, RMD %.3f ms device time, %llu kernel launches, "
@@ -428,6 +482,7 @@ struct HevcdlSession {
 };
 
 HevcdlSession g_session;   // one encoder thread, one TEncCu instance (TEncTop.h:93): a process-wide session is enough
+struct HevcdlEarlyStart { HevcdlEarlyStart() { HevcdlSession::start_early(); } } g_early_start;   // before main(): see HevcdlSession::Early
 
 }  // namespace
 
