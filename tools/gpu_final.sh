@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU box: whole GPU test suite + smoke, compute-sanitizer over the small and the 1080p workloads (all kernels incl. TU core
-# with RDOQ, deblocking, SAO statistics), default bench of both arms.   usage: tools/gpu_final.sh <tag>
+# with RDOQ, intra predictor, deblocking, SAO statistics + application), default bench of both arms.   usage: tools/gpu_final.sh <tag>
 TAG=${1:-r02v}
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_gpu_tests.log

@@ -41,5 +41,14 @@ tu = np.kron(rng.integers(3, 6, (H // 32 + 1, W // 32 + 1)), np.ones((8, 8), np.
 rec = dp.deblock_frame(Y, U, V, tu, np.full(tu.shape, 34, np.int8))
 st = dp.sao_stats((Y, U, V), rec)
 tot += int(rec[0].sum() & 0xFFFF) + int(st[:, :, :, 1].sum() & 0xFFFF)
+nctu = ((W + 63) // 64) * ((H + 63) // 64)
+out = dp.sao_apply(rec, rng.integers(-1, 5, (nctu, 3)).astype(np.int8), rng.integers(-7, 8, (nctu, 3, 32)).astype(np.int8))
+tot += int(out[0].sum() & 0xFFFF)
+# the intra predictor: every size x mode, with and without the luma edge filters
+lines, modes, edge = [], [], []
+for n in (4, 8, 16, 32, 64):
+    for m in range(35):
+        lines.append(rng.integers(0, 256, 4 * n + 1).astype(np.int16)); modes.append(m); edge.append(bool(m & 1))
+tot += sum(int(b.sum()) for b in dp.intra_pred(lines, modes, edge)) & 0xFFFF
 dp.close()
 print("sanitize_frame ok: checksum", tot)
