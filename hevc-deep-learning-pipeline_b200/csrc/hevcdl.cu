@@ -93,10 +93,14 @@ struct hevcdl_ctx {
   hevcdl_stats_t stats{};
   // device time of the most recent hevcdl_tu_code* / hevcdl_deblock_frame / hevcdl_sao_stats kernels (hevcdl_last_aux_ms)
   cudaEvent_t evAux0 = nullptr, evAux1 = nullptr;
-  // scratch for hevcdl_deblock_frame
+  // scratch of the in-loop entry points (deblocking, SAO statistics / application)
   void *dDbf = nullptr;
   void *hDbf = nullptr;
   size_t dbfCap = 0;
+  // the deblocked picture hevcdl_inloop_frame left at the start of dDbf (int16 Y, Cb, Cr, dense): source of a later
+  // hevcdl_sao_apply(src = NULL); any other call that uses the scratch invalidates it
+  bool loopValid = false;
+  int loopW = 0, loopH = 0;
   // scratch for hevcdl_tu_code
   void *dRdoq = nullptr;               // RdoqScratch per resident warp of k_tu_code (RDOQ launches only)
   int rdoqWarps = 0;
@@ -829,85 +833,132 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
   return HEVCDL_OK;
 }
 
-int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int sc, int W, int H, const uint8_t *tu_log2, const int8_t *qp,
-                         int beta_off, int tc_off, int cb_off, int cr_off) {
+namespace {
+// grow-only scratch of the in-loop entry points; keep > 0: the first `keep` bytes (the resident deblocked picture) survive a growth
+int dbf_reserve(hevcdl_ctx *ctx, size_t total, size_t keep) {
+  if (total <= ctx->dbfCap) return HEVCDL_OK;
+  void *nd = nullptr;
+  CK(cudaMalloc(&nd, total));
+  if (keep && ctx->dDbf) {
+    CK(cudaMemcpyAsync(nd, ctx->dDbf, keep, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(ctx->dDbf);
+  ctx->dDbf = nd;
+  if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
+  ctx->dbfCap = 0;
+  CK(cudaMallocHost(&ctx->hDbf, total));
+  ctx->dbfCap = total;
+  return HEVCDL_OK;
+}
+
+// deblocking (+ optionally the SAO statistics of the deblocked picture against `org`) with one upload and one download;
+// the deblocked picture stays at the start of the scratch
+int inloop_impl(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int sc, int W, int H, const uint8_t *tu_log2, const int8_t *qp,
+                int beta_off, int tc_off, int cb_off, int cr_off, const int16_t *oy, const int16_t *ou, const int16_t *ov, int osy, int osc,
+                int64_t *stats) {
   if (!ctx || !y || !u || !v || !tu_log2 || !qp || W < 8 || H < 8 || (W & 7) || (H & 7) || W > 8192 || H > 8192 || sy < W || sc < W / 2 ||
       beta_off < -6 || beta_off > 6 || tc_off < -6 || tc_off > 6 || cb_off < -12 || cb_off > 12 || cr_off < -12 || cr_off > 12)
     return HEVCDL_E_INVAL;
+  const bool with_stats = stats != nullptr;
+  if (with_stats && (!oy || !ou || !ov || osy < W || osc < W / 2)) return HEVCDL_E_INVAL;
   const size_t nu = (size_t)(W / 4) * (H / 4);
   for (size_t i = 0; i < nu; i++)
     if (tu_log2[i] < 2 || tu_log2[i] > 5 || qp[i] < 0 || qp[i] > 51) { ctx->err = "hevcdl_deblock_frame: tu_log2 in 2..5, qp in 0..51"; return HEVCDL_E_INVAL; }
   cudaSetDevice(ctx->cfg.device);
+  ctx->loopValid = false;
+  const int cw = (W + 63) / 64, chh = (H + 63) / 64, nctu = cw * chh;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_m = al(nu);
-  const size_t o_y = 0, o_u = o_y + b_y, o_v = o_u + b_c, o_tu = o_v + b_c, o_qp = o_tu + b_m, total = o_qp + b_m;
-  if (total > ctx->dbfCap) {
-    cudaFree(ctx->dDbf); ctx->dDbf = nullptr; ctx->dbfCap = 0;
-    if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
-    CK(cudaMalloc(&ctx->dDbf, total));
-    CK(cudaMallocHost(&ctx->hDbf, total));
-    ctx->dbfCap = total;
-  }
+  const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_m = al(nu), b_out = al((size_t)nctu * 3 * 5 * 64 * 8);
+  const size_t o_y = 0, o_u = o_y + b_y, o_v = o_u + b_c, o_tu = o_v + b_c, o_qp = o_tu + b_m, o_oy = o_qp + b_m, o_ou = o_oy + b_y, o_ov = o_ou + b_c,
+               o_out = o_ov + b_c, total = with_stats ? o_out + b_out : o_oy;
+  { const int rc = dbf_reserve(ctx, total, 0); if (rc) return rc; }
   uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
-  for (int r = 0; r < H; r++) memcpy(hp + o_y + (size_t)r * W * 2, y + (size_t)r * sy, (size_t)W * 2);      // dense planes on the device
-  for (int r = 0; r < H / 2; r++) {
-    memcpy(hp + o_u + (size_t)r * (W / 2) * 2, u + (size_t)r * sc, (size_t)(W / 2) * 2);
-    memcpy(hp + o_v + (size_t)r * (W / 2) * 2, v + (size_t)r * sc, (size_t)(W / 2) * 2);
-  }
+  auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {      // dense planes on the device
+    for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
+  };
+  pack(o_y, y, sy, W, H); pack(o_u, u, sc, W / 2, H / 2); pack(o_v, v, sc, W / 2, H / 2);
   memcpy(hp + o_tu, tu_log2, nu);
   memcpy(hp + o_qp, qp, nu);
+  if (with_stats) { pack(o_oy, oy, osy, W, H); pack(o_ou, ou, osc, W / 2, H / 2); pack(o_ov, ov, osc, W / 2, H / 2); }
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(dp, hp, total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp, hp, with_stats ? o_out : o_oy, cudaMemcpyHostToDevice, st));
   DbfParams P{(int16_t *)(dp + o_y), (int16_t *)(dp + o_u), (int16_t *)(dp + o_v), W, W / 2, W, H, dp + o_tu, (const int8_t *)(dp + o_qp),
               beta_off, tc_off, cb_off, cr_off};
   const int nv = (W / 8 - 1) * (H / 4), nh = (W / 4) * (H / 8 - 1);
   CK(aux_begin(ctx));
   if (nv > 0) k_dbf<true><<<(nv + 255) / 256, 256, 0, st>>>(P);
   if (nh > 0) k_dbf<false><<<(nh + 255) / 256, 256, 0, st>>>(P);
+  if (with_stats) {
+    SaoParams S{};
+    S.org[0] = (const int16_t *)(dp + o_oy); S.org[1] = (const int16_t *)(dp + o_ou); S.org[2] = (const int16_t *)(dp + o_ov);
+    S.src[0] = (const int16_t *)(dp + o_y); S.src[1] = (const int16_t *)(dp + o_u); S.src[2] = (const int16_t *)(dp + o_v);
+    S.W = W; S.H = H; S.ctu_w = cw; S.out = (long long *)(dp + o_out);
+    k_sao_stats<<<nctu * 3, 256, 0, st>>>(S);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->evAux1, st));
-  ctx->stats.kernel_launches += (nv > 0) + (nh > 0);
+  ctx->stats.kernel_launches += (nv > 0) + (nh > 0) + (with_stats ? 1 : 0);
   CK(cudaMemcpyAsync(hp, dp, o_tu, cudaMemcpyDeviceToHost, st));
+  if (with_stats) CK(cudaMemcpyAsync(hp + o_out, dp + o_out, (size_t)nctu * 3 * 5 * 64 * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  for (int r = 0; r < H; r++) memcpy(y + (size_t)r * sy, hp + o_y + (size_t)r * W * 2, (size_t)W * 2);
-  for (int r = 0; r < H / 2; r++) {
-    memcpy(u + (size_t)r * sc, hp + o_u + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
-    memcpy(v + (size_t)r * sc, hp + o_v + (size_t)r * (W / 2) * 2, (size_t)(W / 2) * 2);
-  }
+  auto unpack = [&](size_t off, int16_t *p, int stride, int w, int h) {
+    for (int r = 0; r < h; r++) memcpy(p + (size_t)r * stride, hp + off + (size_t)r * w * 2, (size_t)w * 2);
+  };
+  unpack(o_y, y, sy, W, H); unpack(o_u, u, sc, W / 2, H / 2); unpack(o_v, v, sc, W / 2, H / 2);
+  if (with_stats) memcpy(stats, hp + o_out, (size_t)nctu * 3 * 5 * 64 * 8);
+  ctx->loopValid = true; ctx->loopW = W; ctx->loopH = H;
   return HEVCDL_OK;
+}
+}  // namespace
+
+int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int sc, int W, int H, const uint8_t *tu_log2, const int8_t *qp,
+                         int beta_off, int tc_off, int cb_off, int cr_off) {
+  return inloop_impl(ctx, y, sy, u, v, sc, W, H, tu_log2, qp, beta_off, tc_off, cb_off, cr_off, nullptr, nullptr, nullptr, 0, 0, nullptr);
+}
+
+int hevcdl_inloop_frame(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int sc, int W, int H, const uint8_t *tu_log2, const int8_t *qp,
+                        int beta_off, int tc_off, int cb_off, int cr_off, const int16_t *oy, const int16_t *ou, const int16_t *ov, int osy, int osc,
+                        int64_t *stats) {
+  if (!stats) return HEVCDL_E_INVAL;
+  return inloop_impl(ctx, y, sy, u, v, sc, W, H, tu_log2, qp, beta_off, tc_off, cb_off, cr_off, oy, ou, ov, osy, osc, stats);
 }
 
 int hevcdl_sao_apply(hevcdl_ctx *ctx, const int16_t *sy, const int16_t *su, const int16_t *sv, int ssy, int ssc, int16_t *ry, int16_t *ru, int16_t *rv,
                      int rsy, int rsc, int W, int H, const hevcdl_sao_param *params) {
-  if (!ctx || !sy || !su || !sv || !ry || !ru || !rv || !params || W < 8 || H < 8 || (W & 7) || (H & 7) || W > 8192 || H > 8192 || ssy < W || rsy < W ||
-      ssc < W / 2 || rsc < W / 2)
+  const bool resident = ctx && !sy && !su && !sv;        // source = the deblocked picture hevcdl_inloop_frame left on the device
+  if (!ctx || (!resident && (!sy || !su || !sv || ssy < W || ssc < W / 2)) || !ry || !ru || !rv || !params || W < 8 || H < 8 || (W & 7) || (H & 7) ||
+      W > 8192 || H > 8192 || rsy < W || rsc < W / 2)
     return HEVCDL_E_INVAL;
+  if (resident && !(ctx->loopValid && ctx->loopW == W && ctx->loopH == H)) {
+    ctx->err = "hevcdl_sao_apply: no deblocked picture of this size is resident (hevcdl_inloop_frame must be the previous in-loop call)";
+    return HEVCDL_E_NOFRAME;
+  }
   const int cw = (W + 63) / 64, chh = (H + 63) / 64, nctu = cw * chh;
   for (int i = 0; i < nctu * 3; i++)
     if (params[i].type < -1 || params[i].type > 4) { ctx->err = "hevcdl_sao_apply: type in -1..4"; return HEVCDL_E_INVAL; }
   cudaSetDevice(ctx->cfg.device);
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_t = al((size_t)nctu * 3), b_o = al((size_t)nctu * 3 * 32);
+  // the source picture sits at the start of the scratch in both cases (the layout hevcdl_inloop_frame leaves behind)
   const size_t o_sy = 0, o_su = o_sy + b_y, o_sv = o_su + b_c, o_t = o_sv + b_c, o_o = o_t + b_t, o_ry = o_o + b_o, o_ru = o_ry + b_y, o_rv = o_ru + b_c,
                total = o_rv + b_c;
-  if (total > ctx->dbfCap) {                      // shares the deblocking entry point's grow-only scratch
-    cudaFree(ctx->dDbf); ctx->dDbf = nullptr; ctx->dbfCap = 0;
-    if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
-    CK(cudaMalloc(&ctx->dDbf, total));
-    CK(cudaMallocHost(&ctx->hDbf, total));
-    ctx->dbfCap = total;
-  }
+  { const int rc = dbf_reserve(ctx, total, resident ? o_t : 0); if (rc) return rc; }
   uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
   auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {
     for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
   };
-  pack(o_sy, sy, ssy, W, H); pack(o_su, su, ssc, W / 2, H / 2); pack(o_sv, sv, ssc, W / 2, H / 2);
+  if (!resident) {
+    ctx->loopValid = false;
+    pack(o_sy, sy, ssy, W, H); pack(o_su, su, ssc, W / 2, H / 2); pack(o_sv, sv, ssc, W / 2, H / 2);
+  }
   for (int i = 0; i < nctu * 3; i++) {
     hp[o_t + i] = (uint8_t)params[i].type;
     memcpy(hp + o_o + (size_t)i * 32, params[i].offset, 32);
   }
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(dp, hp, o_ry, cudaMemcpyHostToDevice, st));
+  if (resident) CK(cudaMemcpyAsync(dp + o_t, hp + o_t, o_ry - o_t, cudaMemcpyHostToDevice, st));
+  else CK(cudaMemcpyAsync(dp, hp, o_ry, cudaMemcpyHostToDevice, st));
   SaoApplyParams P{};
   P.src[0] = (const int16_t *)(dp + o_sy); P.src[1] = (const int16_t *)(dp + o_su); P.src[2] = (const int16_t *)(dp + o_sv);
   P.res[0] = (int16_t *)(dp + o_ry); P.res[1] = (int16_t *)(dp + o_ru); P.res[2] = (int16_t *)(dp + o_rv);
@@ -978,13 +1029,8 @@ int hevcdl_sao_stats(hevcdl_ctx *ctx, const int16_t *oy, const int16_t *ou, cons
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_y = al((size_t)W * H * 2), b_c = al((size_t)(W / 2) * (H / 2) * 2), b_out = al((size_t)nctu * 3 * 5 * 64 * 8);
   const size_t o_oy = 0, o_ou = o_oy + b_y, o_ov = o_ou + b_c, o_ry = o_ov + b_c, o_ru = o_ry + b_y, o_rv = o_ru + b_c, o_out = o_rv + b_c, total = o_out + b_out;
-  if (total > ctx->dbfCap) {                      // shares the deblocking entry point's grow-only scratch
-    cudaFree(ctx->dDbf); ctx->dDbf = nullptr; ctx->dbfCap = 0;
-    if (ctx->hDbf) { cudaFreeHost(ctx->hDbf); ctx->hDbf = nullptr; }
-    CK(cudaMalloc(&ctx->dDbf, total));
-    CK(cudaMallocHost(&ctx->hDbf, total));
-    ctx->dbfCap = total;
-  }
+  ctx->loopValid = false;                          // shares the in-loop entry points' grow-only scratch
+  { const int rc = dbf_reserve(ctx, total, 0); if (rc) return rc; }
   uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
   auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {
     for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);

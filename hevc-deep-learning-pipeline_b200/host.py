@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_sao_apply", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_sao_apply", "hevcdl_inloop_frame", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream",
@@ -107,6 +107,7 @@ def load_library():
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
     L.hevcdl_sao_stats.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
+    L.hevcdl_inloop_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip, vp, vp, vp, ip, ip, vp]
     L.hevcdl_sao_apply.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
     L.hevcdl_intra_pred.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, C.c_size_t]
     L.hevcdl_deblock_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip]
@@ -343,13 +344,29 @@ class DepthPredictor:
                                            W, H, _ptr(out)), "sao_stats")
         return out
 
-    def sao_apply(self, src, types, offsets):
-        """SAO application over a deblocked picture (hevcdl_sao_apply).  src: (Y, U, V) 8-bit planes; types: int8 [nctu, 3]
-        (-1 off, 0..3 edge offset, 4 band offset); offsets: int8 [nctu, 3, 32].  Returns the (Y, U, V) planes as uint8."""
-        H, W = src[0].shape
+    def inloop_frame(self, Y, U, V, tu_log2, qp, org, beta_off_div2=0, tc_off_div2=0, cb_qp_off=0, cr_qp_off=0):
+        """Deblocking + SAO statistics in one round trip (hevcdl_inloop_frame); the deblocked picture stays resident for a following
+        sao_apply(None, ...).  Returns ((Y, U, V) deblocked uint8, stats int64 [nctu, 3, 5, 2, 32])."""
+        H, W = Y.shape
+        y, u, v = (np.ascontiguousarray(p, np.int16).copy() for p in (Y, U, V))
+        o = [np.ascontiguousarray(p, np.int16) for p in org]
+        tu = np.ascontiguousarray(tu_log2, np.uint8).ravel()
+        q = np.ascontiguousarray(qp, np.int8).ravel()
         n = ((W + 63) // 64) * ((H + 63) // 64)
-        s = [np.ascontiguousarray(p, np.int16) for p in src]
-        r = [np.zeros_like(p) for p in s]
+        st = np.zeros((n, 3, 5, 2, 32), np.int64)
+        self._ck(self.lib.hevcdl_inloop_frame(self.h, _ptr(y), W, _ptr(u), _ptr(v), W // 2, W, H, _ptr(tu), _ptr(q), int(beta_off_div2),
+                                              int(tc_off_div2), int(cb_qp_off), int(cr_qp_off), _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), W, W // 2,
+                                              _ptr(st)), "inloop_frame")
+        return [p.astype(np.uint8) for p in (y, u, v)], st
+
+    def sao_apply(self, src, types, offsets, shape=None):
+        """SAO application over a deblocked picture (hevcdl_sao_apply).  src: (Y, U, V) 8-bit planes, or None = the picture the
+        preceding inloop_frame left on the device (then shape = (H, W)); types: int8 [nctu, 3] (-1 off, 0..3 edge offset, 4 band
+        offset); offsets: int8 [nctu, 3, 32].  Returns the (Y, U, V) planes as uint8."""
+        H, W = src[0].shape if src is not None else shape
+        n = ((W + 63) // 64) * ((H + 63) // 64)
+        s = [np.ascontiguousarray(p, np.int16) for p in src] if src is not None else [None, None, None]
+        r = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
         prm = np.zeros((n, 3), SAO_PARAM_DTYPE)
         prm["type"] = np.asarray(types, np.int8).reshape(n, 3)
         prm["offset"] = np.asarray(offsets, np.int8).reshape(n, 3, 32)

@@ -21,8 +21,11 @@
 
 #include "hevcdl.h"
 
+#include "inloop_cache.h"
+
 hevcdl_ctx *hevcdl_hm_context();                                     // TEncCu_hevcdl.cpp: the encoder's session (NULL before the first CTU)
 void hevcdl_hm_count_dbf( bool onDevice );
+HevcdlInloopCache g_hevcdl_inloop;                                   // inloop_cache.h
 void hevcdl_ref_loopFilterPic( TComLoopFilter *lf, TComPic *pcPic ); // ref_loopfilter_call.cpp
 
 Void TComLoopFilter::loopFilterPic( TComPic* pcPic )
@@ -67,13 +70,41 @@ Void TComLoopFilter::loopFilterPic( TComPic* pcPic )
     hevcdl_ref_loopFilterPic( this, pcPic );
     return;
   }
-  const int rc = hevcdl_deblock_frame( ctx, rec->getAddr( COMPONENT_Y ), rec->getStride( COMPONENT_Y ), rec->getAddr( COMPONENT_Cb ),
-                                       rec->getAddr( COMPONENT_Cr ), rec->getStride( COMPONENT_Cb ), W, H, tu.data(), qp.data(),
-                                       sl->getDeblockingFilterBetaOffsetDiv2(), sl->getDeblockingFilterTcOffsetDiv2(),
-                                       pps->getQpOffset( COMPONENT_Cb ), pps->getQpOffset( COMPONENT_Cr ) );
+  // With HEVCDL_SAO=1 as well, and SAO enabled for the sequence, the statistics SAOProcess will ask for next are taken in the same
+  // round trip (hevcdl_inloop_frame) and the deblocked picture stays on the device for the offset pass: TEncSAO_hevcdl.cpp and
+  // TComSAO_hevcdl.cpp pick both up from g_hevcdl_inloop after checking that the picture they are handed is still this one.
+  static const bool fuse = getenv( "HEVCDL_SAO" ) && atoi( getenv( "HEVCDL_SAO" ) ) == 1 && !( getenv( "HEVCDL_INLOOP_FUSE" ) && atoi( getenv( "HEVCDL_INLOOP_FUSE" ) ) == 0 );
+  g_hevcdl_inloop.valid = false;
+  int rc;
+  if ( fuse && sps->getUseSAO() )
+  {
+    TComPicYuv *org = pcPic->getPicYuvOrg();
+    const size_t nst = (size_t)( ( W + 63 ) / 64 ) * ( ( H + 63 ) / 64 ) * 3 * 5 * 64;
+    g_hevcdl_inloop.stats.resize( nst );
+    rc = hevcdl_inloop_frame( ctx, rec->getAddr( COMPONENT_Y ), rec->getStride( COMPONENT_Y ), rec->getAddr( COMPONENT_Cb ),
+                              rec->getAddr( COMPONENT_Cr ), rec->getStride( COMPONENT_Cb ), W, H, tu.data(), qp.data(),
+                              sl->getDeblockingFilterBetaOffsetDiv2(), sl->getDeblockingFilterTcOffsetDiv2(),
+                              pps->getQpOffset( COMPONENT_Cb ), pps->getQpOffset( COMPONENT_Cr ), org->getAddr( COMPONENT_Y ),
+                              org->getAddr( COMPONENT_Cb ), org->getAddr( COMPONENT_Cr ), org->getStride( COMPONENT_Y ),
+                              org->getStride( COMPONENT_Cb ), g_hevcdl_inloop.stats.data() );
+    if ( rc == 0 )
+    {
+      g_hevcdl_inloop.valid = true;
+      g_hevcdl_inloop.W = W; g_hevcdl_inloop.H = H;
+      g_hevcdl_inloop.guard = hevcdl_inloop_guard( rec );
+      g_hevcdl_inloop.org = org;
+    }
+  }
+  else
+  {
+    rc = hevcdl_deblock_frame( ctx, rec->getAddr( COMPONENT_Y ), rec->getStride( COMPONENT_Y ), rec->getAddr( COMPONENT_Cb ),
+                               rec->getAddr( COMPONENT_Cr ), rec->getStride( COMPONENT_Cb ), W, H, tu.data(), qp.data(),
+                               sl->getDeblockingFilterBetaOffsetDiv2(), sl->getDeblockingFilterTcOffsetDiv2(),
+                               pps->getQpOffset( COMPONENT_Cb ), pps->getQpOffset( COMPONENT_Cr ) );
+  }
   if ( rc )
   {
-    fprintf( stderr, "hevcdl: hevcdl_deblock_frame failed: %s (%s)\n", hevcdl_status_str( rc ), hevcdl_last_error( ctx ) );
+    fprintf( stderr, "hevcdl: hevcdl_deblock_frame / hevcdl_inloop_frame failed: %s (%s)\n", hevcdl_status_str( rc ), hevcdl_last_error( ctx ) );
     exit( EXIT_FAILURE );
   }
   hevcdl_hm_count_dbf( true );

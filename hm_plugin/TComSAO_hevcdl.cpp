@@ -19,9 +19,11 @@
 #undef offsetCTU
 
 #include "hevcdl.h"
+#include "inloop_cache.h"
 
 hevcdl_ctx *hevcdl_hm_context();                                     // TEncCu_hevcdl.cpp
 void hevcdl_hm_count_sao_apply( bool onDevice );
+void hevcdl_hm_count_inloop_resident( bool resident );
 
 Void TComSampleAdaptiveOffset::offsetCTU( Int ctuRsAddr, TComPicYuv* srcYuv, TComPicYuv* resYuv, SAOBlkParam& saoblkParam, TComPic* pPic )
 {
@@ -57,7 +59,12 @@ Void TComSampleAdaptiveOffset::offsetCTU( Int ctuRsAddr, TComPicYuv* srcYuv, TCo
     for ( Int k = 0; k < MAX_NUM_SAO_CLASSES; k++ ) p.offset[k] = (int8_t)o.offset[k];
   }
   if ( ctuRsAddr != m_numCTUsPic - 1 ) return;
-  const int rc = hevcdl_sao_apply( ctx, srcYuv->getAddr( COMPONENT_Y ), srcYuv->getAddr( COMPONENT_Cb ), srcYuv->getAddr( COMPONENT_Cr ),
+  // the deblocked picture is still on the device if the fused in-loop call made it and srcYuv is that picture (inloop_cache.h)
+  const bool resident = g_hevcdl_inloop.valid && g_hevcdl_inloop.W == m_picWidth && g_hevcdl_inloop.H == m_picHeight &&
+                        hevcdl_inloop_guard( srcYuv ) == g_hevcdl_inloop.guard;
+  g_hevcdl_inloop.valid = false;
+  const int rc = hevcdl_sao_apply( ctx, resident ? NULL : srcYuv->getAddr( COMPONENT_Y ), resident ? NULL : srcYuv->getAddr( COMPONENT_Cb ),
+                                   resident ? NULL : srcYuv->getAddr( COMPONENT_Cr ),
                                    srcYuv->getStride( COMPONENT_Y ), srcYuv->getStride( COMPONENT_Cb ), resYuv->getAddr( COMPONENT_Y ),
                                    resYuv->getAddr( COMPONENT_Cb ), resYuv->getAddr( COMPONENT_Cr ), resYuv->getStride( COMPONENT_Y ),
                                    resYuv->getStride( COMPONENT_Cb ), m_picWidth, m_picHeight, prm.data() );
@@ -68,4 +75,5 @@ Void TComSampleAdaptiveOffset::offsetCTU( Int ctuRsAddr, TComPicYuv* srcYuv, TCo
   }
   prm.clear();
   hevcdl_hm_count_sao_apply( true );
+  hevcdl_hm_count_inloop_resident( resident );
 }

@@ -41,6 +41,8 @@
 //                     (hevcdl_sao_stats; hm_plugin/TEncSAO_hevcdl.cpp replaces TEncSampleAdaptiveOffset::getStatistics) and
 //                     the application of the decided offsets (hevcdl_sao_apply; hm_plugin/TComSAO_hevcdl.cpp replaces
 //                     TComSampleAdaptiveOffset::offsetCTU); the RD decision between them stays HM's: byte-identical bitstreams
+//                     With HEVCDL_DBF=1 as well the three passes share the picture on the device (hevcdl_inloop_frame: deblocking +
+//                     statistics in one round trip, offsets applied to the resident picture); HEVCDL_INLOOP_FUSE=0 keeps them separate
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
 //                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
 //                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
@@ -247,6 +249,7 @@ struct HevcdlSession {
   unsigned long long exact_calls = 0;
   unsigned long long pred_device = 0, pred_host = 0; // intra-predicted blocks on the device / by the reference's own code
   unsigned long long sao_device = 0, sao_host = 0;
+  unsigned long long inloop_resident = 0;          // pictures whose SAO passes reused the deblocking call's round trip / resident picture
   unsigned long long saoapply_device = 0, saoapply_host = 0;   // pictures whose SAO offsets were applied on the device / by the reference   // SAO statistics passes on the device / by the reference's own code
   unsigned long long dbf_device = 0, dbf_host = 0;   // pictures deblocked on the device / by the reference's own filter
   bool gpu_tq = false;          // HEVCDL_TQ=1: TU transform / quantisation / inverse transform on the device
@@ -464,6 +467,7 @@ struct HevcdlSession {
         fprintf(stderr, "hevcdl: blocks predicted on the device %llu / by the reference's code %llu\n", pred_device, pred_host);
         fprintf(stderr, "hevcdl: SAO statistics passes on the device %llu / by the reference's code %llu\n", sao_device, sao_host);
         fprintf(stderr, "hevcdl: SAO offsets applied on the device for %llu pictures / by the reference's code for %llu\n", saoapply_device, saoapply_host);
+        fprintf(stderr, "hevcdl: in-loop passes of %llu pictures shared one upload (deblocked picture resident between deblocking and SAO)\n", inloop_resident);
         fprintf(stderr, "hevcdl: lookahead %d: %llu frames were on the device before HM asked, %llu uploaded from HM's planes, %llu mismatches\n",
                 lookahead, la_hits, la_direct, la_mismatch);
         fprintf(stderr, "hevcdl: encoder thread blocked %.3f s for hevcdl_create (CUDA context + weights + buffers: %.3f s, started at program "
@@ -563,6 +567,7 @@ bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu
 
 hevcdl_ctx *hevcdl_hm_context() { return g_session.ctx; }
 void hevcdl_hm_count_pred( bool onDevice ) { ( onDevice ? g_session.pred_device : g_session.pred_host )++; }
+void hevcdl_hm_count_inloop_resident( bool resident ) { if ( resident ) g_session.inloop_resident++; }
 void hevcdl_hm_count_sao_apply( bool onDevice ) { ( onDevice ? g_session.saoapply_device : g_session.saoapply_host )++; }
 void hevcdl_hm_count_sao( bool onDevice ) { ( onDevice ? g_session.sao_device : g_session.sao_host )++; }
 void hevcdl_hm_count_dbf( bool onDevice ) { ( onDevice ? g_session.dbf_device : g_session.dbf_host )++; }

@@ -14,6 +14,7 @@
 #include "sao_hook.h"
 
 #include "hevcdl.h"
+#include "inloop_cache.h"
 
 hevcdl_ctx *hevcdl_hm_context();                                     // TEncCu_hevcdl.cpp
 void hevcdl_hm_count_sao( bool onDevice );
@@ -37,7 +38,11 @@ Void TEncSampleAdaptiveOffset::getStatistics( SAOStatData*** blkStats, TComPicYu
     return;
   }
   std::vector<int64_t> st( (size_t)m_numCTUsPic * 3 * NUM_SAO_NEW_TYPES * 2 * MAX_NUM_SAO_CLASSES );
-  const int rc = hevcdl_sao_stats( ctx, orgYuv->getAddr( COMPONENT_Y ), orgYuv->getAddr( COMPONENT_Cb ), orgYuv->getAddr( COMPONENT_Cr ),
+  // taken already, in the deblocking call's round trip (TComLoopFilter_hevcdl.cpp), if srcYuv is still that deblocked picture
+  const bool cached = g_hevcdl_inloop.valid && g_hevcdl_inloop.W == m_picWidth && g_hevcdl_inloop.H == m_picHeight && g_hevcdl_inloop.org == orgYuv &&
+                      g_hevcdl_inloop.stats.size() == st.size() && hevcdl_inloop_guard( srcYuv ) == g_hevcdl_inloop.guard;
+  if ( cached ) st = g_hevcdl_inloop.stats;
+  const int rc = cached ? 0 : hevcdl_sao_stats( ctx, orgYuv->getAddr( COMPONENT_Y ), orgYuv->getAddr( COMPONENT_Cb ), orgYuv->getAddr( COMPONENT_Cr ),
                                    orgYuv->getStride( COMPONENT_Y ), orgYuv->getStride( COMPONENT_Cb ), srcYuv->getAddr( COMPONENT_Y ),
                                    srcYuv->getAddr( COMPONENT_Cb ), srcYuv->getAddr( COMPONENT_Cr ), srcYuv->getStride( COMPONENT_Y ),
                                    srcYuv->getStride( COMPONENT_Cb ), m_picWidth, m_picHeight, st.data() );
@@ -54,5 +59,6 @@ Void TEncSampleAdaptiveOffset::getStatistics( SAOStatData*** blkStats, TComPicYu
         for ( Int k = 0; k < MAX_NUM_SAO_CLASSES; k++ ) blkStats[a][c][t].diff[k] = *p++;
         for ( Int k = 0; k < MAX_NUM_SAO_CLASSES; k++ ) blkStats[a][c][t].count[k] = *p++;
       }
+  if ( !cached ) g_hevcdl_inloop.valid = false;    // hevcdl_sao_stats reused the scratch the resident picture lived in
   hevcdl_hm_count_sao( true );
 }

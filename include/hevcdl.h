@@ -216,6 +216,18 @@ int hevcdl_deblock_frame(hevcdl_ctx *ctx, int16_t *y, int stride_y, int16_t *u, 
                          const uint8_t *tu_log2, const int8_t *qp, int beta_offset_div2, int tc_offset_div2, int cb_qp_offset,
                          int cr_qp_offset);
 
+/* Deblocking and SAO statistics of one picture in ONE round trip, the picture staying on the device: what hevcdl_deblock_frame does
+ * to y / u / v, then what hevcdl_sao_stats does with the deblocked picture against org_* -- one upload (reconstruction, maps,
+ * original), one download (deblocked picture, statistics).  Afterwards the deblocked picture is RESIDENT in the context:
+ * a following hevcdl_sao_apply with src_y = src_u = src_v = NULL takes it as its source, so that applying the offsets HM decides
+ * from these statistics costs only the parameters up and the result down.  Any other in-loop entry point of the context
+ * (hevcdl_deblock_frame, hevcdl_sao_stats, hevcdl_sao_apply with a source) drops the resident picture.  Same restrictions and
+ * bit-exactness as the two calls it combines.  Synchronous. */
+int hevcdl_inloop_frame(hevcdl_ctx *ctx, int16_t *y, int stride_y, int16_t *u, int16_t *v, int stride_c, int width, int height,
+                        const uint8_t *tu_log2, const int8_t *qp, int beta_offset_div2, int tc_offset_div2, int cb_qp_offset,
+                        int cr_qp_offset, const int16_t *org_y, const int16_t *org_u, const int16_t *org_v, int org_stride_y,
+                        int org_stride_c, int64_t *stats);
+
 /* Intra prediction of `n` blocks from explicit reference samples: the arithmetic of TComPrediction::predIntraAng (HM TLibCommon/
  * TComPrediction.cpp:390-472: planar, DC with boundary smoothing, the 33 angular predictors with the projected side reference and
  * the first-column filter of the pure vertical / horizontal modes), which the RD pass calls for every luma and chroma transform

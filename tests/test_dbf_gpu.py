@@ -139,6 +139,14 @@ def test_dropin_sao_statistics_on_the_device_keep_the_bitstream(tmp_path, built,
     assert ra["rc"] == 0 and rb["rc"] == 0, (ra["stderr"][-400:], rb["stderr"][-600:])
     assert re.search(r"SAO statistics passes on the device 2 / by the reference's code 0", rb["stderr"]), rb["stderr"][-600:]
     assert re.search(r"SAO offsets applied on the device for 2 pictures / by the reference's code for 0", rb["stderr"]), rb["stderr"][-600:]
+    assert re.search(r"in-loop passes of 2 pictures shared one upload", rb["stderr"]), rb["stderr"][-800:]
+    # ... and with the three passes kept apart (three round trips per picture): the same bitstream
+    c = tmp_path / "sep"
+    c.mkdir()
+    hm_util.write_yuv(str(c / "in.yuv"), frames)
+    rc_ = hm_util.encode("hevcdl", str(c), "in.yuv", w, h, 2, qp,
+                         env={"HEVCDL_PRECISION": "fp32", "HEVCDL_SAO": "1", "HEVCDL_DBF": "1", "HEVCDL_INLOOP_FUSE": "0", "HEVCDL_VERBOSE": "1"})
+    assert rc_["rc"] == 0 and re.search(r"in-loop passes of 0 pictures shared one upload", rc_["stderr"]) and rc_["sha1"] == ra["sha1"]
     assert ra["sha1"] == rb["sha1"]
     ok, out = hm_util.decode_ok(str(b))
     assert ok, out[-400:]
@@ -210,3 +218,35 @@ def test_sao_application_vs_oracle_synthetic(dp, oracle):
             assert (a == b).all(), (W, H, name, int((a != b).sum()))
         same = dp.sao_apply(src, np.full((n, 3), -1, np.int8), o)
         assert all((a == b).all() for a, b in zip(same, src))
+
+
+def test_fused_inloop_call_and_resident_offsets(dp, oracle, host):
+    """hevcdl_inloop_frame = deblocking + SAO statistics in one round trip, then hevcdl_sao_apply with no source = the picture
+    that call left on the device: all three results equal the oracle's; another in-loop call drops the resident picture."""
+    rng = np.random.default_rng(31)
+    for (W, H) in ((72, 40), (416, 240), (1920, 1080)):
+        base = np.kron(rng.integers(30, 226, ((H + 7) // 8, (W + 7) // 8)), np.ones((8, 8)))[:H, :W]
+        Y = np.clip(base + rng.integers(-3, 4, (H, W)), 0, 255).astype(np.uint8)
+        U = np.clip(np.kron(rng.integers(60, 196, ((H + 15) // 16, (W + 15) // 16)), np.ones((8, 8)))[:H // 2, :W // 2] + rng.integers(-2, 3, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+        V = U[::-1, ::-1].copy()
+        org = [np.clip(p.astype(np.int32) + rng.integers(-5, 6, p.shape), 0, 255).astype(np.uint8) for p in (Y, U, V)]
+        tu = np.kron(rng.integers(2, 6, (H // 32 + 1, W // 32 + 1)), np.ones((8, 8), np.int64))[:H // 4, :W // 4].astype(np.uint8)
+        qp = np.full(tu.shape, 33, np.int8)
+        want_rec = oracle.deblock_frame(Y, U, V, tu, qp, 0, 1, -1, 2)
+        want_st = oracle.sao_stats(org, want_rec)
+        rec, st = dp.inloop_frame(Y, U, V, tu, qp, org, 0, 1, -1, 2)
+        assert all((a == b).all() for a, b in zip(rec, want_rec)) and (st == want_st).all(), (W, H)
+        n = ((W + 63) // 64) * ((H + 63) // 64)
+        t = rng.integers(-1, 5, (n, 3)).astype(np.int8)
+        o = rng.integers(-7, 8, (n, 3, 32)).astype(np.int8)
+        want = oracle.sao_apply(want_rec, t, o)
+        got = dp.sao_apply(None, t, o, shape=(H, W))
+        assert all((a == b).all() for a, b in zip(got, want)), (W, H)
+        again = dp.sao_apply(None, t, o, shape=(H, W))                 # the source is untouched: still resident
+        assert all((a == b).all() for a, b in zip(again, want))
+    n2 = ((W + 63) // 64) * ((H // 2 // 8 * 8 + 63) // 64)
+    with pytest.raises(host.HevcdlError):
+        dp.sao_apply(None, np.full((n2, 3), -1, np.int8), np.zeros((n2, 3, 32), np.int8), shape=(H // 2 // 8 * 8, W))   # no resident picture of that size
+    dp.sao_stats(org, rec)                                              # any other in-loop call drops it
+    with pytest.raises(host.HevcdlError):
+        dp.sao_apply(None, t, o, shape=(H, W))

@@ -297,6 +297,7 @@ def test_dropin_every_device_component_at_once(tmp_path, built, host, pkg):
     assert re.search(r"pictures deblocked on the device %d / by the reference's filter 0" % n, err)
     assert re.search(r"SAO statistics passes on the device %d / by the reference's code 0" % n, err)
     assert re.search(r"SAO offsets applied on the device for %d pictures / by the reference's code for 0" % n, err)
+    assert re.search(r"in-loop passes of %d pictures shared one upload" % n, err)
     m = re.search(r"blocks predicted on the device (\d+) / by the reference's code (\d+)", err)
     assert int(m.group(1)) > 5000 and int(m.group(2)) == 0
     assert re.search(r"lookahead 3: %d frames were on the device before HM asked" % (n - 1), err)

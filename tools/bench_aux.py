@@ -123,6 +123,40 @@ def main():
             want = oracle.sao_apply(src_, ty, of)
             d["cpu_port_ms"] = (time.perf_counter() - t) * 1e3
             d["identical"] = bool(all((x == y).all() for x, y in zip(got, want)))
+        # ---- the three in-loop passes through the C-ABI proper (prepared int16 planes, no numpy conversions in the timed
+        #      region): three separate calls against hevcdl_inloop_frame + hevcdl_sao_apply on the resident picture
+        lib, hctx = dp.lib, dp.h
+        P16 = lambda planes: [np.ascontiguousarray(p, np.int16) for p in planes]
+        rec0, orgp = P16((Y, U, V)), P16(org)
+        tuf, qpf = np.ascontiguousarray(tu, np.uint8).ravel(), np.ascontiguousarray(qp, np.int8).ravel()
+        prm = np.zeros((nctu, 3), host.SAO_PARAM_DTYPE)
+        prm["type"] = ty; prm["offset"] = of
+        st_buf = np.zeros((nctu, 3, 5, 2, 32), np.int64)
+        res = [np.zeros_like(p) for p in rec0]
+        vp = lambda a_: C.c_void_p(a_.ctypes.data)
+
+        def separate():
+            r = [p.copy() for p in rec0]
+            t0 = time.perf_counter()
+            lib.hevcdl_deblock_frame(hctx, vp(r[0]), W, vp(r[1]), vp(r[2]), W // 2, W, H8, vp(tuf), vp(qpf), 0, 0, 0, 0)
+            lib.hevcdl_sao_stats(hctx, vp(orgp[0]), vp(orgp[1]), vp(orgp[2]), W, W // 2, vp(r[0]), vp(r[1]), vp(r[2]), W, W // 2, W, H8, vp(st_buf))
+            lib.hevcdl_sao_apply(hctx, vp(r[0]), vp(r[1]), vp(r[2]), W, W // 2, vp(res[0]), vp(res[1]), vp(res[2]), W, W // 2, W, H8, vp(prm))
+            return (time.perf_counter() - t0) * 1e3, [p.copy() for p in res], st_buf.copy()
+
+        def fused():
+            r = [p.copy() for p in rec0]
+            t0 = time.perf_counter()
+            lib.hevcdl_inloop_frame(hctx, vp(r[0]), W, vp(r[1]), vp(r[2]), W // 2, W, H8, vp(tuf), vp(qpf), 0, 0, 0, 0,
+                                    vp(orgp[0]), vp(orgp[1]), vp(orgp[2]), W, W // 2, vp(st_buf))
+            lib.hevcdl_sao_apply(hctx, None, None, None, W, W // 2, vp(res[0]), vp(res[1]), vp(res[2]), W, W // 2, W, H8, vp(prm))
+            return (time.perf_counter() - t0) * 1e3, [p.copy() for p in res], st_buf.copy()
+        ts, tf = [], []
+        for _ in range(a.reps):
+            ms, res_s, st_s = separate(); ts.append(ms)
+            ms, res_f, st_f = fused(); tf.append(ms)
+        out["inloop_three_passes_c_abi"] = {"separate_calls_ms": med(ts[1:]), "fused_resident_ms": med(tf[1:]),
+                                            "identical": bool(all((x == y).all() for x, y in zip(res_s, res_f)) and (st_s == st_f).all()),
+                                            "pcie_mb_separate": 37.4 * W * H8 / (1920 * 1080), "pcie_mb_fused": 25.0 * W * H8 / (1920 * 1080)}
         # ---- intra predictor: every 16x16 block of the luma picture x 35 modes -----------------------------
         nblk = (W // 16) * (H8 // 16)
         lines = [rng.integers(0, 256, 65).astype(np.int16) for _ in range(64)]
