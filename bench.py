@@ -403,7 +403,8 @@ def run_b200(args, rank, world, local_rank):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.precision)
+        tj = json.load(open(tp))
+        traffic = tj.get(args.precision + "_by_frames_per_launch", {}).get(str(args.batch), tj.get(args.precision) if args.batch == 4 else None)
     out = {
         "metric": "intra CTUs/sec", "value": r["value"], "unit": "CTU/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "frames_timed": frames_timed, "higher_is_better": True,
@@ -423,7 +424,7 @@ def run_b200(args, rank, world, local_rank):
                      "frac": ach_cnn / pk["tensor_burst"], "frac_sustained": ach_cnn / pk["tensor_sustained"],
                      "peak_sustained": pk["tensor_sustained"], "traffic": traffic,
                      "traffic_over_algorithmic": (traffic / (BYTES_PER_CTU * nctu)) if traffic else None,
-                     "traffic_note": "DRAM bytes of the CNN kernels per frame in the pipeline's natural cache state (ncu --cache-control none, profiles/traffic.json): the bf16 intermediates of a 4-frame launch exceed L2",
+                     "traffic_note": "DRAM bytes of the CNN kernels per frame in the pipeline's natural cache state (ncu --cache-control none, profiles/traffic.json): the bf16 intermediates of a multi-frame launch exceed L2; null if not measured for this --batch",
                      "peak_source": pk["src"] + " bf16: burst (a %.0f ms region at full clocks); frac_sustained is against the long-run figure" % r["ms_total"],
                      "kernel": "CNN stage = k_tc_l1 + k_tc_conv2 + k_tc_conv3 + k_tc_fc (tcgen05)" if prec else "k_cnn_fp32", "kernel_ms": ms_cnn,
                      "fused_path": {"achieved": ach_fused, "frac": ach_fused / pk["tensor_burst"], "frac_sustained": ach_fused / pk["tensor_sustained"],
@@ -501,7 +502,7 @@ def main():
     ap.add_argument("--pool", type=int, default=48)
     ap.add_argument("--content", default="mixed", choices=["mixed", "noise", "flat"], help="synthetic content (SURVEY.md 8(d)); noise / flat are the stress cases")
     ap.add_argument("--depth", type=int, default=0, help="frames in flight in the e2e measurement (0: three launch batches)")
-    ap.add_argument("--batch", type=int, default=4, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
+    ap.add_argument("--batch", type=int, default=8, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
     ap.add_argument("--ref-ctus", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
