@@ -231,7 +231,7 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------------------
-def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed, batch, prec):
+def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed, batch, prec, batch_e2e=0):
     """Resident and end-to-end throughput of one picture size on this rank's GPU; every rank calls it with its own frames."""
     def barrier():
         if world > 1:
@@ -267,6 +267,14 @@ def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed
     for i in frames:
         dp.release(i)
     # ---- e2e: pinned host planes -> labels + PU lists + candidates back on the host, pipelined ------------
+    # Frames per launch is the caller's choice (hevcdl_cfg.batch; results do not depend on it).  Resident throughput likes
+    # long launches (8); the end-to-end pipeline overlaps copies and launches better with shorter ones, which shows when 8
+    # ranks share the host's copy bandwidth (8 GPUs end to end: 31.0 M CTU/s with 4 frames per launch, 30.3 M with 8).
+    be = batch_e2e if batch_e2e > 0 else batch
+    if be != batch:
+        dp.close()
+        dp = host.DepthPredictor(w, h, device=local_rank, slots=pool_n, precision=prec, rmd=True, batch=be, outputs=0,
+                                 pinned_input=True, numa_bind=True)
     pinned = []
     for (Y, U, V) in pool[:min(pool_n, 8)]:
         buf = host.PinnedBuffer(frame_bytes, write_combined=args.wc)      # page-locked by the library's own allocator
@@ -274,7 +282,7 @@ def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed
         a[:w * h] = Y.ravel(); a[w * h:w * h * 5 // 4] = U.ravel(); a[w * h * 5 // 4:] = V.ravel()
         pinned.append((buf, a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2),
                        a[w * h * 5 // 4:].reshape(h // 2, w // 2)))
-    depth = min(args.depth if args.depth > 0 else 3 * batch, pool_n)
+    depth = min(args.depth if args.depth > 0 else 3 * be, pool_n)
     d2h = [0]
 
     def consume(f):
@@ -313,7 +321,7 @@ def measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed
     return {"nctu": nctu, "ms_total": ms_total, "ms_cnn": ms[1], "ms_rmd": ms[2], "launches": launches,
             "value": world * frames_timed * nctu / (ms_total / 1000.0),
             "e2e_value": world * frames_timed * nctu / dt, "e2e_py_value": world * frames_timed * nctu / dt_py,
-            "h2d_per_frame": frame_bytes, "d2h_per_frame": nb // frames_timed, "depth": depth,
+            "h2d_per_frame": frame_bytes, "d2h_per_frame": nb // frames_timed, "depth": depth, "batch_e2e": be,
             "pus_per_frame": npu_total / pool_n, "stats": st}
 
 
@@ -389,7 +397,7 @@ def run_b200(args, rank, world, local_rank):
     pool = make_pool(pkg.synth, w, h, args.pool, rank, args.content)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    r = measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed, args.batch, prec)
+    r = measure(host, torch, dist, args, w, h, pool, local_rank, world, frames_timed, args.batch, prec, args.batch_e2e)
     clocks = sampler.stop()                          # sampled every 10 ms over both timed regions (resident and e2e)
     nctu = r["nctu"]
     frame_bytes = w * h * 3 // 2
@@ -417,7 +425,7 @@ def run_b200(args, rank, world, local_rank):
                    "pus_per_frame": r["pus_per_frame"], "numa_node": numa_node},
         "clocks": clocks,
         "e2e": {"value": r["e2e_value"], "unit": "CTU/s", "h2d_bytes_per_step": r["h2d_per_frame"],
-                "d2h_bytes_per_step": r["d2h_per_frame"], "pipeline_depth": r["depth"], "frames_timed": frames_timed,
+                "d2h_bytes_per_step": r["d2h_per_frame"], "pipeline_depth": r["depth"], "frames_per_cnn_launch": r["batch_e2e"], "frames_timed": frames_timed,
                 "python_value": r["e2e_py_value"], "host_planes": "page-locked (hevcdl_host_alloc%s), hevcdl_cfg.pinned_input = 1" % (", write-combined" if args.wc else ""), "outputs": "labels + PU list + ranked candidate modes (hevcdl_cfg.outputs = 0)"},
         "gpu_launches": r["launches"],
         "roofline": {"bound": "tensor", "achieved": ach_cnn, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
@@ -503,6 +511,7 @@ def main():
     ap.add_argument("--content", default="mixed", choices=["mixed", "noise", "flat"], help="synthetic content (SURVEY.md 8(d)); noise / flat are the stress cases")
     ap.add_argument("--depth", type=int, default=0, help="frames in flight in the e2e measurement (0: three launch batches)")
     ap.add_argument("--batch", type=int, default=8, help="frames per CNN launch (hevcdl_cfg.batch); results do not depend on it")
+    ap.add_argument("--batch-e2e", type=int, default=4, help="frames per CNN launch in the end-to-end leg (0: same as --batch)")
     ap.add_argument("--ref-ctus", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
