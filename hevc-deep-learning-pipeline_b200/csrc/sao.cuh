@@ -76,8 +76,8 @@ k_sao_stats(const SaoParams P) {
 // CTU of the picture: res = clip(src + offset[class]) for the samples the CTU's SAO type may touch (edge types leave out
 // samples whose neighbour lies outside the picture -- one slice, no tiles -- with the reference's first / last line ranges
 // of the diagonal types), every other sample keeps its deblocked value.  Classification reads only `src`, so all CTUs are
-// independent: one block per (CTU, component), neighbours straight from global memory (each sample is read at most three
-// times, from L1 / L2), each thread one row segment.  HBM-bound byte work: two pictures' worth of int16 traffic.
+// independent: one block per (CTU, component), one warp per row (the row's valid range is decided once), neighbours straight
+// from global memory (each sample is read at most three times, from L1 / L2).  Byte work: two pictures' worth of int16 traffic.
 struct SaoApplyParams {
   const int16_t *src[3];
   int16_t *res[3];
@@ -100,36 +100,37 @@ k_sao_apply(const SaoApplyParams P) {
   __syncthreads();
   const bool L = xp > 0, A = yp > 0, R = xp + 64 < P.W, B = yp + 64 < P.H, AL = L && A, AR = A && R, BL = B && L, BR = B && R;
   const int sx = L ? 0 : 1, ex = R ? width : width - 1;
-  for (int i = threadIdx.x; i < width * height; i += blockDim.x) {
-    const int y = i / width, x = i - y * width;
-    const int v = s[y * stride + x];
-    int out = v;
-    if (t >= 0) {
-      int xa, xb;
-      if (t == 4) { xa = 0; xb = width; }
-      else if (t == 0) { xa = sx; xb = ex; }
-      else if (t == 1) { xa = 0; xb = (y < (A ? 0 : 1) || y >= (B ? height : height - 1)) ? 0 : width; }
-      else if (t == 2) {
-        if (y == 0) { xa = AL ? 0 : 1; xb = A ? ex : 1; }
-        else if (y == height - 1) { xa = B ? sx : width - 1; xb = BR ? width : width - 1; }
-        else { xa = sx; xb = ex; }
-      } else {
-        if (y == 0) { xa = A ? sx : width - 1; xb = AR ? width : width - 1; }
-        else if (y == height - 1) { xa = BL ? 0 : 1; xb = B ? ex : 1; }
-        else { xa = sx; xb = ex; }
-      }
+  const int dx = t == 1 ? 0 : (t == 3 ? -1 : 1), dy = t == 0 ? 0 : 1;   // second neighbour at (+dx, +dy), first at (-dx, -dy)
+  // one warp per row, a lane per column (two for 64-wide luma rows): the row's valid range is decided once per row
+  for (int y = threadIdx.x >> 5; y < height; y += 8) {
+    int xa = 0, xb = 0;                           // t < 0: nothing is offset
+    if (t == 4) { xb = width; }
+    else if (t == 0) { xa = sx; xb = ex; }
+    else if (t == 1) { xb = (y < (A ? 0 : 1) || y >= (B ? height : height - 1)) ? 0 : width; }
+    else if (t == 2) {
+      if (y == 0) { xa = AL ? 0 : 1; xb = A ? ex : 1; }
+      else if (y == height - 1) { xa = B ? sx : width - 1; xb = BR ? width : width - 1; }
+      else { xa = sx; xb = ex; }
+    } else if (t == 3) {
+      if (y == 0) { xa = A ? sx : width - 1; xb = AR ? width : width - 1; }
+      else if (y == height - 1) { xa = BL ? 0 : 1; xb = B ? ex : 1; }
+      else { xa = sx; xb = ex; }
+    }
+    const int16_t *__restrict__ row = s + (size_t)y * stride;
+    for (int x = threadIdx.x & 31; x < width; x += 32) {
+      const int v = row[x];
+      int out = v;
       if (x >= xa && x < xb) {
         int cls;
         if (t == 4) cls = v >> 3;
         else {
-          const int dx = t == 1 ? 0 : (t == 3 ? -1 : 1), dy = t == 0 ? 0 : 1;   // second neighbour at (+dx, +dy), first at (-dx, -dy)
-          const int n0 = s[(y - dy) * stride + x - dx], n1 = s[(y + dy) * stride + x + dx];
+          const int n0 = row[-dy * stride + x - dx], n1 = row[dy * stride + x + dx];
           cls = 2 + ((v > n0) - (v < n0)) + ((v > n1) - (v < n1));
         }
         out = min(255, max(0, v + s_off[cls]));
       }
+      r[(size_t)y * stride + x] = (int16_t)out;
     }
-    r[y * stride + x] = (int16_t)out;
   }
 }
 
