@@ -834,6 +834,37 @@ int hevcdl_rmd_exact(hevcdl_ctx *ctx, int n, const uint8_t *sizes, const uint8_t
 }
 
 namespace {
+// Is `p` page-locked host memory (hevcdl_host_alloc, hevcdl_host_register, or the caller's own cudaHostAlloc / cudaHostRegister)?
+bool host_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Transfers of one picture plane between the caller's strided int16 rows and a dense device plane.  Page-locked caller memory
+// is copied directly (cudaMemcpy2DAsync, no host-side pass); anything else goes through the context's pinned scratch (rows
+// packed before / unpacked after, `mirror` = the scratch location that mirrors the device plane).
+struct PlaneIO {
+  struct Pending { const uint8_t *mirror; int16_t *p; int stride, w, h; };
+  cudaStream_t st;
+  std::vector<Pending> later;
+  cudaError_t up(uint8_t *dev, uint8_t *mirror, const int16_t *p, int stride, int w, int h) {
+    if (host_is_pinned(p)) return cudaMemcpy2DAsync(dev, (size_t)w * 2, p, (size_t)stride * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, st);
+    for (int r = 0; r < h; r++) memcpy(mirror + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
+    return cudaMemcpyAsync(dev, mirror, (size_t)w * h * 2, cudaMemcpyHostToDevice, st);
+  }
+  cudaError_t down(const uint8_t *dev, uint8_t *mirror, int16_t *p, int stride, int w, int h) {
+    if (host_is_pinned(p)) return cudaMemcpy2DAsync(p, (size_t)stride * 2, dev, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost, st);
+    later.push_back(Pending{mirror, p, stride, w, h});
+    return cudaMemcpyAsync(mirror, dev, (size_t)w * h * 2, cudaMemcpyDeviceToHost, st);
+  }
+  void finish() {                                 // after the stream has been synchronised
+    for (const Pending &q : later)
+      for (int r = 0; r < q.h; r++) memcpy(q.p + (size_t)r * q.stride, q.mirror + (size_t)r * q.w * 2, (size_t)q.w * 2);
+    later.clear();
+  }
+};
+
 // grow-only scratch of the in-loop entry points; keep > 0: the first `keep` bytes (the resident deblocked picture) survive a growth
 int dbf_reserve(hevcdl_ctx *ctx, size_t total, size_t keep) {
   if (total <= ctx->dbfCap) return HEVCDL_OK;
@@ -874,15 +905,15 @@ int inloop_impl(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int
                o_out = o_ov + b_c, total = with_stats ? o_out + b_out : o_oy;
   { const int rc = dbf_reserve(ctx, total, 0); if (rc) return rc; }
   uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
-  auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {      // dense planes on the device
-    for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
-  };
-  pack(o_y, y, sy, W, H); pack(o_u, u, sc, W / 2, H / 2); pack(o_v, v, sc, W / 2, H / 2);
+  cudaStream_t st = ctx->stream;
+  PlaneIO io{st, {}};
+  CK(io.up(dp + o_y, hp + o_y, y, sy, W, H)); CK(io.up(dp + o_u, hp + o_u, u, sc, W / 2, H / 2)); CK(io.up(dp + o_v, hp + o_v, v, sc, W / 2, H / 2));
   memcpy(hp + o_tu, tu_log2, nu);
   memcpy(hp + o_qp, qp, nu);
-  if (with_stats) { pack(o_oy, oy, osy, W, H); pack(o_ou, ou, osc, W / 2, H / 2); pack(o_ov, ov, osc, W / 2, H / 2); }
-  cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(dp, hp, with_stats ? o_out : o_oy, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp + o_tu, hp + o_tu, o_oy - o_tu, cudaMemcpyHostToDevice, st));
+  if (with_stats) {
+    CK(io.up(dp + o_oy, hp + o_oy, oy, osy, W, H)); CK(io.up(dp + o_ou, hp + o_ou, ou, osc, W / 2, H / 2)); CK(io.up(dp + o_ov, hp + o_ov, ov, osc, W / 2, H / 2));
+  }
   DbfParams P{(int16_t *)(dp + o_y), (int16_t *)(dp + o_u), (int16_t *)(dp + o_v), W, W / 2, W, H, dp + o_tu, (const int8_t *)(dp + o_qp),
               beta_off, tc_off, cb_off, cr_off};
   const int nv = (W / 8 - 1) * (H / 4), nh = (W / 4) * (H / 8 - 1);
@@ -899,13 +930,10 @@ int inloop_impl(hevcdl_ctx *ctx, int16_t *y, int sy, int16_t *u, int16_t *v, int
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->evAux1, st));
   ctx->stats.kernel_launches += (nv > 0) + (nh > 0) + (with_stats ? 1 : 0);
-  CK(cudaMemcpyAsync(hp, dp, o_tu, cudaMemcpyDeviceToHost, st));
+  CK(io.down(dp + o_y, hp + o_y, y, sy, W, H)); CK(io.down(dp + o_u, hp + o_u, u, sc, W / 2, H / 2)); CK(io.down(dp + o_v, hp + o_v, v, sc, W / 2, H / 2));
   if (with_stats) CK(cudaMemcpyAsync(hp + o_out, dp + o_out, (size_t)nctu * 3 * 5 * 64 * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  auto unpack = [&](size_t off, int16_t *p, int stride, int w, int h) {
-    for (int r = 0; r < h; r++) memcpy(p + (size_t)r * stride, hp + off + (size_t)r * w * 2, (size_t)w * 2);
-  };
-  unpack(o_y, y, sy, W, H); unpack(o_u, u, sc, W / 2, H / 2); unpack(o_v, v, sc, W / 2, H / 2);
+  io.finish();
   if (with_stats) memcpy(stats, hp + o_out, (size_t)nctu * 3 * 5 * 64 * 8);
   ctx->loopValid = true; ctx->loopW = W; ctx->loopH = H;
   return HEVCDL_OK;
@@ -945,20 +973,17 @@ int hevcdl_sao_apply(hevcdl_ctx *ctx, const int16_t *sy, const int16_t *su, cons
                total = o_rv + b_c;
   { const int rc = dbf_reserve(ctx, total, resident ? o_t : 0); if (rc) return rc; }
   uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
-  auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {
-    for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
-  };
+  cudaStream_t st = ctx->stream;
+  PlaneIO io{st, {}};
   if (!resident) {
     ctx->loopValid = false;
-    pack(o_sy, sy, ssy, W, H); pack(o_su, su, ssc, W / 2, H / 2); pack(o_sv, sv, ssc, W / 2, H / 2);
+    CK(io.up(dp + o_sy, hp + o_sy, sy, ssy, W, H)); CK(io.up(dp + o_su, hp + o_su, su, ssc, W / 2, H / 2)); CK(io.up(dp + o_sv, hp + o_sv, sv, ssc, W / 2, H / 2));
   }
   for (int i = 0; i < nctu * 3; i++) {
     hp[o_t + i] = (uint8_t)params[i].type;
     memcpy(hp + o_o + (size_t)i * 32, params[i].offset, 32);
   }
-  cudaStream_t st = ctx->stream;
-  if (resident) CK(cudaMemcpyAsync(dp + o_t, hp + o_t, o_ry - o_t, cudaMemcpyHostToDevice, st));
-  else CK(cudaMemcpyAsync(dp, hp, o_ry, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp + o_t, hp + o_t, o_ry - o_t, cudaMemcpyHostToDevice, st));
   SaoApplyParams P{};
   P.src[0] = (const int16_t *)(dp + o_sy); P.src[1] = (const int16_t *)(dp + o_su); P.src[2] = (const int16_t *)(dp + o_sv);
   P.res[0] = (int16_t *)(dp + o_ry); P.res[1] = (int16_t *)(dp + o_ru); P.res[2] = (int16_t *)(dp + o_rv);
@@ -968,12 +993,9 @@ int hevcdl_sao_apply(hevcdl_ctx *ctx, const int16_t *sy, const int16_t *su, cons
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->evAux1, st));
   ctx->stats.kernel_launches++;
-  CK(cudaMemcpyAsync(hp + o_ry, dp + o_ry, total - o_ry, cudaMemcpyDeviceToHost, st));
+  CK(io.down(dp + o_ry, hp + o_ry, ry, rsy, W, H)); CK(io.down(dp + o_ru, hp + o_ru, ru, rsc, W / 2, H / 2)); CK(io.down(dp + o_rv, hp + o_rv, rv, rsc, W / 2, H / 2));
   CK(cudaStreamSynchronize(st));
-  auto unpack = [&](size_t off, int16_t *p, int stride, int w, int h) {
-    for (int r = 0; r < h; r++) memcpy(p + (size_t)r * stride, hp + off + (size_t)r * w * 2, (size_t)w * 2);
-  };
-  unpack(o_ry, ry, rsy, W, H); unpack(o_ru, ru, rsc, W / 2, H / 2); unpack(o_rv, rv, rsc, W / 2, H / 2);
+  io.finish();
   return HEVCDL_OK;
 }
 
@@ -1032,13 +1054,10 @@ int hevcdl_sao_stats(hevcdl_ctx *ctx, const int16_t *oy, const int16_t *ou, cons
   ctx->loopValid = false;                          // shares the in-loop entry points' grow-only scratch
   { const int rc = dbf_reserve(ctx, total, 0); if (rc) return rc; }
   uint8_t *hp = (uint8_t *)ctx->hDbf, *dp = (uint8_t *)ctx->dDbf;
-  auto pack = [&](size_t off, const int16_t *p, int stride, int w, int h) {
-    for (int r = 0; r < h; r++) memcpy(hp + off + (size_t)r * w * 2, p + (size_t)r * stride, (size_t)w * 2);
-  };
-  pack(o_oy, oy, osy, W, H); pack(o_ou, ou, osc, W / 2, H / 2); pack(o_ov, ov, osc, W / 2, H / 2);
-  pack(o_ry, ry, rsy, W, H); pack(o_ru, ru, rsc, W / 2, H / 2); pack(o_rv, rv, rsc, W / 2, H / 2);
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(dp, hp, o_out, cudaMemcpyHostToDevice, st));
+  PlaneIO io{st, {}};
+  CK(io.up(dp + o_oy, hp + o_oy, oy, osy, W, H)); CK(io.up(dp + o_ou, hp + o_ou, ou, osc, W / 2, H / 2)); CK(io.up(dp + o_ov, hp + o_ov, ov, osc, W / 2, H / 2));
+  CK(io.up(dp + o_ry, hp + o_ry, ry, rsy, W, H)); CK(io.up(dp + o_ru, hp + o_ru, ru, rsc, W / 2, H / 2)); CK(io.up(dp + o_rv, hp + o_rv, rv, rsc, W / 2, H / 2));
   SaoParams P{};
   P.org[0] = (const int16_t *)(dp + o_oy); P.org[1] = (const int16_t *)(dp + o_ou); P.org[2] = (const int16_t *)(dp + o_ov);
   P.src[0] = (const int16_t *)(dp + o_ry); P.src[1] = (const int16_t *)(dp + o_ru); P.src[2] = (const int16_t *)(dp + o_rv);
@@ -1132,6 +1151,21 @@ int hevcdl_tu_code_rdoq(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const hevc
 int hevcdl_tu_code(hevcdl_ctx *ctx, int n, const hevcdl_tu *tus, const int16_t *resi, size_t nelem, int32_t *coeff, int16_t *level,
                    int32_t *deq, int16_t *rec, uint32_t *abs_sum, uint64_t *ssd) {
   return hevcdl_tu_code_rdoq(ctx, n, tus, nullptr, nullptr, 0, resi, nelem, coeff, level, deq, rec, abs_sum, ssd);
+}
+
+int hevcdl_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return HEVCDL_E_INVAL;
+  if (host_is_pinned(p)) return HEVCDL_OK;
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return HEVCDL_E_CUDA; }
+  return HEVCDL_OK;
+}
+
+int hevcdl_host_unregister(void *p) {
+  if (!p) return HEVCDL_E_INVAL;
+  const cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return HEVCDL_E_CUDA; }
+  return HEVCDL_OK;
 }
 
 int hevcdl_last_aux_ms(hevcdl_ctx *ctx, float *ms) {

@@ -24,7 +24,7 @@ EXPORTS = [
     "hevcdl_create", "hevcdl_destroy", "hevcdl_last_error", "hevcdl_status_str",
     "hevcdl_submit_frame_u8", "hevcdl_submit_frame_pel16", "hevcdl_wait_frame", "hevcdl_ctu_labels",
     "hevcdl_frame_labels", "hevcdl_frame_pu_count", "hevcdl_frame_pus", "hevcdl_ctu_pu_range",
-    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_sao_apply", "hevcdl_inloop_frame", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free",
+    "hevcdl_frame_view_get", "hevcdl_release_frame", "hevcdl_rmd_exact", "hevcdl_tu_code", "hevcdl_tu_code_rdoq", "hevcdl_deblock_frame", "hevcdl_sao_stats", "hevcdl_sao_apply", "hevcdl_inloop_frame", "hevcdl_intra_pred", "hevcdl_get_stats", "hevcdl_numa_bind_thread", "hevcdl_host_alloc", "hevcdl_host_free", "hevcdl_host_register", "hevcdl_host_unregister",
 ]
 # include/hevcdl_internal.h: measurement and test hooks
 EXPORTS_INTERNAL = ["hevcdl_bench_resident", "hevcdl_bench_e2e", "hevcdl_debug_copy", "hevcdl_debug_rerun_rmd", "hevcdl_stream",
@@ -107,6 +107,8 @@ def load_library():
     L.hevcdl_host_free.argtypes = [vp]
     L.hevcdl_host_free.restype = None
     L.hevcdl_sao_stats.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
+    L.hevcdl_host_register.argtypes = [vp, C.c_size_t]
+    L.hevcdl_host_unregister.argtypes = [vp]
     L.hevcdl_inloop_frame.argtypes = [vp, vp, ip, vp, vp, ip, ip, ip, vp, vp, ip, ip, ip, ip, vp, vp, vp, ip, ip, vp]
     L.hevcdl_sao_apply.argtypes = [vp, vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, ip, vp]
     L.hevcdl_intra_pred.argtypes = [vp, ip, vp, vp, C.c_size_t, vp, C.c_size_t]

@@ -25,6 +25,7 @@
 
 hevcdl_ctx *hevcdl_hm_context();                                     // TEncCu_hevcdl.cpp: the encoder's session (NULL before the first CTU)
 void hevcdl_hm_count_dbf( bool onDevice );
+void hevcdl_hm_pin_picture( TComPicYuv *pic );                        // TEncCu_hevcdl.cpp
 HevcdlInloopCache g_hevcdl_inloop;                                   // inloop_cache.h
 void hevcdl_ref_loopFilterPic( TComLoopFilter *lf, TComPic *pcPic ); // ref_loopfilter_call.cpp
 
@@ -73,12 +74,14 @@ Void TComLoopFilter::loopFilterPic( TComPic* pcPic )
   // With HEVCDL_SAO=1 as well, and SAO enabled for the sequence, the statistics SAOProcess will ask for next are taken in the same
   // round trip (hevcdl_inloop_frame) and the deblocked picture stays on the device for the offset pass: TEncSAO_hevcdl.cpp and
   // TComSAO_hevcdl.cpp pick both up from g_hevcdl_inloop after checking that the picture they are handed is still this one.
+  hevcdl_hm_pin_picture( rec );
   static const bool fuse = getenv( "HEVCDL_SAO" ) && atoi( getenv( "HEVCDL_SAO" ) ) == 1 && !( getenv( "HEVCDL_INLOOP_FUSE" ) && atoi( getenv( "HEVCDL_INLOOP_FUSE" ) ) == 0 );
   g_hevcdl_inloop.valid = false;
   int rc;
   if ( fuse && sps->getUseSAO() )
   {
     TComPicYuv *org = pcPic->getPicYuvOrg();
+    hevcdl_hm_pin_picture( org );
     const size_t nst = (size_t)( ( W + 63 ) / 64 ) * ( ( H + 63 ) / 64 ) * 3 * 5 * 64;
     g_hevcdl_inloop.stats.resize( nst );
     rc = hevcdl_inloop_frame( ctx, rec->getAddr( COMPONENT_Y ), rec->getStride( COMPONENT_Y ), rec->getAddr( COMPONENT_Cb ),

@@ -23,6 +23,7 @@
 
 hevcdl_ctx *hevcdl_hm_context();                                     // TEncCu_hevcdl.cpp
 void hevcdl_hm_count_sao_apply( bool onDevice );
+void hevcdl_hm_pin_picture( TComPicYuv *pic );                        // TEncCu_hevcdl.cpp
 void hevcdl_hm_count_inloop_resident( bool resident );
 
 Void TComSampleAdaptiveOffset::offsetCTU( Int ctuRsAddr, TComPicYuv* srcYuv, TComPicYuv* resYuv, SAOBlkParam& saoblkParam, TComPic* pPic )
@@ -63,6 +64,8 @@ Void TComSampleAdaptiveOffset::offsetCTU( Int ctuRsAddr, TComPicYuv* srcYuv, TCo
   const bool resident = g_hevcdl_inloop.valid && g_hevcdl_inloop.W == m_picWidth && g_hevcdl_inloop.H == m_picHeight &&
                         hevcdl_inloop_guard( srcYuv ) == g_hevcdl_inloop.guard;
   g_hevcdl_inloop.valid = false;
+  hevcdl_hm_pin_picture( resYuv );
+  if ( !resident ) hevcdl_hm_pin_picture( srcYuv );
   const int rc = hevcdl_sao_apply( ctx, resident ? NULL : srcYuv->getAddr( COMPONENT_Y ), resident ? NULL : srcYuv->getAddr( COMPONENT_Cb ),
                                    resident ? NULL : srcYuv->getAddr( COMPONENT_Cr ),
                                    srcYuv->getStride( COMPONENT_Y ), srcYuv->getStride( COMPONENT_Cb ), resYuv->getAddr( COMPONENT_Y ),

@@ -43,6 +43,7 @@
 //                     TComSampleAdaptiveOffset::offsetCTU); the RD decision between them stays HM's: byte-identical bitstreams
 //                     With HEVCDL_DBF=1 as well the three passes share the picture on the device (hevcdl_inloop_frame: deblocking +
 //                     statistics in one round trip, offsets applied to the resident picture); HEVCDL_INLOOP_FUSE=0 keeps them separate
+//   HEVCDL_PIN        0 = do not page-lock HM's picture buffers (the in-loop calls then stage every plane through the library's buffer)
 //   HEVCDL_RMD        1 = run the batched 35-mode SATD pass on the B200 and let estIntraPredLumaQT's first pass take its
 //                     per-mode SATDs from it (hm_plugin/rmd_hook.h; references are ORIGINAL pixels, so mode
 //                     decisions follow the +-1 % BD-rate clause, not the bit-exact one);
@@ -249,6 +250,7 @@ struct HevcdlSession {
   unsigned long long exact_calls = 0;
   unsigned long long pred_device = 0, pred_host = 0; // intra-predicted blocks on the device / by the reference's own code
   unsigned long long sao_device = 0, sao_host = 0;
+  unsigned long long pinned_buffers = 0;           // HM picture buffers page-locked for direct copies (hevcdl_host_register)
   unsigned long long inloop_resident = 0;          // pictures whose SAO passes reused the deblocking call's round trip / resident picture
   unsigned long long saoapply_device = 0, saoapply_host = 0;   // pictures whose SAO offsets were applied on the device / by the reference   // SAO statistics passes on the device / by the reference's own code
   unsigned long long dbf_device = 0, dbf_host = 0;   // pictures deblocked on the device / by the reference's own filter
@@ -467,7 +469,8 @@ struct HevcdlSession {
         fprintf(stderr, "hevcdl: blocks predicted on the device %llu / by the reference's code %llu\n", pred_device, pred_host);
         fprintf(stderr, "hevcdl: SAO statistics passes on the device %llu / by the reference's code %llu\n", sao_device, sao_host);
         fprintf(stderr, "hevcdl: SAO offsets applied on the device for %llu pictures / by the reference's code for %llu\n", saoapply_device, saoapply_host);
-        fprintf(stderr, "hevcdl: in-loop passes of %llu pictures shared one upload (deblocked picture resident between deblocking and SAO)\n", inloop_resident);
+        fprintf(stderr, "hevcdl: in-loop passes of %llu pictures shared one upload (deblocked picture resident between deblocking and SAO); "
+                        "%llu of HM's picture buffers page-locked for direct copies\n", inloop_resident, pinned_buffers);
         fprintf(stderr, "hevcdl: lookahead %d: %llu frames were on the device before HM asked, %llu uploaded from HM's planes, %llu mismatches\n",
                 lookahead, la_hits, la_direct, la_mismatch);
         fprintf(stderr, "hevcdl: encoder thread blocked %.3f s for hevcdl_create (CUDA context + weights + buffers: %.3f s, started at program "
@@ -567,6 +570,25 @@ bool hevcdl_hm_rmd_satd( TComPrediction* pred, TComDataCU* pcCU, unsigned x0InCu
 
 hevcdl_ctx *hevcdl_hm_context() { return g_session.ctx; }
 void hevcdl_hm_count_pred( bool onDevice ) { ( onDevice ? g_session.pred_device : g_session.pred_host )++; }
+// Page-lock the three component buffers of one of HM's pictures (once per buffer; HM allocates its pictures once and reuses
+// them), so that the in-loop entry points copy straight between HM's strided planes and the device.  HEVCDL_PIN=0: off.
+void hevcdl_hm_pin_picture( TComPicYuv *pic )
+{
+  static const bool on = !( getenv( "HEVCDL_PIN" ) && atoi( getenv( "HEVCDL_PIN" ) ) == 0 );
+  static std::vector<const void *> done;
+  if ( !on || !pic ) return;
+  for ( int c = 0; c < 3; c++ )
+  {
+    const ComponentID id = ComponentID( c );
+    Pel *buf = pic->getBuf( id );
+    if ( !buf ) continue;
+    bool seen = false;
+    for ( const void *q : done ) seen = seen || q == buf;
+    if ( seen ) continue;
+    done.push_back( buf );
+    if ( hevcdl_host_register( buf, (size_t)pic->getStride( id ) * pic->getTotalHeight( id ) * sizeof( Pel ) ) == 0 ) g_session.pinned_buffers++;
+  }
+}
 void hevcdl_hm_count_inloop_resident( bool resident ) { if ( resident ) g_session.inloop_resident++; }
 void hevcdl_hm_count_sao_apply( bool onDevice ) { ( onDevice ? g_session.saoapply_device : g_session.saoapply_host )++; }
 void hevcdl_hm_count_sao( bool onDevice ) { ( onDevice ? g_session.sao_device : g_session.sao_host )++; }

@@ -18,6 +18,7 @@
 
 hevcdl_ctx *hevcdl_hm_context();                                     // TEncCu_hevcdl.cpp
 void hevcdl_hm_count_sao( bool onDevice );
+void hevcdl_hm_pin_picture( TComPicYuv *pic );                        // TEncCu_hevcdl.cpp
 
 Void TEncSampleAdaptiveOffset::getStatistics( SAOStatData*** blkStats, TComPicYuv* orgYuv, TComPicYuv* srcYuv, TComPic* pPic, Bool isCalculatePreDeblockSamples )
 {
@@ -42,6 +43,7 @@ Void TEncSampleAdaptiveOffset::getStatistics( SAOStatData*** blkStats, TComPicYu
   const bool cached = g_hevcdl_inloop.valid && g_hevcdl_inloop.W == m_picWidth && g_hevcdl_inloop.H == m_picHeight && g_hevcdl_inloop.org == orgYuv &&
                       g_hevcdl_inloop.stats.size() == st.size() && hevcdl_inloop_guard( srcYuv ) == g_hevcdl_inloop.guard;
   if ( cached ) st = g_hevcdl_inloop.stats;
+  if ( !cached ) { hevcdl_hm_pin_picture( orgYuv ); hevcdl_hm_pin_picture( srcYuv ); }
   const int rc = cached ? 0 : hevcdl_sao_stats( ctx, orgYuv->getAddr( COMPONENT_Y ), orgYuv->getAddr( COMPONENT_Cb ), orgYuv->getAddr( COMPONENT_Cr ),
                                    orgYuv->getStride( COMPONENT_Y ), orgYuv->getStride( COMPONENT_Cb ), srcYuv->getAddr( COMPONENT_Y ),
                                    srcYuv->getAddr( COMPONENT_Cb ), srcYuv->getAddr( COMPONENT_Cr ), srcYuv->getStride( COMPONENT_Y ),

@@ -281,6 +281,14 @@ int hevcdl_sao_apply(hevcdl_ctx *ctx, const int16_t *src_y, const int16_t *src_u
 void *hevcdl_host_alloc(size_t bytes, int write_combined);
 void hevcdl_host_free(void *p);
 
+/* Page-lock memory the caller already owns (cudaHostRegister), e.g. the encoder's picture buffers: the in-loop entry points
+ * (hevcdl_deblock_frame, hevcdl_inloop_frame, hevcdl_sao_stats, hevcdl_sao_apply) copy planes that lie in page-locked memory
+ * straight between the caller's strided rows and the device (no packing pass through the context's staging buffer), planes in
+ * ordinary memory through that buffer -- the results are the same.  Registering a range twice is not an error.  Unregister
+ * before freeing the memory.  HEVCDL_E_CUDA if the range cannot be locked (the calls above still work, through staging). */
+int hevcdl_host_register(void *p, size_t bytes);
+int hevcdl_host_unregister(void *p);
+
 /* Pin the calling thread to the CPUs of `device`'s NUMA node (what hevcdl_cfg.numa_bind does inside hevcdl_create),
  * for callers that allocate their own pinned frame buffers before creating a context.  Returns the node (>= 0), or a
  * negative hevcdl_status when the topology cannot be read (single-node hosts report node 0 or -1 in sysfs: no-op, 0). */

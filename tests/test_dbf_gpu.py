@@ -250,3 +250,28 @@ def test_fused_inloop_call_and_resident_offsets(dp, oracle, host):
     dp.sao_stats(org, rec)                                              # any other in-loop call drops it
     with pytest.raises(host.HevcdlError):
         dp.sao_apply(None, t, o, shape=(H, W))
+
+
+def test_page_locked_planes_take_the_direct_copy_path(dp, oracle, host):
+    """hevcdl_host_register: planes in page-locked memory are copied with their stride straight to / from the device, planes in
+    ordinary memory through the staging buffer -- mixed in one call here (Y page-locked with a row stride larger than the width,
+    chroma ordinary); results equal the oracle's either way."""
+    import ctypes as C
+    rng = np.random.default_rng(41)
+    W, H, S = 416, 240, 480                     # luma stride 480 > width
+    Yb = np.zeros((H, S), np.int16)
+    Yb[:, :W] = np.clip(np.kron(rng.integers(30, 226, (H // 8, W // 8)), np.ones((8, 8))) + rng.integers(-3, 4, (H, W)), 0, 255)
+    Yb[:, W:] = -77                              # must come back untouched
+    U = np.clip(np.kron(rng.integers(60, 196, (H // 16, W // 16)), np.ones((8, 8))) + rng.integers(-2, 3, (H // 2, W // 2)), 0, 255).astype(np.int16)
+    V = U[::-1, ::-1].copy()
+    tu = np.kron(rng.integers(2, 6, (H // 32 + 1, W // 32 + 1)), np.ones((8, 8), np.int64))[:H // 4, :W // 4].astype(np.uint8)
+    qp = np.full(tu.shape, 35, np.int8)
+    want = oracle.deblock_frame(Yb[:, :W], U, V, tu, qp)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    assert dp.lib.hevcdl_host_register(vp(Yb), Yb.nbytes) == 0
+    try:
+        rc = dp.lib.hevcdl_deblock_frame(dp.h, vp(Yb), S, vp(U), vp(V), W // 2, W, H, vp(np.ascontiguousarray(tu.ravel())), vp(np.ascontiguousarray(qp.ravel())), 0, 0, 0, 0)
+        assert rc == 0
+        assert (Yb[:, :W] == want[0]).all() and (Yb[:, W:] == -77).all() and (U == want[1]).all() and (V == want[2]).all()
+    finally:
+        assert dp.lib.hevcdl_host_unregister(vp(Yb)) == 0

@@ -150,12 +150,31 @@ def main():
                                     vp(orgp[0]), vp(orgp[1]), vp(orgp[2]), W, W // 2, vp(st_buf))
             lib.hevcdl_sao_apply(hctx, None, None, None, W, W // 2, vp(res[0]), vp(res[1]), vp(res[2]), W, W // 2, W, H8, vp(prm))
             return (time.perf_counter() - t0) * 1e3, [p.copy() for p in res], st_buf.copy()
-        ts, tf = [], []
+        # the same fused pair with every plane in page-locked memory (hevcdl_host_register, what hm_plugin does with HM's picture
+        # buffers): planes go straight between the caller's rows and the device, no packing pass
+        rp = [p.copy() for p in rec0]
+        resp = [np.zeros_like(p) for p in rec0]
+        pinned_ok = all(lib.hevcdl_host_register(vp(x), x.nbytes) == 0 for x in rp + resp + orgp)
+
+        def fused_pinned():
+            for dst, src0 in zip(rp, rec0):
+                np.copyto(dst, src0)
+            t0 = time.perf_counter()
+            lib.hevcdl_inloop_frame(hctx, vp(rp[0]), W, vp(rp[1]), vp(rp[2]), W // 2, W, H8, vp(tuf), vp(qpf), 0, 0, 0, 0,
+                                    vp(orgp[0]), vp(orgp[1]), vp(orgp[2]), W, W // 2, vp(st_buf))
+            lib.hevcdl_sao_apply(hctx, None, None, None, W, W // 2, vp(resp[0]), vp(resp[1]), vp(resp[2]), W, W // 2, W, H8, vp(prm))
+            return (time.perf_counter() - t0) * 1e3, [p.copy() for p in resp], st_buf.copy()
+        ts, tf, tp = [], [], []
         for _ in range(a.reps):
             ms, res_s, st_s = separate(); ts.append(ms)
             ms, res_f, st_f = fused(); tf.append(ms)
+            ms, res_p, st_p = fused_pinned(); tp.append(ms)
+        for x in rp + resp + orgp:
+            lib.hevcdl_host_unregister(vp(x))
         out["inloop_three_passes_c_abi"] = {"separate_calls_ms": med(ts[1:]), "fused_resident_ms": med(tf[1:]),
-                                            "identical": bool(all((x == y).all() for x, y in zip(res_s, res_f)) and (st_s == st_f).all()),
+                                            "fused_resident_page_locked_planes_ms": med(tp[1:]) if pinned_ok else None,
+                                            "identical": bool(all((x == y).all() for x, y in zip(res_s, res_f)) and (st_s == st_f).all() and
+                                                              all((x == y).all() for x, y in zip(res_s, res_p)) and (st_s == st_p).all()),
                                             "pcie_mb_separate": 37.4 * W * H8 / (1920 * 1080), "pcie_mb_fused": 25.0 * W * H8 / (1920 * 1080)}
         # ---- intra predictor: every 16x16 block of the luma picture x 35 modes -----------------------------
         nblk = (W // 16) * (H8 // 16)
