@@ -764,7 +764,10 @@ k_tc_conv3(FrameGeom geo, const uint8_t *__restrict__ blob, const uint8_t *__res
 template <int NT_, int NSTAGE_>
 struct FcCfg {
   static constexpr int NT = NT_, NSTAGE = NSTAGE_;
-  static constexpr int KPH = NT <= 32 ? 4 : (NT <= 64 ? 2 : 1);   // K-phases = independent accumulators per output tile
+  static constexpr int KPH = NT <= 32 ? 4 : 2;                    // K-phases = independent accumulators per output tile
+  // fc2's accumulators sit behind fc1's, or -- when fc1's 2 * KPH tiles fill the 512 columns (NT = 128) -- over them: fc1's
+  // are read out (and the CTA synchronised) before the first fc2 MMA is issued
+  static constexpr int FC2_COL = 3 * KPH * NT <= 512 ? 2 * KPH * NT : 0;
   static constexpr int STAGE = 32768 + NT * 128;                  // fc1 weights [256 x 64] + features [NT x 64], bf16
   static constexpr int BAR = NSTAGE * STAGE;
   static constexpr int FC2W = (BAR + 128 + 1023) / 1024 * 1024;   // fc2 weights, loaded in the prologue
@@ -774,12 +777,13 @@ struct FcCfg {
   static constexpr int H1 = 0 /* bf16 fc2 operand [NT/8][32][8][8] */, H2 = H1 + NT * 512 /* fp32 [NT][65] */,
                        LG = H2 + (NT * 65 * 4 + 15) / 16 * 16 /* fp32 [NT][16] */;
   static_assert(SMEM <= 227 * 1024, "K4 shared memory");
-  static_assert(3 * KPH * NT <= 512, "K4 tensor memory: 2*KPH fc1 + KPH fc2 accumulators");
+  static_assert(2 * KPH * NT <= 512, "K4 tensor memory: 2*KPH fc1 accumulators (+ KPH fc2 accumulators, behind or over them)");
   static_assert(LG + NT * 16 * 4 <= BAR, "K4 epilogue scratch must fit in the stage memory");
   static_assert(NSTAGE <= 6, "barrier slots");
 };
 using FcSmall = FcCfg<32, 4>;
 using FcLarge = FcCfg<64, 3>;
+using FcXL = FcCfg<128, 3>;
 
 template <class CFG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -812,7 +816,7 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
     mbar_init(bar_done, 1); mbar_init(bar_w2, 1); mbar_init(bar_done2, 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);   // fc1: 8 x FC_NT columns, fc2: 4 x FC_NT columns
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);   // fc1: 2 * KPH tiles of FC_NT columns, fc2: KPH tiles (FcCfg::FC2_COL)
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -904,7 +908,7 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
       const uint64_t da = smem_desc(sb + K4_FC2W, 128, 4096), db = smem_desc(sb + K4_H1, 128, 4096);
 #pragma unroll
       for (int t = 0; t < 16; t++)
-        mma_bf16_ss(tbase + (2 * FC_KPH + (t % FC_KPH)) * FC_NT, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t >= FC_KPH ? 1u : 0u);
+        mma_bf16_ss(tbase + CFG::FC2_COL + (t % FC_KPH) * FC_NT, da + (uint64_t)(t * 16), db + (uint64_t)(t * 16), idesc, t >= FC_KPH ? 1u : 0u);
       mma_commit(bar_done2);
     }
     __syncwarp();
@@ -920,10 +924,10 @@ k_tc_fc(FrameGeom geo, const FrameBatch fb, const uint8_t *__restrict__ blob, co
 #pragma unroll 1
       for (int cb = 0; cb < FC_NT; cb += 32) {
         float v[32], w[32];
-        tmem_ld32(tmem_addr(tbase, lq * 32, 2 * FC_KPH * FC_NT + cb), v);
+        tmem_ld32(tmem_addr(tbase, lq * 32, CFG::FC2_COL + cb), v);
 #pragma unroll
         for (int t = 1; t < FC_KPH; t++) {
-          tmem_ld32(tmem_addr(tbase, lq * 32, (2 * FC_KPH + t) * FC_NT + cb), w);
+          tmem_ld32(tmem_addr(tbase, lq * 32, CFG::FC2_COL + t * FC_NT + cb), w);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] += w[j];
@@ -1023,7 +1027,8 @@ inline int tc_configure(std::string &err) {
       cudaFuncSetAttribute(k_tc_conv2, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(k_tc_conv3, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(k_tc_fc<FcSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcSmall::SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(k_tc_fc<FcLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcLarge::SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(k_tc_fc<FcLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcLarge::SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_tc_fc<FcXL>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcXL::SMEM) != cudaSuccess) {
     err = std::string("tensor-core kernels: shared-memory attribute: ") + cudaGetErrorString(cudaGetLastError());
     return HEVCDL_E_CUDA;
   }
@@ -1054,7 +1059,10 @@ inline cudaError_t tc_launch(const TcParams &p, const FrameBatch &fb, const Tmap
   if ((e = tc_launch_pdl(k_tc_l1, grid, K1_THREADS, K1_SMEM, st, fb, tm, g, pitch, cpitch, p.blob, p.cat)) != cudaSuccess) return e;
   if ((e = tc_launch_pdl(k_tc_conv2, grid, K2_THREADS, K2_SMEM, st, gt, p.blob, (const uint8_t *)p.cat, p.a2)) != cudaSuccess) return e;
   if ((e = tc_launch_pdl(k_tc_conv3, grid, TC_THREADS, K3_SMEM, st, gt, p.blob, (const uint8_t *)p.a2, p.feats, npad)) != cudaSuccess) return e;
-  if (npad / FcSmall::NT > num_sms)             // more 32-sample tiles than SMs: 64-sample tiles halve the weight traffic
+  // every CTA streams fc1's 1 MB of weights: as few sample tiles as still fill one wave of SMs
+  if (npad / FcLarge::NT > num_sms)             // more 64-sample tiles than SMs (8-frame 1080p launches): 128-sample tiles
+    e = tc_launch_pdl(k_tc_fc<FcXL>, npad / FcXL::NT, TC_THREADS, FcXL::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
+  else if (npad / FcSmall::NT > num_sms)        // more 32-sample tiles than SMs: 64-sample tiles halve the weight traffic
     e = tc_launch_pdl(k_tc_fc<FcLarge>, npad / FcLarge::NT, TC_THREADS, FcLarge::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);
   else
     e = tc_launch_pdl(k_tc_fc<FcSmall>, npad / FcSmall::NT, TC_THREADS, FcSmall::SMEM, st, g, fb, p.blob, (const uint8_t *)p.feats, npad, boundary_fix);

@@ -208,6 +208,30 @@ def test_frame_view_is_the_same_bytes_as_the_copying_getters(built, host, pkg):
     dp2.release(0); dp.close(); dp2.close()
 
 
+def test_fc_sample_tile_sizes_give_the_same_results(built, host, pkg):
+    """The fc kernel picks its sample tile by launch size (cnn_tc.cuh: tc_launch): 1080p x 4 frames = 8160 samples runs 64-sample
+    tiles, x 8 frames = 16320 samples 128-sample tiles (fc2's accumulators over fc1's in tensor memory).  Both accumulate fc1 in
+    two K-phases in the same order, so labels, logits and everything derived from them must be bit-identical."""
+    w, h, n = 1920, 1080, 8
+    frames = [pkg.synth.synth_frame(w, h, 60 + i) for i in range(n)]
+    out = {}
+    for batch in (4, 8):
+        dp = _mk(host, w, h, 1, rmd=True, slots=n + 1, batch=batch)
+        for i, f in enumerate(frames):
+            dp.submit(i, *f)
+        res = []
+        for i in range(n):
+            v = dp.view(i)
+            res.append({k: v[k].copy() for k in ("labels", "logits", "pus", "satd", "cand")})
+            dp.release(i)
+        dp.close()
+        out[batch] = res
+    for i in range(n):
+        for k in out[4][i]:
+            assert (out[4][i][k] == out[8][i][k]).all(), (i, k)
+    assert len({r["labels"].tobytes() for r in out[8]}) == n          # eight different frames, not one frame eight times
+
+
 @pytest.mark.parametrize("batch,nframes", [(2, 5), (3, 5), (8, 10)])
 def test_batched_launches_give_the_same_results(built, host, pkg, batch, nframes):
     """cfg.batch > 1: several frames share one CNN launch.  Frames are independent, so every output must be bit-identical
