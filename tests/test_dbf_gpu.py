@@ -275,3 +275,30 @@ def test_page_locked_planes_take_the_direct_copy_path(dp, oracle, host):
         assert (Yb[:, :W] == want[0]).all() and (Yb[:, W:] == -77).all() and (U == want[1]).all() and (V == want[2]).all()
     finally:
         assert dp.lib.hevcdl_host_unregister(vp(Yb)) == 0
+
+
+def test_inloop_entry_points_reject_bad_arguments(dp, host):
+    """Sizes that are not multiples of 8, TU sizes / QPs / SAO types out of range, missing planes: HEVCDL_E_INVAL, nothing
+    launched, and the context keeps working afterwards."""
+    import ctypes as C
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    W, H = 64, 64
+    y, u, v = np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)
+    tu, qp = np.full(W * H // 16, 3, np.uint8), np.full(W * H // 16, 30, np.int8)
+    L = dp.lib
+    E_INVAL = L.hevcdl_deblock_frame(dp.h, vp(y), W, vp(u), vp(v), W // 2, 60, H, vp(tu), vp(qp), 0, 0, 0, 0)       # width not a multiple of 8
+    assert E_INVAL != 0
+    bad_tu = tu.copy(); bad_tu[5] = 6
+    assert L.hevcdl_deblock_frame(dp.h, vp(y), W, vp(u), vp(v), W // 2, W, H, vp(bad_tu), vp(qp), 0, 0, 0, 0) == E_INVAL
+    bad_qp = qp.copy(); bad_qp[7] = 52
+    assert L.hevcdl_deblock_frame(dp.h, vp(y), W, vp(u), vp(v), W // 2, W, H, vp(tu), vp(bad_qp), 0, 0, 0, 0) == E_INVAL
+    assert L.hevcdl_deblock_frame(dp.h, vp(y), W, vp(u), vp(v), W // 2, W, H, vp(tu), vp(qp), 7, 0, 0, 0) == E_INVAL    # beta offset out of range
+    assert L.hevcdl_deblock_frame(dp.h, vp(y), W - 8, vp(u), vp(v), W // 2, W, H, vp(tu), vp(qp), 0, 0, 0, 0) == E_INVAL  # stride < width
+    st = np.zeros((1, 3, 5, 2, 32), np.int64)
+    assert L.hevcdl_sao_stats(dp.h, vp(y), vp(u), None, W, W // 2, vp(y), vp(u), vp(v), W, W // 2, W, H, vp(st)) == E_INVAL
+    assert L.hevcdl_inloop_frame(dp.h, vp(y), W, vp(u), vp(v), W // 2, W, H, vp(tu), vp(qp), 0, 0, 0, 0, vp(y), vp(u), vp(v), W, W // 2, None) == E_INVAL
+    prm = np.zeros((1, 3), host.SAO_PARAM_DTYPE)
+    prm["type"] = 5
+    assert L.hevcdl_sao_apply(dp.h, vp(y), vp(u), vp(v), W, W // 2, vp(y.copy()), vp(u.copy()), vp(v.copy()), W, W // 2, W, H, vp(prm)) == E_INVAL
+    got = dp.deblock_frame(y, u, v, tu.reshape(H // 4, W // 4), qp.reshape(H // 4, W // 4))          # still alive
+    assert all((a == 0).all() for a in got)
