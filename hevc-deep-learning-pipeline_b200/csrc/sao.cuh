@@ -7,8 +7,8 @@
 //
 // Byte work bound by HBM: one block per (CTU, component) reads the CTU's samples of both pictures once (plus a one-sample
 // ring of the deblocked picture) into shared memory, every thread classifies its samples for all five types and adds into
-// shared-memory histograms (int32: at most 4096 samples x 255 per class), which are written out as the reference's int64
-// arrays.  What a CTU counts excludes the columns / rows its right / lower neighbours have not deblocked yet (5 / 4 luma,
+// per-warp shared-memory histograms (one packed word per class: count << 20 + sum of differences), which are unpacked, summed
+// and written out as the reference's int64 arrays.  What a CTU counts excludes the columns / rows its right / lower neighbours have not deblocked yet (5 / 4 luma,
 // 3 / 2 chroma) and, for the edge types, samples whose neighbour lies outside the picture.
 #pragma once
 #include "common.cuh"
@@ -24,7 +24,7 @@ struct SaoParams {
 __global__ void __launch_bounds__(256)
 k_sao_stats(const SaoParams P) {
   __shared__ int16_t s_src[66][66];                          // the CTU's deblocked samples with a one-sample ring
-  __shared__ int s_hist[8][5][2][32];                        // one histogram per warp: the edge types have only five classes
+  __shared__ int s_hist[8][5][32];                           // per warp, type and class: count << 20 + sum of differences
   const int a = blockIdx.x / 3, c = blockIdx.x - 3 * a;
   const int xp = (a % P.ctu_w) * 64, yp = (a / P.ctu_w) * 64;
   const int hl = yp + 64 > P.H ? P.H - yp : 64, wl = xp + 64 > P.W ? P.W - xp : 64;
@@ -32,12 +32,27 @@ k_sao_stats(const SaoParams P) {
   const int sh = c ? 1 : 0, stride = P.W >> sh, pw = P.W >> sh, ph = P.H >> sh, width = wl >> sh, height = hl >> sh;
   const int x0p = xp >> sh, y0p = yp >> sh;
   const int16_t *__restrict__ src = P.src[c], *__restrict__ org = P.org[c];
-  for (int i = threadIdx.x; i < 8 * 5 * 2 * 32; i += blockDim.x) (&s_hist[0][0][0][0])[i] = 0;
-  int (*hist)[2][32] = s_hist[threadIdx.x >> 5];
-  for (int i = threadIdx.x; i < (height + 2) * (width + 2); i += blockDim.x) {
-    const int ly = i / (width + 2), lx = i - ly * (width + 2);
-    const int gy = y0p + ly - 1, gx = x0p + lx - 1;
-    s_src[ly][lx] = (gy >= 0 && gy < ph && gx >= 0 && gx < pw) ? src[(size_t)gy * stride + gx] : (int16_t)0;   // ring samples outside the picture are never used
+  for (int i = threadIdx.x; i < 8 * 5 * 32; i += blockDim.x) (&s_hist[0][0][0])[i] = 0;
+  int (*hist)[32] = s_hist[threadIdx.x >> 5];
+  {
+    // one warp per row, a lane per column: every load of the thread (<= 9 rows x 3 column steps) is issued before the first
+    // store, so the block pays one global-memory latency for its tile instead of one per row
+    int16_t t[9][3];
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int ly = (threadIdx.x >> 5) + 8 * k, lx = (threadIdx.x & 31) + 32 * j;
+        const int gy = y0p + ly - 1, gx = x0p + lx - 1;
+        t[k][j] = (ly < height + 2 && lx < width + 2 && gy >= 0 && gy < ph && gx >= 0 && gx < pw) ? src[(size_t)gy * stride + gx] : (int16_t)0;   // ring samples outside the picture are never used
+      }
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int ly = (threadIdx.x >> 5) + 8 * k, lx = (threadIdx.x & 31) + 32 * j;
+        if (ly < height + 2 && lx < width + 2) s_src[ly][lx] = t[k][j];
+      }
   }
   __syncthreads();
   const int skip_r = c ? 3 : 5, skip_b = c ? 2 : 4;
@@ -45,29 +60,47 @@ k_sao_stats(const SaoParams P) {
   const int ex0 = left ? 0 : 1, ex1 = right ? width - skip_r : width - 1;          // types that look left / right
   const int fx1 = right ? width - skip_r : width;                                   // types that do not (EO 90, BO)
   const int ey1 = below ? height - skip_b : height - 1, fy1 = below ? height - skip_b : height;
-  for (int i = threadIdx.x; i < height * width; i += blockDim.x) {
-    const int y = i / width, x = i - y * width;
-    const int v = s_src[y + 1][x + 1];
-    const int d = (int)org[(size_t)(y0p + y) * stride + x0p + x] - v;
-    auto sgn = [](int t) { return (t > 0) - (t < 0); };
-    auto add = [&](int t, int cls) { atomicAdd(&hist[t][0][cls], d); atomicAdd(&hist[t][1][cls], 1); };
-    if (x >= ex0 && x < ex1 && y < fy1) add(0, 2 + sgn(v - s_src[y + 1][x]) + sgn(v - s_src[y + 1][x + 2]));
-    if (x < fx1 && y >= (above ? 0 : 1) && y < ey1) add(1, 2 + sgn(v - s_src[y][x + 1]) + sgn(v - s_src[y + 2][x + 1]));
-    if (y < ey1) {
-      const bool in135 = y == 0 ? (x >= ((left && above) ? 0 : 1) && x < (above ? ex1 : 1)) : (x >= ex0 && x < ex1);
-      if (in135) add(2, 2 + sgn(v - s_src[y][x]) + sgn(v - s_src[y + 2][x + 2]));
-      const bool in45 = y == 0 ? (above && x >= ex0 && x < ex1) : (x >= ex0 && x < ex1);
-      if (in45) add(3, 2 + sgn(v - s_src[y][x + 2]) + sgn(v - s_src[y + 2][x]));
+  // a thread owns one column and every `bands`-th row; a warp's (count, sum) of a class is ONE word -- count << 20 + sum,
+  // |sum| <= 512 samples x 255 < 2^19 -- so a sample costs one shared-memory atomic per type
+  const int cols = width > 32 ? 64 : 32, bands = 256 / cols;
+  const int x = threadIdx.x % cols;
+  const bool inx = x >= ex0 && x < ex1;
+  int16_t og[16];                               // the thread's original samples (<= 16 rows), loaded ahead of the loop
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int y = threadIdx.x / cols + bands * k;
+    og[k] = (x < width && y < height) ? org[(size_t)(y0p + y) * stride + x0p + x] : (int16_t)0;
+  }
+  if (x < width) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int y = threadIdx.x / cols + bands * k;
+      if (y >= height) break;
+      const int v = s_src[y + 1][x + 1];
+      const int w = (1 << 20) + (int)og[k] - v;
+      auto sgn = [&](int ly, int lx) { const int n = s_src[ly][lx]; return (v > n) - (v < n); };
+      if (inx && y < fy1) atomicAdd(&hist[0][2 + sgn(y + 1, x) + sgn(y + 1, x + 2)], w);
+      if (y < ey1) {
+        if (x < fx1 && y >= (above ? 0 : 1)) atomicAdd(&hist[1][2 + sgn(y, x + 1) + sgn(y + 2, x + 1)], w);
+        const bool in135 = y == 0 ? (x >= ((left && above) ? 0 : 1) && x < (above ? ex1 : 1)) : inx;
+        if (in135) atomicAdd(&hist[2][2 + sgn(y, x) + sgn(y + 2, x + 2)], w);
+        const bool in45 = y == 0 ? (above && inx) : inx;
+        if (in45) atomicAdd(&hist[3][2 + sgn(y, x + 2) + sgn(y + 2, x)], w);
+      }
+      if (x < fx1 && y < fy1) atomicAdd(&hist[4][v >> 3], w);
     }
-    if (x < fx1 && y < fy1) add(4, v >> 3);
   }
   __syncthreads();
   long long *o = P.out + ((size_t)a * 3 + c) * 5 * 64;
   for (int i = threadIdx.x; i < 5 * 2 * 32; i += blockDim.x) {
-    long long t = 0;
+    const int t = i >> 6, which = (i >> 5) & 1, k = i & 31;
+    long long r = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) t += (&s_hist[w][0][0][0])[i];
-    o[i] = t;
+    for (int wq = 0; wq < 8; wq++) {
+      const int word = s_hist[wq][t][k], n = (word + (1 << 19)) >> 20;
+      r += which ? n : word - (n << 20);
+    }
+    o[i] = r;
   }
 }
 
@@ -101,9 +134,21 @@ k_sao_apply(const SaoApplyParams P) {
   const bool L = xp > 0, A = yp > 0, R = xp + 64 < P.W, B = yp + 64 < P.H, AL = L && A, AR = A && R, BL = B && L, BR = B && R;
   const int sx = L ? 0 : 1, ex = R ? width : width - 1;
   const int dx = t == 1 ? 0 : (t == 3 ? -1 : 1), dy = t == 0 ? 0 : 1;   // second neighbour at (+dx, +dy), first at (-dx, -dy)
-  // one warp per row, a lane per column (two for 64-wide luma rows): the row's valid range is decided once per row
-  for (int y = threadIdx.x >> 5; y < height; y += 8) {
-    int xa = 0, xb = 0;                           // t < 0: nothing is offset
+  // one warp per row, a lane per column (two for 64-wide luma rows); the thread's centre samples (<= 8 rows x 2 column steps)
+  // are all loaded before the first one is used, so the row loop does not pay one global-memory latency per row
+  int16_t cv[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int y = (threadIdx.x >> 5) + 8 * k, x = (threadIdx.x & 31) + 32 * j;
+      cv[k][j] = (y < height && x < width) ? s[(size_t)y * stride + x] : (int16_t)0;
+    }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int y = (threadIdx.x >> 5) + 8 * k;
+    if (y >= height) break;
+    int xa = 0, xb = 0;                           // t < 0: nothing is offset; the row's valid range is decided once
     if (t == 4) { xb = width; }
     else if (t == 0) { xa = sx; xb = ex; }
     else if (t == 1) { xb = (y < (A ? 0 : 1) || y >= (B ? height : height - 1)) ? 0 : width; }
@@ -117,8 +162,11 @@ k_sao_apply(const SaoApplyParams P) {
       else { xa = sx; xb = ex; }
     }
     const int16_t *__restrict__ row = s + (size_t)y * stride;
-    for (int x = threadIdx.x & 31; x < width; x += 32) {
-      const int v = row[x];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int x = (threadIdx.x & 31) + 32 * j;
+      if (x >= width) break;
+      const int v = cv[k][j];
       int out = v;
       if (x >= xa && x < xb) {
         int cls;
